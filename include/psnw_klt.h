@@ -1,0 +1,194 @@
+/*
+ * psnw_klt.h -- C ABI of the B200-native KLT hot path of PSN_Where's 2D tracker.
+ *
+ * Drop-in boundary.  The reference has no FFI layer; the numeric callees of
+ * CPSNWhere_Tracker2D::Run (psn_where/PSNWhere_Tracker2D.h:140, .cpp:251-373) are replaced one-for-one:
+ *
+ *   reference callee                                             call site (Tracker2D.cpp)   export
+ *   cv::cvtColor + cv::resize into m_vecPtGrayFrameBuffer        :256-263, ring :70,:311-316  psnw_push_frame(s)
+ *   cv::FeatureDetector::detect(img, keypoints, mask)            :741 (mask :735-742)         psnw_klt_detect
+ *   cv::calcOpticalFlowPyrLK(prev,next,pts,out,status,err,win)   :776-782, :871-877           psnw_klt_track(_batch)
+ *   LocalSearchKLT(box, pre, cur, inlierIdx)                     :452-554 (callers :787,:893) psnw_box_update
+ *   Initialize / Finalize                                        :99-163 / :176-237           psnw_create / psnw_destroy
+ *
+ * Conventions: extern "C", POD arguments only, every call returns 0 or a negative PSNW_E* code, never
+ * throws, never exits.  A context owns one GPU's shard of the camera rig: n_cameras cameras, each with
+ * a ring of `ring_slots` frames kept on the device as Gaussian pyramid + Scharr derivatives.  Calls on
+ * one context are serialised by the caller (as Tracker2D instances are); different
+ * contexts may be driven from different host threads or processes (one per GPU).
+ *
+ * Memory flags select how caller pointers are interpreted:
+ *   PSNW_MEM_HOST    pageable or pinned host memory; the call returns with outputs written (synchronous,
+ *                    like the OpenCV calls it replaces).
+ *   PSNW_MEM_PINNED  page-locked host memory; copies are enqueued on the context stream and the call
+ *                    returns immediately -- psnw_sync() before reading outputs or reusing inputs.
+ *   PSNW_MEM_DEVICE  device pointers; nothing is copied, everything is enqueued (track -> box_update ->
+ *                    track chains stay on the GPU).
+ * There is no CPU fallback: without a CUDA device psnw_create fails with PSNW_ECUDA.
+ */
+#ifndef PSNW_KLT_H_
+#define PSNW_KLT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PSNW_API __attribute__((visibility("default")))
+#else
+#define PSNW_API
+#endif
+
+#define PSNW_VERSION 100
+
+enum {
+    PSNW_OK = 0,
+    PSNW_EARG = -1,   /* bad argument */
+    PSNW_ECUDA = -2,  /* CUDA runtime / driver failure (psnw_last_error has the text) */
+    PSNW_ENOMEM = -3, /* allocation failed or a capacity given at create time was exceeded */
+    PSNW_ESTATE = -4  /* call not valid in this state (e.g. slot not filled yet) */
+};
+
+enum { PSNW_MEM_HOST = 0, PSNW_MEM_PINNED = 1, PSNW_MEM_DEVICE = 2 };
+
+/* psnw_box_update estimators */
+enum {
+    PSNW_BOX_REFERENCE = 0 /* LocalSearchKLT semantics, Tracker2D.cpp:452-554 (parity-graded) */
+};
+
+#define PSNW_MAX_LEVELS 8
+#define PSNW_MAX_PTS_PER_TARGET 4096
+
+typedef struct psnw_ctx psnw_ctx;
+
+typedef struct psnw_params {
+    int device;           /* CUDA ordinal */
+    int n_cameras;        /* cameras owned by this context */
+    int width, height;    /* frame size (camera model W x H, Tracker2D.cpp:118-119) */
+    int levels;           /* pyramid levels built per frame = maxLevel + 1; OpenCV default 4 */
+    int ring_slots;       /* frames kept per camera; 4 == PSN_2D_BACKTRACKING_INTERVAL (Tracker2D.cpp:16) */
+    int win_w, win_h;     /* default LK window when no per-target window is given (21 x 21) */
+    int max_iters;        /* 30  (OpenCV default TermCriteria) */
+    double epsilon;       /* 0.01 (double, like cv::TermCriteria::epsilon) */
+    float min_eig_thresh; /* 1e-4 */
+    float fb_thresh;      /* forward-backward gate in px; < 0: single direction only (no backward pass) */
+    int max_points;       /* capacity of one klt_track(_batch) call, all jobs together */
+    int max_targets;      /* capacity of one klt_track(_batch) / box_update / detect call */
+    void *stream;         /* cudaStream_t to enqueue on; NULL: the context creates its own */
+} psnw_params;
+
+/* Fills *p with the reference-faithful defaults (4 levels, 21x21, 30 it, 0.01, 1e-4, fb 1.0, 4 slots). */
+PSNW_API int psnw_default_params(psnw_params *p);
+
+PSNW_API int psnw_create(psnw_ctx **out, const psnw_params *p);   /* Tracker2D::Initialize, .cpp:99-163 */
+PSNW_API int psnw_destroy(psnw_ctx *ctx);                         /* Tracker2D::Finalize,   .cpp:176-237 */
+
+/*
+ * Frame intake (replaces .cpp:256-263 + ring rotation :311-316).  `gray` is 8-bit single channel,
+ * `pitch` bytes per row.  The frame goes into the camera's next ring slot; its pyramid (pyrDown) and
+ * Scharr derivatives of every level are built once, on the device.  After the call slot 0 is this
+ * frame, slot 1 the previous one, ... (slot k == *(m_vecPtGrayFrameBuffer.rbegin() + k)).
+ */
+PSNW_API int psnw_push_frame(psnw_ctx *ctx, int cam, const uint8_t *gray, size_t pitch,
+                             uint32_t frame_idx, int mem_flags);
+/* Same for several cameras at once (one batched launch per level; CPSNWhere::TrackPeople's camera loop,
+ * psn_where/PSNWhere.cpp:257-266). cams[i] must be distinct. */
+PSNW_API int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const *grays,
+                              size_t pitch, uint32_t frame_idx, int mem_flags);
+/* BGR (8UC3, cv::imread layout) intake: cvtColor(BGR2GRAY) of .cpp:257 fused into the upload.
+ * luma_bits 14 = OpenCV 2.4.6 rounding, 15 = OpenCV 4.x. */
+PSNW_API int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const *bgr,
+                                  size_t pitch, uint32_t frame_idx, int luma_bits, int mem_flags);
+
+/* Number of frames currently held for `cam` (0..ring_slots). */
+PSNW_API int psnw_frames_held(psnw_ctx *ctx, int cam);
+
+/*
+ * Feature detection inside detection boxes (replaces m_detector->detect + mask, .cpp:735-757).
+ * Shi-Tomasi min-eigenvalue corners (north_star) == cv::goodFeaturesToTrack(img, max_per_target, quality,
+ * min_dist, mask = box cropped like PSN_Rect::cropWithSize, blockSize 3).  boxes: PSN_Rect layout
+ * {x,y,w,h} doubles (PSNWhere_Types.h:112-122).  pts_xy: [n_targets][max_per_target][2] floats, strongest
+ * first; counts[n_targets].
+ */
+PSNW_API int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n_targets,
+                             int max_per_target, float quality, float min_dist,
+                             float *pts_xy, int *counts, int mem_flags);
+
+/*
+ * Sparse pyramidal LK from ring slot `slot_from` to `slot_to` of camera `cam` (replaces
+ * cv::calcOpticalFlowPyrLK at .cpp:776-782 [slot_from = newer frame] and :871-877 [slot_from = 1, slot_to = 0]).
+ *   pts_xy[n_pts][2]      seed points in slot_from
+ *   target_of_pt[n_pts]   target index of each point, or NULL (all points use target 0 / the default window)
+ *   win_wh[n_targets][2]  per-target window (reference: (int)box.w x (int)box.w backward, x (int)box.h forward),
+ *                         or NULL for the context default
+ *   out_xy, status, err   as calcOpticalFlowPyrLK's nextPts / status / err (err = 0 where status = 0)
+ *   fb_err                if the context was created with fb_thresh >= 0 the kernel also runs the backward
+ *                         pass out_xy -> p'' and sets status = st_f & st_b & (|p - p''| <= fb_thresh),
+ *                         fb_err = |p - p''| (may be NULL to drop it).  With fb_thresh < 0 it is ignored.
+ * Pyramid levels are truncated per window exactly like buildOpticalFlowPyramid (level kept while both
+ * dimensions stay > window).
+ */
+PSNW_API int psnw_klt_track(psnw_ctx *ctx, int cam, int slot_from, int slot_to,
+                            const float *pts_xy, const int *target_of_pt, int n_pts,
+                            const int *win_wh, int n_targets,
+                            float *out_xy, uint8_t *status, float *err, float *fb_err, int mem_flags);
+
+typedef struct psnw_track_job {
+    int cam, slot_from, slot_to;
+    int n_pts;
+    const float *pts_xy;
+    const int *target_of_pt; /* may be NULL */
+    int n_targets;           /* >= 1 */
+    const int *win_wh;       /* [n_targets][2] or NULL */
+    float *out_xy;
+    uint8_t *status;
+    float *err;
+    float *fb_err;           /* may be NULL */
+} psnw_track_job;
+
+/* Several psnw_klt_track calls (any cameras / slot pairs) as ONE upload, ONE launch, ONE download. */
+PSNW_API int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, int mem_flags);
+
+/*
+ * Per-target box motion (replaces LocalSearchKLT, .cpp:452-554; callers :787 and :893).
+ *   boxes_in[n_targets][4]       PSN_Rect {x,y,w,h}
+ *   pre_xy, cur_xy               all targets' points, CSR by target_offsets[n_targets + 1]
+ *   status                       NULL: every point takes part (backward caller, :787); else only points with
+ *                                status != 0 (forward caller's filter, :883-888, or the previous step's inliers)
+ *   boxes_out[n_targets][4]      translated box (w,h unchanged)
+ *   inlier_mask[n_points]        1 for the points LocalSearchKLT lists in inlierFeatureIndex
+ *   inlier_counts[n_targets]
+ */
+PSNW_API int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets,
+                             const float *pre_xy, const float *cur_xy, const uint8_t *status,
+                             const int *target_offsets, int mode,
+                             double *boxes_out, uint8_t *inlier_mask, int *inlier_counts, int mem_flags);
+
+PSNW_API int psnw_sync(psnw_ctx *ctx);
+PSNW_API const char *psnw_last_error(psnw_ctx *ctx);
+PSNW_API void *psnw_get_stream(psnw_ctx *ctx);
+
+/* --- inspection (tests, bench) ---------------------------------------------------------------- */
+/* Geometry of pyramid level `level`: width, height, u8 row pitch in bytes (dxy pitch = 4 * that). */
+PSNW_API int psnw_level_info(psnw_ctx *ctx, int level, int *w, int *h, int *pitch);
+/* Copies one level of (cam, slot) to host: img_out[h][w] u8 and/or dxy_out[h][w][2] int16 (NULL to skip). */
+PSNW_API int psnw_read_level(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *img_out, int16_t *dxy_out);
+/* Copies the Shi-Tomasi min-eigenvalue map of (cam, slot) level 0 to host float[h][w] (computes it if needed). */
+PSNW_API int psnw_read_min_eig(psnw_ctx *ctx, int cam, int slot, float *eig_out);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+PSNW_API uint64_t psnw_launch_count(psnw_ctx *ctx);
+/* Algorithmic bytes one psnw_push_frame moves: N*(6*S_L - 1), SURVEY.md section 8d. */
+PSNW_API uint64_t psnw_push_frame_bytes(psnw_ctx *ctx);
+/* Re-runs the pyramid + Scharr build of the frames already in slot 0 of `cams` (no copy): lets bench.py time
+ * the HBM-bound kernels alone with CUDA events on the context stream. */
+PSNW_API int psnw_rebuild_pyramids(psnw_ctx *ctx, int n, const int *cams);
+/* Levels actually built (levels whose smaller side would drop under 8 px are skipped). */
+PSNW_API int psnw_levels_built(psnw_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSNW_KLT_H_ */

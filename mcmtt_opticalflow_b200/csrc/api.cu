@@ -1,0 +1,703 @@
+// Host shim behind the C ABI of include/psnw_klt.h: context (= one GPU's shard of cameras), device ring of
+// pyramids, staging, and the launch sequences.  No tracking arithmetic happens on the host; without a CUDA
+// device every entry point fails with PSNW_ECUDA (there is no CPU fallback).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace psnw;
+
+namespace {
+
+struct DevBuf {
+    char *p = nullptr;
+    size_t cap = 0;
+};
+
+struct StageSlot {
+    char *h = nullptr;       // pinned
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+    bool pending = false;
+};
+
+constexpr int kStageSlots = 4;
+
+}  // namespace
+
+struct psnw_ctx {
+    psnw_params p;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    PyrDesc pyr;
+    CUtensorMap maps[PSNW_MAX_LEVELS];
+    int planes = 0;
+    std::vector<int> head, held;
+    std::vector<uint64_t> plane_seq;     // push counter per plane (min-eig cache tag)
+    uint64_t seq = 0;
+    DevBuf arena;                         // per-call device scratch (stream ordered)
+    size_t arena_off = 0;
+    DevBuf desc;                          // job / group / target descriptors
+    DevBuf cand;                          // detect candidate scratch
+    DevBuf bgr;                           // BGR staging for psnw_push_frames_bgr
+    std::vector<float *> eig;             // per camera min-eig map (level-0 pitch), lazily allocated
+    std::vector<uint64_t> eig_tag;
+    StageSlot stage[kStageSlots];
+    int stage_next = 0;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(psnw_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CK(call)                                                            \
+    do {                                                                    \
+        cudaError_t e_ = (call);                                            \
+        if (e_ != cudaSuccess) return fail(ctx, PSNW_ECUDA, #call, e_);     \
+    } while (0)
+
+int ensure(psnw_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return PSNW_OK;
+    if (b.p) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+    }
+    const size_t want = std::max(bytes, (size_t)1 << 16);
+    if (cudaMalloc(&b.p, want) != cudaSuccess) return fail(ctx, PSNW_ENOMEM, "cudaMalloc scratch", cudaGetLastError());
+    b.cap = want;
+    return PSNW_OK;
+}
+
+template <typename T>
+T *take(psnw_ctx *ctx, size_t n)
+{
+    const size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    T *r = reinterpret_cast<T *>(ctx->arena.p + ctx->arena_off);
+    ctx->arena_off += bytes;
+    return r;
+}
+
+// pinned staging slot for small descriptor uploads; waits for the previous upload from the same slot
+int stage_acquire(psnw_ctx *ctx, size_t bytes, StageSlot **out)
+{
+    StageSlot &s = ctx->stage[ctx->stage_next];
+    ctx->stage_next = (ctx->stage_next + 1) % kStageSlots;
+    if (s.pending) { CK(cudaEventSynchronize(s.ev)); s.pending = false; }
+    if (bytes > s.cap) {
+        if (s.h) CK(cudaFreeHost(s.h));
+        s.h = nullptr; s.cap = 0;
+        const size_t want = std::max(bytes, (size_t)1 << 14);
+        if (cudaMallocHost(&s.h, want) != cudaSuccess) return fail(ctx, PSNW_ENOMEM, "cudaMallocHost", cudaGetLastError());
+        s.cap = want;
+    }
+    if (!s.ev) CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    *out = &s;
+    return PSNW_OK;
+}
+
+int stage_upload(psnw_ctx *ctx, StageSlot *s, void *dst, size_t bytes)
+{
+    CK(cudaMemcpyAsync(dst, s->h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(s->ev, ctx->stream));
+    s->pending = true;
+    return PSNW_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_maps(psnw_ctx *ctx)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, PSNW_ECUDA, "cuTensorMapEncodeTiled not available");
+    EncodeTiledFn encode = reinterpret_cast<EncodeTiledFn>(fn);
+    for (int l = 0; l < ctx->pyr.levels; ++l) {
+        const LevelGeom &g = ctx->pyr.lv[l];
+        const cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)ctx->planes};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.plane_px};
+        const cuuint32_t box[3] = {(cuuint32_t)kBoxW, (cuuint32_t)kBoxH, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode(&ctx->maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            char msg[96];
+            snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(level %d) -> CUresult %d", l, (int)r);
+            return fail(ctx, PSNW_ECUDA, msg);
+        }
+    }
+    return PSNW_OK;
+}
+
+inline int plane_of(const psnw_ctx *c, int cam, int slot)
+{
+    const int S = c->p.ring_slots;
+    return cam * S + ((c->head[cam] - slot) % S + S) % S;
+}
+
+bool slot_ok(const psnw_ctx *c, int cam, int slot)
+{
+    return cam >= 0 && cam < c->p.n_cameras && slot >= 0 && slot < c->held[cam];
+}
+
+// buildOpticalFlowPyramid's truncation: a level is kept while both dimensions stay > window
+int effective_max_level(const psnw_ctx *c, int win_w, int win_h)
+{
+    int level = 0;
+    while (level + 1 < c->pyr.levels) {
+        const LevelGeom &n = c->pyr.lv[level + 1];
+        if (n.w <= win_w || n.h <= win_h) break;
+        ++level;
+    }
+    return level;
+}
+
+cudaMemcpyKind h2d(int mem_flags) { return mem_flags == PSNW_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
+
+int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes)
+{
+    for (size_t b = 0; b < planes.size(); b += 63) {
+        PlaneList pl;
+        pl.n = (int)std::min<size_t>(63, planes.size() - b);
+        for (int i = 0; i < pl.n; ++i) pl.plane[i] = planes[b + i];
+        for (int l = 0; l < ctx->pyr.levels; ++l) {
+            const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, ctx->stream);
+            if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_scharr_kernel launch", cudaGetLastError());
+            ctx->launches += r;
+        }
+    }
+    return PSNW_OK;
+}
+
+int advance_ring(psnw_ctx *ctx, int n, const int *cams, std::vector<int> &planes)
+{
+    for (int i = 0; i < n; ++i) {
+        const int cam = cams[i];
+        if (cam < 0 || cam >= ctx->p.n_cameras) return fail(ctx, PSNW_EARG, "camera index out of range");
+        for (int j = 0; j < i; ++j)
+            if (cams[j] == cam) return fail(ctx, PSNW_EARG, "duplicate camera in psnw_push_frames");
+    }
+    planes.resize(n);
+    for (int i = 0; i < n; ++i) {
+        const int cam = cams[i];
+        ctx->head[cam] = (ctx->head[cam] + 1) % ctx->p.ring_slots;
+        ctx->held[cam] = std::min(ctx->held[cam] + 1, ctx->p.ring_slots);
+        planes[i] = plane_of(ctx, cam, 0);
+        ctx->plane_seq[planes[i]] = ++ctx->seq;
+    }
+    return PSNW_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int psnw_default_params(psnw_params *p)
+{
+    if (!p) return PSNW_EARG;
+    memset(p, 0, sizeof *p);
+    p->device = 0;
+    p->n_cameras = 1;
+    p->width = 768; p->height = 576;
+    p->levels = 4;
+    p->ring_slots = 4;
+    p->win_w = 21; p->win_h = 21;
+    p->max_iters = 30;
+    p->epsilon = 0.01;
+    p->min_eig_thresh = 1e-4f;
+    p->fb_thresh = 1.0f;
+    p->max_points = 1 << 16;
+    p->max_targets = 1 << 12;
+    p->stream = nullptr;
+    return PSNW_OK;
+}
+
+int psnw_create(psnw_ctx **out, const psnw_params *p)
+{
+    if (!out || !p) return PSNW_EARG;
+    *out = nullptr;
+    if (p->n_cameras < 1 || p->width < 16 || p->height < 16 || p->levels < 1 || p->levels > PSNW_MAX_LEVELS ||
+        p->ring_slots < 1 || p->win_w < 1 || p->win_h < 1 || p->max_iters < 0 || p->max_points < 1 || p->max_targets < 1)
+        return PSNW_EARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || p->device < 0 || p->device >= ndev) return PSNW_ECUDA;
+    if (cudaSetDevice(p->device) != cudaSuccess) return PSNW_ECUDA;
+
+    psnw_ctx *ctx = new psnw_ctx();
+    ctx->p = *p;
+    ctx->p.max_iters = std::min(std::max(p->max_iters, 0), 100);                 // calcOpticalFlowPyrLK clamps
+    ctx->p.epsilon = std::min(std::max(p->epsilon, 0.0), 10.0);
+    ctx->planes = p->n_cameras * p->ring_slots;
+    ctx->head.assign(p->n_cameras, p->ring_slots - 1);
+    ctx->held.assign(p->n_cameras, 0);
+    ctx->plane_seq.assign(ctx->planes, 0);
+    ctx->eig.assign(p->n_cameras, nullptr);
+    ctx->eig_tag.assign(p->n_cameras, 0);
+    memset(&ctx->pyr, 0, sizeof ctx->pyr);
+
+    auto bail = [&](int code) { psnw_destroy(ctx); return code; };
+
+    if (p->stream) {
+        ctx->stream = (cudaStream_t)p->stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PSNW_ECUDA);
+        ctx->own_stream = true;
+    }
+
+    // level geometry; levels smaller than 8 px are not built (no window fits them anyway)
+    int w = p->width, h = p->height, levels = 0;
+    for (int l = 0; l < p->levels; ++l) {
+        if (l > 0) { w = (w + 1) / 2; h = (h + 1) / 2; }
+        if (w < 8 || h < 8) break;
+        LevelGeom &g = ctx->pyr.lv[l];
+        g.w = w; g.h = h;
+        g.pitch = (w + 127) & ~127;
+        g.plane_px = g.pitch * h;
+        const size_t px = (size_t)g.plane_px * ctx->planes;
+        if (cudaMalloc(&g.img, px) != cudaSuccess || cudaMalloc(&g.dxy, px * sizeof(short2)) != cudaSuccess) {
+            *out = nullptr;
+            return bail(PSNW_ENOMEM);
+        }
+        cudaMemsetAsync(g.img, 0, px, ctx->stream);
+        cudaMemsetAsync(g.dxy, 0, px * sizeof(short2), ctx->stream);
+        ++levels;
+    }
+    ctx->pyr.levels = levels;
+    if (make_tensor_maps(ctx) != PSNW_OK) {
+        fprintf(stderr, "psnw_create: %s\n", ctx->err.c_str());
+        return bail(PSNW_ECUDA);
+    }
+    // scratch sized from the capacities given at create time
+    const size_t arena = (size_t)p->max_points * 48 + (size_t)p->max_targets * 2048 + (1 << 16);
+    if (ensure(ctx, ctx->arena, arena) != PSNW_OK || ensure(ctx, ctx->desc, (size_t)p->max_targets * 64 + (1 << 16)) != PSNW_OK)
+        return bail(PSNW_ENOMEM);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return bail(PSNW_ECUDA);
+    *out = ctx;
+    return PSNW_OK;
+}
+
+int psnw_destroy(psnw_ctx *ctx)
+{
+    if (!ctx) return PSNW_EARG;
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int l = 0; l < PSNW_MAX_LEVELS; ++l) {
+        if (ctx->pyr.lv[l].img) cudaFree(ctx->pyr.lv[l].img);
+        if (ctx->pyr.lv[l].dxy) cudaFree(ctx->pyr.lv[l].dxy);
+    }
+    for (float *e : ctx->eig) if (e) cudaFree(e);
+    if (ctx->arena.p) cudaFree(ctx->arena.p);
+    if (ctx->desc.p) cudaFree(ctx->desc.p);
+    if (ctx->cand.p) cudaFree(ctx->cand.p);
+    if (ctx->bgr.p) cudaFree(ctx->bgr.p);
+    for (StageSlot &s : ctx->stage) {
+        if (s.h) cudaFreeHost(s.h);
+        if (s.ev) cudaEventDestroy(s.ev);
+    }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PSNW_OK;
+}
+
+int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const *grays, size_t pitch,
+                     uint32_t frame_idx, int mem_flags)
+{
+    (void)frame_idx;
+    if (!ctx) return PSNW_EARG;
+    if (n <= 0 || !cams || !grays || pitch < (size_t)ctx->p.width) return fail(ctx, PSNW_EARG, "psnw_push_frames arguments");
+    for (int i = 0; i < n; ++i)
+        if (!grays[i]) return fail(ctx, PSNW_EARG, "null frame pointer");
+    std::vector<int> planes;
+    int rc = advance_ring(ctx, n, cams, planes);
+    if (rc) return rc;
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    for (int i = 0; i < n; ++i)
+        CK(cudaMemcpy2DAsync(l0.img + (size_t)planes[i] * l0.plane_px, l0.pitch, grays[i], pitch, l0.w, l0.h,
+                             h2d(mem_flags), ctx->stream));
+    rc = build_pyramids(ctx, planes);
+    if (rc) return rc;
+    if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return PSNW_OK;
+}
+
+int psnw_push_frame(psnw_ctx *ctx, int cam, const uint8_t *gray, size_t pitch, uint32_t frame_idx, int mem_flags)
+{
+    return psnw_push_frames(ctx, 1, &cam, &gray, pitch, frame_idx, mem_flags);
+}
+
+int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const *bgr, size_t pitch,
+                         uint32_t frame_idx, int luma_bits, int mem_flags)
+{
+    (void)frame_idx;
+    if (!ctx) return PSNW_EARG;
+    if (n <= 0 || !cams || !bgr || pitch < (size_t)ctx->p.width * 3 || (luma_bits != 14 && luma_bits != 15))
+        return fail(ctx, PSNW_EARG, "psnw_push_frames_bgr arguments");
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    const size_t row = ((size_t)l0.w * 3 + 255) & ~(size_t)255, frame = row * l0.h;
+    if (mem_flags != PSNW_MEM_DEVICE) {
+        int rc = ensure(ctx, ctx->bgr, frame * n);
+        if (rc) return rc;
+    }
+    std::vector<int> planes;
+    int rc = advance_ring(ctx, n, cams, planes);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+        const uint8_t *src = bgr[i];
+        size_t src_pitch = pitch;
+        if (!src) return fail(ctx, PSNW_EARG, "null frame pointer");
+        if (mem_flags != PSNW_MEM_DEVICE) {
+            uint8_t *dst = reinterpret_cast<uint8_t *>(ctx->bgr.p) + frame * i;
+            CK(cudaMemcpy2DAsync(dst, row, bgr[i], pitch, (size_t)l0.w * 3, l0.h, cudaMemcpyHostToDevice, ctx->stream));
+            src = dst; src_pitch = row;
+        }
+        const int r = launch_bgr2gray(src, src_pitch, l0.img + (size_t)planes[i] * l0.plane_px, l0.pitch, l0.w, l0.h,
+                                      luma_bits, ctx->stream);
+        if (r < 0) return fail(ctx, PSNW_ECUDA, "bgr2gray_kernel launch", cudaGetLastError());
+        ctx->launches += r;
+    }
+    rc = build_pyramids(ctx, planes);
+    if (rc) return rc;
+    if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return PSNW_OK;
+}
+
+int psnw_rebuild_pyramids(psnw_ctx *ctx, int n, const int *cams)
+{
+    if (!ctx || n <= 0 || !cams) return PSNW_EARG;
+    std::vector<int> planes(n);
+    for (int i = 0; i < n; ++i) {
+        if (!slot_ok(ctx, cams[i], 0)) return fail(ctx, PSNW_ESTATE, "psnw_rebuild_pyramids: camera holds no frame");
+        planes[i] = plane_of(ctx, cams[i], 0);
+    }
+    return build_pyramids(ctx, planes);
+}
+
+int psnw_frames_held(psnw_ctx *ctx, int cam)
+{
+    if (!ctx || cam < 0 || cam >= ctx->p.n_cameras) return PSNW_EARG;
+    return ctx->held[cam];
+}
+
+int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, int mem_flags)
+{
+    if (!ctx) return PSNW_EARG;
+    if (!jobs || n_jobs <= 0) return fail(ctx, PSNW_EARG, "psnw_klt_track_batch: no jobs");
+    const bool dev = mem_flags == PSNW_MEM_DEVICE;
+    int total = 0, total_groups = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const psnw_track_job &J = jobs[j];
+        if (J.n_pts < 0 || J.n_targets < 1 || (J.n_pts > 0 && (!J.pts_xy || !J.out_xy || !J.status || !J.err)))
+            return fail(ctx, PSNW_EARG, "psnw_klt_track: bad job arrays");
+        if (!slot_ok(ctx, J.cam, J.slot_from) || !slot_ok(ctx, J.cam, J.slot_to))
+            return fail(ctx, PSNW_ESTATE, "psnw_klt_track: camera/slot holds no frame");
+        total += J.n_pts;
+        total_groups += J.n_targets;
+    }
+    if (total > ctx->p.max_points || total_groups > ctx->p.max_targets)
+        return fail(ctx, PSNW_ENOMEM, "psnw_klt_track: max_points / max_targets given at create time exceeded");
+    if (total == 0) return PSNW_OK;
+
+    const bool do_fb = ctx->p.fb_thresh >= 0.f;
+    std::vector<TrackJob> dj(n_jobs);
+    std::vector<TrackGroup> dg(total_groups);
+    ctx->arena_off = 0;
+    bool all21 = true;
+    int max_win_px = 1;
+    int pt = 0, gb = 0;
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    for (int j = 0; j < n_jobs; ++j) {
+        const psnw_track_job &J = jobs[j];
+        const int pf = plane_of(ctx, J.cam, J.slot_from), pt_to = plane_of(ctx, J.cam, J.slot_to);
+        for (int t = 0; t < J.n_targets; ++t) {
+            const int ww = J.win_wh ? J.win_wh[2 * t] : ctx->p.win_w, wh = J.win_wh ? J.win_wh[2 * t + 1] : ctx->p.win_h;
+            if (ww < 1 || wh < 1 || ww >= l0.w || wh >= l0.h) return fail(ctx, PSNW_EARG, "psnw_klt_track: window must be >= 1 and smaller than the frame");
+            TrackGroup &g = dg[gb + t];
+            g.plane_from = pf; g.plane_to = pt_to; g.win_w = ww; g.win_h = wh;
+            g.max_level = effective_max_level(ctx, ww, wh);
+            g.pad = 0;
+            all21 = all21 && ww == 21 && wh == 21;
+            max_win_px = std::max(max_win_px, ww * wh);
+        }
+        TrackJob &D = dj[j];
+        D.pt_begin = pt; D.n_pts = J.n_pts; D.group_base = gb; D.n_targets = J.n_targets;
+        if (dev) {
+            D.pts = reinterpret_cast<const float2 *>(J.pts_xy); D.target_of_pt = J.target_of_pt;
+            D.out = reinterpret_cast<float2 *>(J.out_xy); D.status = J.status; D.err = J.err; D.fb_err = do_fb ? J.fb_err : nullptr;
+        } else {
+            float2 *d_pts = take<float2>(ctx, J.n_pts);
+            int *d_tgt = J.target_of_pt ? take<int>(ctx, J.n_pts) : nullptr;
+            D.pts = d_pts; D.target_of_pt = d_tgt;
+            D.out = take<float2>(ctx, J.n_pts); D.status = take<uint8_t>(ctx, J.n_pts); D.err = take<float>(ctx, J.n_pts);
+            D.fb_err = (do_fb && J.fb_err) ? take<float>(ctx, J.n_pts) : nullptr;
+            if (ctx->arena_off > ctx->arena.cap) return fail(ctx, PSNW_ENOMEM, "psnw_klt_track: scratch arena exhausted");
+            if (J.n_pts > 0) {
+                CK(cudaMemcpyAsync(d_pts, J.pts_xy, sizeof(float2) * J.n_pts, cudaMemcpyHostToDevice, ctx->stream));
+                if (d_tgt) CK(cudaMemcpyAsync(d_tgt, J.target_of_pt, sizeof(int) * J.n_pts, cudaMemcpyHostToDevice, ctx->stream));
+            }
+        }
+        pt += J.n_pts; gb += J.n_targets;
+    }
+
+    // descriptors -> device
+    const size_t jb = sizeof(TrackJob) * n_jobs, gbytes = sizeof(TrackGroup) * total_groups;
+    const size_t goff = (jb + 255) & ~(size_t)255;
+    int rc = ensure(ctx, ctx->desc, goff + gbytes);
+    if (rc) return rc;
+    StageSlot *s;
+    rc = stage_acquire(ctx, goff + gbytes, &s);
+    if (rc) return rc;
+    memcpy(s->h, dj.data(), jb);
+    memcpy(s->h + goff, dg.data(), gbytes);
+    rc = stage_upload(ctx, s, ctx->desc.p, goff + gbytes);
+    if (rc) return rc;
+
+    LkParams P;
+    memcpy(P.lv, ctx->pyr.lv, sizeof P.lv);
+    P.jobs = reinterpret_cast<const TrackJob *>(ctx->desc.p);
+    P.groups = reinterpret_cast<const TrackGroup *>(ctx->desc.p + goff);
+    P.n_jobs = n_jobs; P.n_pts = total;
+    P.max_iters = ctx->p.max_iters;
+    P.eps2 = ctx->p.epsilon * ctx->p.epsilon;
+    P.min_eig = ctx->p.min_eig_thresh;
+    P.fb_thresh = ctx->p.fb_thresh;
+    P.do_fb = do_fb ? 1 : 0;
+    const int r = launch_lk(P, all21 ? 1 : 0, max_win_px, ctx->stream);
+    if (r == -2) return fail(ctx, PSNW_EARG, "psnw_klt_track: window too large for shared memory");
+    if (r < 0) return fail(ctx, PSNW_ECUDA, "lk kernel launch", cudaGetLastError());
+    ctx->launches += r;
+
+    if (!dev) {
+        for (int j = 0; j < n_jobs; ++j) {
+            const psnw_track_job &J = jobs[j];
+            const TrackJob &D = dj[j];
+            if (J.n_pts == 0) continue;
+            CK(cudaMemcpyAsync(J.out_xy, D.out, sizeof(float2) * J.n_pts, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(J.status, D.status, J.n_pts, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(J.err, D.err, sizeof(float) * J.n_pts, cudaMemcpyDeviceToHost, ctx->stream));
+            if (D.fb_err) CK(cudaMemcpyAsync(J.fb_err, D.fb_err, sizeof(float) * J.n_pts, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return PSNW_OK;
+}
+
+int psnw_klt_track(psnw_ctx *ctx, int cam, int slot_from, int slot_to, const float *pts_xy, const int *target_of_pt,
+                   int n_pts, const int *win_wh, int n_targets, float *out_xy, uint8_t *status, float *err,
+                   float *fb_err, int mem_flags)
+{
+    psnw_track_job j;
+    j.cam = cam; j.slot_from = slot_from; j.slot_to = slot_to;
+    j.n_pts = n_pts; j.pts_xy = pts_xy; j.target_of_pt = target_of_pt;
+    j.n_targets = n_targets < 1 ? 1 : n_targets; j.win_wh = win_wh;
+    j.out_xy = out_xy; j.status = status; j.err = err; j.fb_err = fb_err;
+    return psnw_klt_track_batch(ctx, &j, 1, mem_flags);
+}
+
+int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const float *pre_xy, const float *cur_xy,
+                    const uint8_t *status, const int *target_offsets, int mode, double *boxes_out,
+                    uint8_t *inlier_mask, int *inlier_counts, int mem_flags)
+{
+    if (!ctx) return PSNW_EARG;
+    if (n_targets < 0 || !boxes_in || !target_offsets || !boxes_out || !inlier_mask || !inlier_counts || mode != PSNW_BOX_REFERENCE)
+        return fail(ctx, PSNW_EARG, "psnw_box_update arguments");
+    if (n_targets == 0) return PSNW_OK;
+    if (n_targets > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_box_update: max_targets exceeded");
+    int r;
+    if (mem_flags == PSNW_MEM_DEVICE) {
+        r = launch_box_update(boxes_in, n_targets, reinterpret_cast<const float2 *>(pre_xy), reinterpret_cast<const float2 *>(cur_xy),
+                              status, target_offsets, boxes_out, inlier_mask, inlier_counts, PSNW_MAX_PTS_PER_TARGET, ctx->stream);
+        if (r < 0) return fail(ctx, PSNW_ECUDA, "box_update_kernel launch", cudaGetLastError());
+        ctx->launches += r;
+        return PSNW_OK;
+    }
+    const int n_pts = target_offsets[n_targets];
+    int max_per = 1;
+    for (int t = 0; t < n_targets; ++t) {
+        const int k = target_offsets[t + 1] - target_offsets[t];
+        if (k < 0 || k > PSNW_MAX_PTS_PER_TARGET) return fail(ctx, PSNW_EARG, "psnw_box_update: offsets not ascending or > PSNW_MAX_PTS_PER_TARGET points in a target");
+        max_per = std::max(max_per, k);
+    }
+    if (n_pts > ctx->p.max_points) return fail(ctx, PSNW_ENOMEM, "psnw_box_update: max_points exceeded");
+    if (n_pts > 0 && (!pre_xy || !cur_xy)) return fail(ctx, PSNW_EARG, "psnw_box_update: null points");
+    ctx->arena_off = 0;
+    double *d_in = take<double>(ctx, (size_t)n_targets * 4), *d_out = take<double>(ctx, (size_t)n_targets * 4);
+    int *d_off = take<int>(ctx, n_targets + 1), *d_cnt = take<int>(ctx, n_targets);
+    float2 *d_pre = take<float2>(ctx, n_pts), *d_cur = take<float2>(ctx, n_pts);
+    uint8_t *d_st = status ? take<uint8_t>(ctx, n_pts) : nullptr, *d_mask = take<uint8_t>(ctx, n_pts);
+    if (ctx->arena_off > ctx->arena.cap) return fail(ctx, PSNW_ENOMEM, "psnw_box_update: scratch arena exhausted");
+    CK(cudaMemcpyAsync(d_in, boxes_in, sizeof(double) * 4 * n_targets, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_off, target_offsets, sizeof(int) * (n_targets + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_pts > 0) {
+        CK(cudaMemcpyAsync(d_pre, pre_xy, sizeof(float2) * n_pts, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_cur, cur_xy, sizeof(float2) * n_pts, cudaMemcpyHostToDevice, ctx->stream));
+        if (d_st) CK(cudaMemcpyAsync(d_st, status, n_pts, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    r = launch_box_update(d_in, n_targets, d_pre, d_cur, d_st, d_off, d_out, d_mask, d_cnt, max_per, ctx->stream);
+    if (r < 0) return fail(ctx, PSNW_ECUDA, "box_update_kernel launch", cudaGetLastError());
+    ctx->launches += r;
+    CK(cudaMemcpyAsync(boxes_out, d_out, sizeof(double) * 4 * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(inlier_counts, d_cnt, sizeof(int) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_pts > 0) CK(cudaMemcpyAsync(inlier_mask, d_mask, n_pts, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return PSNW_OK;
+}
+
+static int ensure_min_eig(psnw_ctx *ctx, int cam, int slot, float **eig_out)
+{
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    const int plane = plane_of(ctx, cam, slot);
+    if (!ctx->eig[cam]) {
+        if (cudaMalloc(&ctx->eig[cam], sizeof(float) * (size_t)l0.plane_px) != cudaSuccess)
+            return fail(ctx, PSNW_ENOMEM, "cudaMalloc min-eig map", cudaGetLastError());
+        ctx->eig_tag[cam] = 0;
+    }
+    if (ctx->eig_tag[cam] != ctx->plane_seq[plane]) {
+        const int r = launch_min_eig(l0, plane, ctx->eig[cam], ctx->stream);
+        if (r < 0) return fail(ctx, PSNW_ECUDA, "min_eig_kernel launch", cudaGetLastError());
+        ctx->launches += r;
+        ctx->eig_tag[cam] = ctx->plane_seq[plane];
+    }
+    *eig_out = ctx->eig[cam];
+    return PSNW_OK;
+}
+
+int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n_targets, int max_per_target,
+                    float quality, float min_dist, float *pts_xy, int *counts, int mem_flags)
+{
+    if (!ctx) return PSNW_EARG;
+    if (n_targets < 0 || max_per_target < 1 || !boxes || !pts_xy || !counts || !(quality > 0.f) || min_dist < 0.f)
+        return fail(ctx, PSNW_EARG, "psnw_klt_detect arguments");
+    if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_klt_detect: camera/slot holds no frame");
+    if (n_targets == 0) return PSNW_OK;
+    if (n_targets > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_klt_detect: max_targets exceeded");
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    float *eig;
+    int rc = ensure_min_eig(ctx, cam, slot, &eig);
+    if (rc) return rc;
+
+    // mask ROI = box.cropWithSize(cols, rows).cv()  (PSNWhere_Types.h:146-153,181; Tracker2D.cpp:735).  `boxes` is
+    // always host memory: detections come from the host-side detector files (PSNWhere.cpp:261).
+    std::vector<DetectTarget> T(n_targets);
+    size_t cand_total = 0;
+    for (int t = 0; t < n_targets; ++t) {
+        const double x = boxes[4 * t], y = boxes[4 * t + 1], w = boxes[4 * t + 2], h = boxes[4 * t + 3];
+        const double nx = std::max(0.0, x), ny = std::max(0.0, y);
+        const double nw = std::min((double)l0.w - nx - 1, w), nh = std::min((double)l0.h - ny - 1, h);
+        DetectTarget &d = T[t];
+        d.x0 = (int)nx; d.y0 = (int)ny;
+        d.x1 = d.x0 + std::max((int)nw, 0); d.y1 = d.y0 + std::max((int)nh, 0);
+        d.x0 = std::min(d.x0, l0.w); d.y0 = std::min(d.y0, l0.h);
+        d.x1 = std::min(std::max(d.x1, d.x0), l0.w); d.y1 = std::min(std::max(d.y1, d.y0), l0.h);
+        d.cand_begin = (int)cand_total;
+        d.cand_cap = (d.x1 - d.x0) * (d.y1 - d.y0);
+        cand_total += (size_t)d.cand_cap;
+    }
+    if (cand_total > ((size_t)1 << 30)) return fail(ctx, PSNW_ENOMEM, "psnw_klt_detect: candidate scratch too large");
+    rc = ensure(ctx, ctx->cand, cand_total * sizeof(unsigned long long) + 256);
+    if (rc) return rc;
+    const bool dev = mem_flags == PSNW_MEM_DEVICE;
+    const size_t n_out = (size_t)n_targets * max_per_target;
+    const size_t tb = (sizeof(DetectTarget) * n_targets + 255) & ~(size_t)255;
+    const size_t need = tb + (dev ? 0 : n_out * sizeof(float2) + 256 + sizeof(int) * n_targets + 256);
+    rc = ensure(ctx, ctx->desc, need);
+    if (rc) return rc;
+    StageSlot *s;
+    rc = stage_acquire(ctx, tb, &s);
+    if (rc) return rc;
+    memcpy(s->h, T.data(), sizeof(DetectTarget) * n_targets);
+    rc = stage_upload(ctx, s, ctx->desc.p, sizeof(DetectTarget) * n_targets);
+    if (rc) return rc;
+    float2 *d_out = dev ? reinterpret_cast<float2 *>(pts_xy) : reinterpret_cast<float2 *>(ctx->desc.p + tb);
+    int *d_cnt = dev ? counts : reinterpret_cast<int *>(ctx->desc.p + tb + ((n_out * sizeof(float2) + 255) & ~(size_t)255));
+    const int r = launch_detect_select(eig, l0.w, l0.h, l0.pitch, reinterpret_cast<const DetectTarget *>(ctx->desc.p), n_targets,
+                                       max_per_target, quality, min_dist, reinterpret_cast<unsigned long long *>(ctx->cand.p),
+                                       d_out, d_cnt, ctx->stream);
+    if (r < 0) return fail(ctx, PSNW_ECUDA, "detect_select_kernel launch", cudaGetLastError());
+    ctx->launches += r;
+    if (!dev) {
+        CK(cudaMemcpyAsync(pts_xy, d_out, n_out * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(counts, d_cnt, sizeof(int) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+        if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return PSNW_OK;
+}
+
+int psnw_sync(psnw_ctx *ctx)
+{
+    if (!ctx) return PSNW_EARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PSNW_OK;
+}
+
+const char *psnw_last_error(psnw_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void *psnw_get_stream(psnw_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int psnw_level_info(psnw_ctx *ctx, int level, int *w, int *h, int *pitch)
+{
+    if (!ctx || level < 0 || level >= ctx->pyr.levels) return PSNW_EARG;
+    if (w) *w = ctx->pyr.lv[level].w;
+    if (h) *h = ctx->pyr.lv[level].h;
+    if (pitch) *pitch = ctx->pyr.lv[level].pitch;
+    return PSNW_OK;
+}
+
+int psnw_levels_built(psnw_ctx *ctx) { return ctx ? ctx->pyr.levels : PSNW_EARG; }
+
+int psnw_read_level(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *img_out, int16_t *dxy_out)
+{
+    if (!ctx || level < 0 || level >= ctx->pyr.levels) return PSNW_EARG;
+    if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_read_level: camera/slot holds no frame");
+    const LevelGeom &g = ctx->pyr.lv[level];
+    const int plane = plane_of(ctx, cam, slot);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (img_out) CK(cudaMemcpy2D(img_out, g.w, g.img + (size_t)plane * g.plane_px, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+    if (dxy_out) CK(cudaMemcpy2D(dxy_out, (size_t)g.w * 4, g.dxy + (size_t)plane * g.plane_px, (size_t)g.pitch * 4, (size_t)g.w * 4, g.h, cudaMemcpyDeviceToHost));
+    return PSNW_OK;
+}
+
+int psnw_read_min_eig(psnw_ctx *ctx, int cam, int slot, float *eig_out)
+{
+    if (!ctx || !eig_out) return PSNW_EARG;
+    if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_read_min_eig: camera/slot holds no frame");
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    float *eig;
+    const int rc = ensure_min_eig(ctx, cam, slot, &eig);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy2D(eig_out, (size_t)l0.w * 4, eig, (size_t)l0.pitch * 4, (size_t)l0.w * 4, l0.h, cudaMemcpyDeviceToHost));
+    return PSNW_OK;
+}
+
+uint64_t psnw_launch_count(psnw_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t psnw_push_frame_bytes(psnw_ctx *ctx)
+{
+    if (!ctx) return 0;
+    uint64_t b = 0;
+    for (int l = 0; l < ctx->pyr.levels; ++l) {
+        const uint64_t n = (uint64_t)ctx->pyr.lv[l].w * ctx->pyr.lv[l].h;
+        b += n + 4 * n + (l > 0 ? n : 0);      // read u8, write short2, write u8 (levels >= 1)
+    }
+    return b;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// K4: per-target box motion from tracked features == LocalSearchKLT,
+// psn_where/PSNWhere_Tracker2D.cpp:452-554 (callers :787 backward, :893 forward); SURVEY.md Appendix B.
+//
+// One CTA per target.  All comparisons are in double like the reference (PSN_Point2D, PSNWhere_Types.h:18-66);
+// the displacement itself is a float subtraction promoted to double (cv::Point2f operator-, :479).
+// std::sort + "first strict maximum" (:498-537) is restated without a sort: the estimate on each axis is
+// the SMALLEST displacement among those with the largest neighbour count.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace psnw {
+
+namespace {
+
+constexpr int kBoxThreads = 128;
+constexpr int kMaxPts = PSNW_MAX_PTS_PER_TARGET;
+
+struct Best {
+    int cnt;
+    double val;
+};
+
+__device__ __forceinline__ Best better(Best a, Best b)
+{
+    if (b.cnt > a.cnt || (b.cnt == a.cnt && b.cnt > 0 && b.val < a.val)) return b;
+    return a;
+}
+
+__global__ void __launch_bounds__(kBoxThreads)
+box_update_kernel(const double *__restrict__ boxes_in, const float2 *__restrict__ pre, const float2 *__restrict__ cur,
+                  const uint8_t *__restrict__ status, const int *__restrict__ offsets,
+                  double *__restrict__ boxes_out, uint8_t *__restrict__ mask, int *__restrict__ counts, int cap)
+{
+    extern __shared__ __align__(16) unsigned char box_smem[];
+    __shared__ int s_n, s_moving, s_inl;
+    __shared__ Best s_bx[kBoxThreads], s_by[kBoxThreads];
+    __shared__ double s_est[2];
+
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const int beg = offsets[t], end = offsets[t + 1];
+    const int n_all = min(max(end - beg, 0), cap);
+    double *mvx = reinterpret_cast<double *>(box_smem);
+    double *mvy = mvx + n_all;
+    uint8_t *mov = reinterpret_cast<uint8_t *>(mvy + n_all);
+
+    if (tid == 0) { s_n = 0; s_moving = 0; s_inl = 0; }
+    __syncthreads();
+
+    // :477-490  moving features (disparity >= 0.1 px)
+    int n_loc = 0, m_loc = 0;
+    for (int i = tid; i < n_all; i += kBoxThreads) {
+        const bool valid = status ? (status[beg + i] != 0) : true;
+        const float2 a = pre[beg + i], b = cur[beg + i];
+        const double x = (double)__fsub_rn(b.x, a.x), y = (double)__fsub_rn(b.y, a.y);
+        const double d = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+        const bool m = valid && !(d < 0.1);
+        mvx[i] = x; mvy[i] = y; mov[i] = m ? 1 : 0;
+        n_loc += valid; m_loc += m;
+        mask[beg + i] = 0;
+    }
+    atomicAdd(&s_n, n_loc);
+    atomicAdd(&s_moving, m_loc);
+    __syncthreads();
+    const int n = s_n, n_moving = s_moving;
+
+    const double bx = boxes_in[4 * t], by = boxes_in[4 * t + 1], bw = boxes_in[4 * t + 2], bh = boxes_in[4 * t + 3];
+    if ((double)n_moving < __dmul_rn((double)n, 0.5)) {          // :493-496 static target: box unchanged, no inliers
+        if (tid == 0) {
+            boxes_out[4 * t] = bx; boxes_out[4 * t + 1] = by; boxes_out[4 * t + 2] = bw; boxes_out[4 * t + 3] = bh;
+            counts[t] = 0;
+        }
+        return;
+    }
+
+    // :502-537  per-axis mode: most neighbours within 0.2 * box.w, ties -> smallest displacement
+    const double win = __dmul_rn(bw, 0.2);
+    Best kx = {0, 0.0}, ky = {0, 0.0};
+    for (int k = tid; k < n_all; k += kBoxThreads) {
+        if (!mov[k]) continue;
+        const double vx = mvx[k], vy = mvy[k];
+        int cx = 0, cy = 0;
+        for (int j = 0; j < n_all; ++j) {
+            if (!mov[j]) continue;
+            cx += fabs(__dsub_rn(vx, mvx[j])) < win;
+            cy += fabs(__dsub_rn(vy, mvy[j])) < win;
+        }
+        kx = better(kx, Best{cx, vx});
+        ky = better(ky, Best{cy, vy});
+    }
+    s_bx[tid] = kx; s_by[tid] = ky;
+    __syncthreads();
+    if (tid == 0) {
+        Best ax = {0, 0.0}, ay = {0, 0.0};
+        for (int i = 0; i < kBoxThreads; ++i) { ax = better(ax, s_bx[i]); ay = better(ay, s_by[i]); }
+        s_est[0] = ax.cnt > 0 ? ax.val : 0.0;      // estimatedDisparity starts at (0,0), Types.h:27
+        s_est[1] = ay.cnt > 0 ? ay.val : 0.0;
+    }
+    __syncthreads();
+    const double ex = s_est[0], ey = s_est[1];
+
+    // :540-546 inliers among the moving features
+    int inl = 0;
+    for (int i = tid; i < n_all; i += kBoxThreads) {
+        if (!mov[i]) continue;
+        const double rx = __dsub_rn(mvx[i], ex), ry = __dsub_rn(mvy[i], ey);
+        if (sqrt(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry))) < win) { mask[beg + i] = 1; ++inl; }
+    }
+    atomicAdd(&s_inl, inl);
+    __syncthreads();
+    if (tid == 0) {                                              // :549-553
+        boxes_out[4 * t] = __dadd_rn(bx, ex); boxes_out[4 * t + 1] = __dadd_rn(by, ey);
+        boxes_out[4 * t + 2] = bw; boxes_out[4 * t + 3] = bh;
+        counts[t] = s_inl;
+    }
+}
+
+}  // namespace
+
+int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
+                      const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,
+                      int *counts, int max_pts_per_target, cudaStream_t stream)
+{
+    if (n_targets <= 0) return 0;
+    const int cap = std::min(std::max(max_pts_per_target, 1), kMaxPts);
+    const size_t smem = (size_t)cap * 17 + 16;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(box_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPts * 17 + 16) != cudaSuccess) return -1;
+        configured = true;
+    }
+    box_update_kernel<<<n_targets, kBoxThreads, smem, stream>>>(boxes_in, pre, cur, status, offsets, boxes_out, mask, counts, cap);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace psnw

@@ -1,0 +1,86 @@
+// Shared device/host declarations of the psnw KLT library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "psnw_klt.h"
+
+namespace psnw {
+
+// One pyramid level of the whole context: planes are [camera][ring slot], row pitch in u8 bytes ==
+// row pitch of the derivative image in short2 elements.
+struct LevelGeom {
+    uint8_t *img;      // [planes][h][pitch] u8
+    short2 *dxy;       // [planes][h][pitch] (dx,dy) int16, Scharr x32 (calcSharrDeriv layout)
+    int w, h, pitch;
+    int plane_px;      // h * pitch
+};
+
+struct PyrDesc {
+    LevelGeom lv[PSNW_MAX_LEVELS];
+    int levels;
+};
+
+struct PlaneList {
+    int n;
+    int plane[63];
+};
+
+// One (job, target) of a klt_track launch.
+struct TrackGroup {
+    int plane_from, plane_to;
+    int win_w, win_h;
+    int max_level;     // after buildOpticalFlowPyramid's truncation rule
+    int pad;
+};
+
+// One job of a klt_track_batch launch (device-visible pointers).
+struct TrackJob {
+    const float2 *pts;
+    const int *target_of_pt;   // may be null
+    float2 *out;
+    uint8_t *status;
+    float *err;
+    float *fb_err;             // may be null
+    int pt_begin, n_pts;
+    int group_base, n_targets;
+};
+
+struct LkParams {
+    LevelGeom lv[PSNW_MAX_LEVELS];
+    const TrackJob *jobs;
+    const TrackGroup *groups;
+    int n_jobs, n_pts;
+    int max_iters;
+    double eps2;
+    float min_eig;
+    float fb_thresh;
+    int do_fb;
+};
+
+// --- launchers (each returns the number of kernels it enqueued, or -1 with cudaGetLastError set) ---
+int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes,
+                     cudaStream_t stream);
+int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,
+                    int luma_bits, cudaStream_t stream);
+int launch_lk(const LkParams &P, int all_21x21, int max_win_px, cudaStream_t stream);
+int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
+                      const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,
+                      int *counts, int max_pts_per_target, cudaStream_t stream);
+int launch_min_eig(const LevelGeom &l0, int plane, float *eig, cudaStream_t stream);
+
+struct DetectTarget {
+    int x0, y0, x1, y1;        // cropped ROI, half open
+    int cand_begin, cand_cap;  // slice of the candidate scratch
+};
+int launch_detect_select(const float *eig, int w, int h, int pitch, const DetectTarget *targets, int n_targets,
+                         int max_per_target, float quality, float min_dist, unsigned long long *cand,
+                         float2 *out, int *counts, cudaStream_t stream);
+
+// tile geometry of the pyramid kernel (the TMA box must match on host and device)
+constexpr int kTileW = 128, kTileH = 32;
+constexpr int kBoxW = 144, kBoxH = kTileH + 3;
+constexpr int kHaloL = 4, kHaloT = 2;
+
+}  // namespace psnw

@@ -1,0 +1,232 @@
+// K1: fused Gaussian pyrDown + Scharr derivative of one pyramid level, batched over camera-frames.
+//
+// Replaces the pyramid / derivative construction that cv::calcOpticalFlowPyrLK repeats inside every
+// call at psn_where/PSNWhere_Tracker2D.cpp:776 and :871:
+// here it runs once per pushed frame.  Arithmetic is integer and bit-exact with OpenCV:
+//   pyrDown : [1 4 6 4 1]^2, REFLECT_101, (sum + 128) >> 8, size ((w+1)/2, (h+1)/2)
+//   Scharr  : dx = t0[x+1]-t0[x-1], t0 = 3(r[y-1]+r[y+1]) + 10 r[y];  dy = 3(t1[x-1]+t1[x+1]) + 10 t1[x],
+//             t1 = r[y+1]-r[y-1]; interleaved int16 (dx,dy), REFLECT_101.
+//
+// One CTA (4 warps) owns a 128x32 tile of level l.  The u8 tile plus halo (144x35 bytes) is fetched by a
+// single TMA 3-D box (x, y, plane) that completes on an mbarrier; out-of-image halo bytes arrive as zeros
+// and edge tiles rewrite them with the REFLECT_101 mirror in shared memory.  Each lane then owns 4
+// adjacent columns and slides down 8 output rows: the horizontal taps are dp4a dot products on the packed
+// u8 words (no byte unpacking), the vertical taps run on registers.  Stores are 16-byte (4 x short2) per
+// lane = 512 contiguous bytes per warp row for the derivative image and 2 bytes per lane for the next
+// u8 level.  HBM traffic per level-l pixel: 1 B read, 4 B + 0.25 B written.
+#include "common.cuh"
+
+namespace psnw {
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
+constexpr int kRowWords = kBoxW / 4;   // 36
+constexpr int kRowsPerWarp = 8;
+
+// dp4a coefficient words (byte 0 = lowest address)
+constexpr int kDiffLo = 0x000100FF;     // (-1, 0, 1, 0)
+constexpr int kDiffHi = 0x0100FF00;     // ( 0,-1, 0, 1)
+constexpr int kSmoothLo = 0x00030A03;   // ( 3,10, 3, 0)
+constexpr int kSmoothHi = 0x030A0300;   // ( 0, 3,10, 3)
+constexpr int kGauss = 0x04060401;      // ( 1, 4, 6, 4)
+
+template <bool kHasNext>
+__global__ void __launch_bounds__(128)
+pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, const LevelGeom nxt,
+                  const PlaneList planes)
+{
+    __shared__ __align__(128) uint32_t tile[kBoxH * kRowWords];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+    const int plane = planes.plane[blockIdx.z];
+    const uint32_t bar_a = smem_u32(&bar);
+
+    if (tid == 0) mbar_init(bar_a, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar_a, kBoxW * kBoxH);
+        tma_load_3d(smem_u32(tile), &map, x0 - kHaloL, y0 - kHaloT, plane, bar_a);
+    }
+    mbar_wait(bar_a, 0);
+
+    // ---- REFLECT_101 fix-up of halo bytes that fell outside the image (TMA wrote zeros there) ----
+    const int W = cur.w, H = cur.h;
+    const bool edge_l = (x0 == 0), edge_r = (W - x0 + 5 < kBoxW);
+    const bool edge_t = (y0 == 0), edge_b = (H - y0 + 2 < kBoxH);
+    if (edge_l || edge_r || edge_t || edge_b) {
+        uint8_t *tb = reinterpret_cast<uint8_t *>(tile);
+        if (edge_l || edge_r) {
+            if (tid < kBoxH) {
+                uint8_t *row = tb + tid * kBoxW;
+                if (edge_l) { row[3] = row[5]; row[2] = row[6]; }                 // x=-1 <- 1, x=-2 <- 2
+                if (edge_r) {
+                    const int c = W - x0 + kHaloL;                                  // column of x = W
+                    row[c] = row[c - 2];                                            // x=W   <- W-2
+                    row[c + 1] = row[c - 3];                                        // x=W+1 <- W-3
+                }
+            }
+            __syncthreads();
+        }
+        if (edge_t || edge_b) {
+            for (int i = tid; i < kRowWords; i += 128) {
+                if (edge_t) { tile[1 * kRowWords + i] = tile[3 * kRowWords + i]; tile[i] = tile[4 * kRowWords + i]; }
+                if (edge_b) {
+                    const int r = H - y0 + kHaloT;                                  // row of y = H
+                    tile[r * kRowWords + i] = tile[(r - 2) * kRowWords + i];        // y=H   <- H-2
+                    if (r + 1 < kBoxH) tile[(r + 1) * kRowWords + i] = tile[(r - 3) * kRowWords + i];   // y=H+1 <- H-3
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t *base = tile + (warp * kRowsPerWarp) * kRowWords + lane;   // words (prev, cur, next) = base[0..2]
+    const int ybase = y0 + warp * kRowsPerWarp;                               // first output row of this warp
+
+    int hd[3][4], hs[3][4];     // horizontal difference / 3-10-3 smooth of the last three rows
+    int pg[5][2];               // horizontal 1-4-6-4-1 of the last five rows (even columns only)
+
+    uint4 *dxy_out = reinterpret_cast<uint4 *>(cur.dxy + (size_t)plane * cur.plane_px + (size_t)ybase * cur.pitch + x0) + lane;
+    const int dxy_row_u4 = cur.pitch / 4;
+
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp + 3; ++rr) {
+        const uint32_t wp = base[rr * kRowWords], wc = base[rr * kRowWords + 1], wn = base[rr * kRowWords + 2];
+        if (rr >= 1) {
+            const uint32_t sa = __funnelshift_r(wp, wc, 24);    // bytes x-1 .. x+2
+            const uint32_t sb = __funnelshift_r(wc, wn, 8);     // bytes x+1 .. x+4
+            int *d = hd[rr % 3], *s = hs[rr % 3];
+            d[0] = dp4a_us(sa, kDiffLo, 0);   d[1] = dp4a_us(sa, kDiffHi, 0);
+            d[2] = dp4a_us(sb, kDiffLo, 0);   d[3] = dp4a_us(sb, kDiffHi, 0);
+            s[0] = dp4a_us(sa, kSmoothLo, 0); s[1] = dp4a_us(sa, kSmoothHi, 0);
+            s[2] = dp4a_us(sb, kSmoothLo, 0); s[3] = dp4a_us(sb, kSmoothHi, 0);
+        }
+        if (kHasNext) {
+            const uint32_t sc = __funnelshift_r(wp, wc, 16);    // bytes x-2 .. x+1
+            pg[rr % 5][0] = dp4a_us(sc, kGauss, (int)((wc >> 16) & 0xffu));   // + byte x+2
+            pg[rr % 5][1] = dp4a_us(wc, kGauss, (int)(wn & 0xffu));           // centre x+2: bytes x..x+3, + byte x+4
+        }
+        if (rr >= 3) {
+            const int k = rr - 3;                               // output row ybase + k: rows rr-2, rr-1, rr
+            const int *dm = hd[(rr - 2) % 3], *d0 = hd[(rr - 1) % 3], *dp = hd[rr % 3];
+            const int *sm = hs[(rr - 2) % 3], *sp = hs[rr % 3];
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int dx = 3 * (dm[i] + dp[i]) + 10 * d0[i];
+                const int dy = sp[i] - sm[i];
+                o[i] = __byte_perm((uint32_t)dx, (uint32_t)dy, 0x5410);
+            }
+            if (ybase + k < H) dxy_out[(size_t)k * dxy_row_u4] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (kHasNext && rr >= 4 && (rr & 1) == 0) {
+            const int m = (rr - 4) >> 1;                        // rows rr-4 .. rr, centre rr-2
+            const int j = (ybase >> 1) + m;
+            int v[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                v[i] = (pg[(rr - 4) % 5][i] + pg[rr % 5][i]) + 4 * (pg[(rr - 3) % 5][i] + pg[(rr - 1) % 5][i]) +
+                       6 * pg[(rr - 2) % 5][i];
+            const int ox = (x0 >> 1) + 2 * lane;
+            if (j < nxt.h && ox < nxt.pitch) {
+                const uint16_t pk = (uint16_t)(((v[0] + 128) >> 8) | (((v[1] + 128) >> 8) << 8));
+                *reinterpret_cast<uint16_t *>(nxt.img + (size_t)plane * nxt.plane_px + (size_t)j * nxt.pitch + ox) = pk;
+            }
+        }
+    }
+}
+
+// BGR (8UC3) -> gray, cv::cvtColor(BGR2GRAY) fixed point (Tracker2D.cpp:257):
+//   15 bit: (3735 B + 19235 G + 9798 R + 2^14) >> 15 (OpenCV 4.x);  14 bit: (1868 B + 9617 G + 4899 R + 2^13) >> 14 (2.4.6)
+__global__ void __launch_bounds__(256)
+bgr2gray_kernel(const uint8_t *__restrict__ bgr, size_t bgr_pitch, uint8_t *__restrict__ gray, int gray_pitch,
+                int w, int h, int luma_bits)
+{
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x4 >= w || y >= h) return;
+    const uint8_t *src = bgr + (size_t)y * bgr_pitch + (size_t)x4 * 3;
+    const int cb = luma_bits == 14 ? 1868 : 3735, cg = luma_bits == 14 ? 9617 : 19235, cr = luma_bits == 14 ? 4899 : 9798;
+    const int rnd = 1 << (luma_bits - 1);
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (x4 + i < w) {
+            const int v = (cb * src[3 * i] + cg * src[3 * i + 1] + cr * src[3 * i + 2] + rnd) >> luma_bits;
+            out |= (uint32_t)v << (8 * i);
+        }
+    }
+    *reinterpret_cast<uint32_t *>(gray + (size_t)y * gray_pitch + x4) = out;
+}
+
+}  // namespace
+
+int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes,
+                     cudaStream_t stream)
+{
+    const LevelGeom &cur = pyr.lv[level];
+    const bool has_next = level + 1 < pyr.levels;
+    const LevelGeom &nxt = pyr.lv[has_next ? level + 1 : level];
+    dim3 grid((cur.w + kTileW - 1) / kTileW, (cur.h + kTileH - 1) / kTileH, planes.n);
+    if (has_next)
+        pyr_scharr_kernel<true><<<grid, 128, 0, stream>>>(*map_in, cur, nxt, planes);
+    else
+        pyr_scharr_kernel<false><<<grid, 128, 0, stream>>>(*map_in, cur, nxt, planes);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,
+                    int luma_bits, cudaStream_t stream)
+{
+    dim3 grid((w + 1023) / 1024, h);
+    bgr2gray_kernel<<<grid, 256, 0, stream>>>(bgr, bgr_pitch, gray, gray_pitch, w, h, luma_bits);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace psnw
