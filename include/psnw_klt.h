@@ -110,8 +110,10 @@ PSNW_API int psnw_frames_held(psnw_ctx *ctx, int cam);
  * Feature detection inside detection boxes (replaces m_detector->detect + mask, .cpp:735-757).
  * Shi-Tomasi min-eigenvalue corners (north_star) == cv::goodFeaturesToTrack(img, max_per_target, quality,
  * min_dist, mask = box cropped like PSN_Rect::cropWithSize, blockSize 3).  boxes: PSN_Rect layout
- * {x,y,w,h} doubles (PSNWhere_Types.h:112-122).  pts_xy: [n_targets][max_per_target][2] floats, strongest
- * first; counts[n_targets].
+ * {x,y,w,h} doubles (PSNWhere_Types.h:112-122), ALWAYS host memory (detections come from the host-side
+ * detector, psn_where/PSNWhere.cpp:261).  pts_xy: [n_targets][max_per_target][2] floats, strongest first;
+ * counts[n_targets].  Slots >= counts[t] are set to (-1e6,-1e6), which psnw_klt_track rejects at once
+ * (status 0), so the padded array can be tracked as is without a host round trip.
  */
 PSNW_API int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n_targets,
                              int max_per_target, float quality, float min_dist,

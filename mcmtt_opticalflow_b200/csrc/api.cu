@@ -516,9 +516,9 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
                     uint8_t *inlier_mask, int *inlier_counts, int mem_flags)
 {
     if (!ctx) return PSNW_EARG;
+    if (n_targets == 0) return PSNW_OK;
     if (n_targets < 0 || !boxes_in || !target_offsets || !boxes_out || !inlier_mask || !inlier_counts || mode != PSNW_BOX_REFERENCE)
         return fail(ctx, PSNW_EARG, "psnw_box_update arguments");
-    if (n_targets == 0) return PSNW_OK;
     if (n_targets > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_box_update: max_targets exceeded");
     int r;
     if (mem_flags == PSNW_MEM_DEVICE) {
@@ -583,10 +583,10 @@ int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n
                     float quality, float min_dist, float *pts_xy, int *counts, int mem_flags)
 {
     if (!ctx) return PSNW_EARG;
+    if (n_targets == 0) return PSNW_OK;
     if (n_targets < 0 || max_per_target < 1 || !boxes || !pts_xy || !counts || !(quality > 0.f) || min_dist < 0.f)
         return fail(ctx, PSNW_EARG, "psnw_klt_detect arguments");
     if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_klt_detect: camera/slot holds no frame");
-    if (n_targets == 0) return PSNW_OK;
     if (n_targets > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_klt_detect: max_targets exceeded");
     const LevelGeom &l0 = ctx->pyr.lv[0];
     float *eig;

@@ -80,7 +80,9 @@ int launch_detect_select(const float *eig, int w, int h, int pitch, const Detect
 
 // tile geometry of the pyramid kernel (the TMA box must match on host and device)
 constexpr int kTileW = 128, kTileH = 32;
-constexpr int kBoxW = 144, kBoxH = kTileH + 3;
-constexpr int kHaloL = 4, kHaloT = 2;
+// The innermost TMA start coordinate must be 16-byte aligned (u8 elements: a multiple of 16 pixels; a start at
+// x0 - 4 faults with "illegal instruction" on sm_100a), so the box starts 16 px left of the tile: 16 + 128 + 16.
+constexpr int kBoxW = 160, kBoxH = kTileH + 3;
+constexpr int kHaloL = 16, kHaloT = 2;
 
 }  // namespace psnw

@@ -84,6 +84,7 @@ min_eig_kernel(const uint8_t *__restrict__ img, int w, int h, int pitch, float *
 }
 
 constexpr int kSelThreads = 256;
+constexpr float kUnusedSlot = -1.0e6f;
 constexpr int kSmemCand = 4096;
 
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
@@ -113,6 +114,7 @@ detect_select_kernel(const float *__restrict__ eig, int w, int h, int pitch, con
 
     if (T.x1 <= T.x0 || T.y1 <= T.y0 || max_per_target <= 0) {
         if (tid == 0) counts[blockIdx.x] = 0;
+        for (int i = tid; i < max_per_target; i += kSelThreads) my_out[i] = make_float2(kUnusedSlot, kUnusedSlot);
         return;
     }
 
@@ -200,6 +202,8 @@ detect_select_kernel(const float *__restrict__ eig, int w, int h, int pitch, con
         ++n_out;
     }
     if (tid == 0) counts[blockIdx.x] = n_out;
+    // unused slots get a far-away sentinel: fed to psnw_klt_track they fail the bounds test at once (status 0)
+    for (int i = n_out + tid; i < max_per_target; i += kSelThreads) my_out[i] = make_float2(kUnusedSlot, kUnusedSlot);
 }
 
 }  // namespace

@@ -7,7 +7,7 @@
 //   Scharr  : dx = t0[x+1]-t0[x-1], t0 = 3(r[y-1]+r[y+1]) + 10 r[y];  dy = 3(t1[x-1]+t1[x+1]) + 10 t1[x],
 //             t1 = r[y+1]-r[y-1]; interleaved int16 (dx,dy), REFLECT_101.
 //
-// One CTA (4 warps) owns a 128x32 tile of level l.  The u8 tile plus halo (144x35 bytes) is fetched by a
+// One CTA (4 warps) owns a 128x32 tile of level l.  The u8 tile plus halo (160x35 bytes) is fetched by a
 // single TMA 3-D box (x, y, plane) that completes on an mbarrier; out-of-image halo bytes arrive as zeros
 // and edge tiles rewrite them with the REFLECT_101 mirror in shared memory.  Each lane then owns 4
 // adjacent columns and slides down 8 output rows: the horizontal taps are dp4a dot products on the packed
@@ -63,7 +63,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
-constexpr int kRowWords = kBoxW / 4;   // 36
+constexpr int kRowWords = kBoxW / 4;   // 40
+constexpr int kLaneWord0 = kHaloL / 4 - 1;   // word holding columns x-4..x-1 of lane 0
 constexpr int kRowsPerWarp = 8;
 
 // dp4a coefficient words (byte 0 = lowest address)
@@ -86,6 +87,7 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
     const int plane = planes.plane[blockIdx.z];
     const uint32_t bar_a = smem_u32(&bar);
 
+#ifndef PSNW_DEBUG_NO_TMA
     if (tid == 0) mbar_init(bar_a, 1);
     __syncthreads();
     if (tid == 0) {
@@ -93,17 +95,28 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
         tma_load_3d(smem_u32(tile), &map, x0 - kHaloL, y0 - kHaloT, plane, bar_a);
     }
     mbar_wait(bar_a, 0);
+#else   // bring-up aid only (never built into libpsnw_klt.so): same tile contents through plain loads
+    (void)bar_a;
+    for (int i = tid; i < kBoxW * kBoxH; i += 128) {
+        const int r = i / kBoxW, c = i - r * kBoxW;
+        const int gx = x0 - kHaloL + c, gy = y0 - kHaloT + r;
+        uint8_t v = 0;
+        if (gx >= 0 && gy >= 0 && gx < cur.w && gy < cur.h) v = cur.img[(size_t)plane * cur.plane_px + (size_t)gy * cur.pitch + gx];
+        reinterpret_cast<uint8_t *>(tile)[i] = v;
+    }
+    __syncthreads();
+#endif
 
     // ---- REFLECT_101 fix-up of halo bytes that fell outside the image (TMA wrote zeros there) ----
     const int W = cur.w, H = cur.h;
-    const bool edge_l = (x0 == 0), edge_r = (W - x0 + 5 < kBoxW);
+    const bool edge_l = (x0 == 0), edge_r = (W - x0 + kHaloL + 1 < kBoxW);
     const bool edge_t = (y0 == 0), edge_b = (H - y0 + 2 < kBoxH);
     if (edge_l || edge_r || edge_t || edge_b) {
         uint8_t *tb = reinterpret_cast<uint8_t *>(tile);
         if (edge_l || edge_r) {
             if (tid < kBoxH) {
                 uint8_t *row = tb + tid * kBoxW;
-                if (edge_l) { row[3] = row[5]; row[2] = row[6]; }                 // x=-1 <- 1, x=-2 <- 2
+                if (edge_l) { row[kHaloL - 1] = row[kHaloL + 1]; row[kHaloL - 2] = row[kHaloL + 2]; }   // x=-1 <- 1, x=-2 <- 2
                 if (edge_r) {
                     const int c = W - x0 + kHaloL;                                  // column of x = W
                     row[c] = row[c - 2];                                            // x=W   <- W-2
@@ -126,7 +139,7 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
     }
 
     const int warp = tid >> 5, lane = tid & 31;
-    const uint32_t *base = tile + (warp * kRowsPerWarp) * kRowWords + lane;   // words (prev, cur, next) = base[0..2]
+    const uint32_t *base = tile + (warp * kRowsPerWarp) * kRowWords + kLaneWord0 + lane;   // words (prev, cur, next) = base[0..2]
     const int ybase = y0 + warp * kRowsPerWarp;                               // first output row of this warp
 
     int hd[3][4], hs[3][4];     // horizontal difference / 3-10-3 smooth of the last three rows

@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsnw_klt.so")
+LIB_PATH = os.environ.get("PSNW_KLT_LIB") or os.path.join(_HERE, "libpsnw_klt.so")
 
 OK, EARG, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4
 MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2

@@ -1,0 +1,103 @@
+"""GPU tier: K4 (LocalSearchKLT box motion, bit-exact in double) and K5 (Shi-Tomasi detect) through the C ABI."""
+import numpy as np
+import pytest
+
+from mcmtt_opticalflow_b200 import klt, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = klt.KLTContext(256, 192, levels=3, max_points=1 << 17, max_targets=1 << 10)
+    yield c
+    c.close()
+
+
+def test_box_update_golden(ctx, golden):
+    off = np.concatenate([[0], np.cumsum(golden["ls_n"])]).astype(np.int32)
+    ioff = np.concatenate([[0], np.cumsum(golden["ls_inl_n"])])
+    boxes, mask, counts = ctx.box_update(golden["ls_box"], golden["ls_pre"], golden["ls_cur"], off)
+    assert np.array_equal(boxes, golden["ls_box_out"])           # bit-exact doubles
+    assert np.array_equal(counts, golden["ls_inl_n"])
+    for c in range(len(golden["ls_n"])):
+        inl = np.flatnonzero(mask[off[c]:off[c + 1]])
+        assert np.array_equal(inl, golden["ls_inl"][ioff[c]:ioff[c + 1]]), c
+
+
+def test_box_update_random_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(42)
+    n_t = 200
+    ns = rng.integers(0, 257, size=n_t)
+    ns[:3] = [0, 1, 256]
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    pre = rng.uniform(0, 1900, size=(off[-1], 2)).astype(np.float32)
+    cur = pre.copy()
+    boxes = np.stack([rng.uniform(0, 1800, n_t), rng.uniform(0, 900, n_t), rng.uniform(5, 140, n_t), rng.uniform(20, 330, n_t)], 1)
+    for t in range(n_t):
+        s = slice(off[t], off[t + 1])
+        kind = t % 4
+        d = rng.uniform(-8, 8, size=2)
+        if kind == 0:
+            cur[s] = pre[s] + d + rng.normal(0, 0.4, size=(ns[t], 2))
+        elif kind == 1:
+            cur[s] = pre[s] + np.round(rng.uniform(-2, 2, size=(ns[t], 2)) * 4) / 4       # many exact ties
+        elif kind == 2:
+            cur[s] = pre[s] + rng.normal(0, 0.06, size=(ns[t], 2))                        # around the 0.1 px gate
+        else:
+            cur[s] = pre[s] + d
+            k = ns[t] // 2
+            cur[off[t]:off[t] + k] = pre[off[t]:off[t] + k] + rng.uniform(-40, 40, size=(k, 2))
+    cur = cur.astype(np.float32)
+    status = (rng.random(off[-1]) < 0.8).astype(np.uint8)
+    for st in (None, status):
+        g_boxes, g_mask, g_counts = ctx.box_update(boxes, pre, cur, off, status=st)
+        for t in range(n_t):
+            s = slice(off[t], off[t + 1])
+            b, inl = oracle.local_search_klt(boxes[t], pre[s], cur[s], None if st is None else st[s])
+            assert np.array_equal(g_boxes[t], b), t
+            assert np.array_equal(np.flatnonzero(g_mask[s]), inl), t
+            assert g_counts[t] == len(inl)
+
+
+def test_min_eig_map_bit_exact_and_selection(golden, oracle):
+    a = golden["a"]
+    with klt.KLTContext(a.shape[1], a.shape[0], levels=2) as c:
+        c.push_frame(a)
+        eig = c.read_min_eig()
+        assert np.array_equal(eig, oracle.min_eig_map(a))                         # same float ops, same order
+        assert np.abs(eig - golden["eig_a"]).max() <= 2e-6 * golden["eig_a"].max()
+        boxes = golden["gftt_boxes"]
+        for si, (mc, q, md) in enumerate(golden["gftt_cfgs"]):
+            pts, counts = c.detect(boxes, int(mc), float(q), float(md))
+            for bi in range(len(boxes)):
+                got = pts[bi, :counts[bi]]
+                want = oracle.detect(a, boxes[bi], int(mc), float(q), float(md), eig=eig)
+                assert got.shape == want.shape and np.array_equal(got, want), (bi, si)
+                g = golden["gftt_%d_%d" % (bi, si)]                               # cv2: own map -> near-ties may reorder
+                assert len(set(map(tuple, got)) ^ set(map(tuple, g))) <= max(2, len(g) // 50), (bi, si)
+    t = golden["tie_img"]
+    with klt.KLTContext(64, 64, levels=1) as c:
+        c.push_frame(t)
+        pts, counts = c.detect([[0, 0, 200, 200]], 50, 0.01, 3.0)
+        assert np.array_equal(pts[0, :counts[0]], golden["tie_out"])               # exact ties: higher address first
+
+
+def test_detect_full_rig_vs_oracle(oracle):
+    w, h, ntgt = 768, 576, 40
+    cam = synth.Camera(w, h, ntgt, cam=4)
+    f = cam.frame(0)
+    with klt.KLTContext(w, h, levels=2) as c:
+        c.push_frame(f)
+        eig = c.read_min_eig()
+        assert np.array_equal(eig, oracle.min_eig_map(f))
+        boxes = cam.boxes(0)
+        pts, counts = c.detect(boxes, 100, 0.01, 3.0)
+        for t in range(ntgt):
+            want = oracle.detect(f, boxes[t], 100, 0.01, 3.0, eig=eig)
+            assert np.array_equal(pts[t, :counts[t]], want), t
+        pts, counts = c.detect([[0, 0, w, h]], 1000, 0.001, 1.0)                   # large candidate list (global scratch)
+        want = oracle.detect(f, [0, 0, w, h], 1000, 0.001, 1.0, eig=eig)
+        assert np.array_equal(pts[0, :counts[0]], want)
+        pts, counts = c.detect(np.zeros((0, 4)), 10)
+        assert counts.shape == (0,)

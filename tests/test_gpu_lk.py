@@ -1,0 +1,176 @@
+"""GPU tier: K2/K3 (pyramidal LK + fused forward-backward check) through the C ABI.
+
+Gates (north_star): status agreement >= 99.5 %, position within 0.05 px for >= 99 % of agreeing points -- against
+the cv2 fixtures; and a much tighter gate against the oracle in exact-sum mode, which performs the same
+arithmetic as the kernel (identical status, positions within 1e-4 px)."""
+import numpy as np
+import pytest
+
+from mcmtt_opticalflow_b200 import klt, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_PX = 0.05          # north_star position tolerance
+MIN_STATUS_AGREE = 0.995
+MIN_WITHIN_TOL = 0.99
+
+
+def _gate(o, st, g_o, g_st, tag=""):
+    assert (st == g_st).mean() >= MIN_STATUS_AGREE, tag
+    ok = (st == 1) & (g_st == 1)
+    if ok.any():
+        d = np.linalg.norm(o - g_o, axis=1)[ok]
+        assert (d <= TOL_PX).mean() >= MIN_WITHIN_TOL, (tag, float(d.max()))
+
+
+def _tight(o, st, er, g_o, g_st, g_er, tag=""):
+    assert np.array_equal(st, g_st), (tag, int((st != g_st).sum()))
+    d = np.linalg.norm(o - g_o, axis=1)
+    assert d.max() <= 1e-4, (tag, float(d.max()))
+    assert np.abs(er - g_er).max() <= 1e-5, tag
+
+
+def test_golden_single_direction(oracle, golden):
+    a, b, pts = golden["a"], golden["b"], golden["lk_pts"]
+    for i, (ww, wh, ml) in enumerate(golden["lk_cfgs"]):
+        ww, wh, ml = int(ww), int(wh), int(ml)
+        with klt.KLTContext(a.shape[1], a.shape[0], levels=ml + 1, win=(ww, wh), fb_thresh=-1.0) as ctx:
+            ctx.push_frame(a); ctx.push_frame(b)
+            o, st, er, _ = ctx.track(pts, slot_from=1, slot_to=0)
+        _gate(o, st, golden["lk_out_%d" % i], golden["lk_st_%d" % i], (ww, wh, ml))
+        pa, pb = oracle.build_pyramid(a, ml), oracle.build_pyramid(b, ml)
+        g_o, g_st, g_er = oracle.lk_track(pa, pb, pts, (ww, wh), ml, exact_sums=True)
+        _tight(o, st, er, g_o, g_st, g_er, (ww, wh, ml))
+
+
+def test_golden_forward_backward(oracle, golden):
+    a, b, pts = golden["a"], golden["b"], golden["lk_pts"]
+    with klt.KLTContext(a.shape[1], a.shape[0], levels=4, fb_thresh=1.0) as ctx:
+        ctx.push_frame(a); ctx.push_frame(b)
+        o, st, er, fb = ctx.track(pts)
+    _gate(o, st, golden["fb_out"], golden["fb_st"], "fb")
+    ok = (st == 1) & (golden["fb_st"] == 1)
+    assert np.abs(fb - golden["fb_err"])[ok].max() < TOL_PX
+    pa, pb = oracle.build_pyramid(a, 3), oracle.build_pyramid(b, 3)
+    g_o, g_st, g_er, g_fb = oracle.track_fb(pa, pb, pts, fb_thresh=1.0, exact_sums=True)
+    _tight(o, st, er, g_o, g_st, g_er, "fb")
+    assert np.abs(fb - g_fb).max() <= 1e-4
+
+
+def test_odd_frame_size(oracle, golden):
+    a, b, pts = golden["pyr_odd_0"], golden["odd_b"], golden["lk_pts"]
+    with klt.KLTContext(a.shape[1], a.shape[0], levels=4, fb_thresh=-1.0) as ctx:
+        ctx.push_frame(a); ctx.push_frame(b)
+        o, st, er, _ = ctx.track(pts)
+    _gate(o, st, golden["lk_odd_out"], golden["lk_odd_st"], "odd")
+
+
+def test_generic_and_w21_kernels_agree(golden):
+    """The 21x21 fast path and the generic kernel are the same arithmetic: results must be bit-identical."""
+    a, b, pts = golden["a"], golden["b"], golden["lk_pts"]
+    n = len(pts)
+    with klt.KLTContext(a.shape[1], a.shape[0], levels=4, fb_thresh=1.0) as ctx:
+        ctx.push_frame(a); ctx.push_frame(b)
+        o1, st1, er1, fb1 = ctx.track(pts)                                        # all 21x21 -> lk_w21_kernel
+        tgt = np.zeros(n, np.int32); tgt[-1] = 1
+        o2, st2, er2, fb2 = ctx.track(pts, target_of_pt=tgt, win_wh=[[21, 21], [23, 23]])   # mixed -> lk_generic_kernel
+    assert np.array_equal(o1[:-1], o2[:-1]) and np.array_equal(st1[:-1], st2[:-1])
+    assert np.array_equal(er1[:-1], er2[:-1]) and np.array_equal(fb1[:-1], fb2[:-1])
+
+
+@pytest.mark.parametrize("fb", [False, True])
+def test_c2_shaped_batch_vs_oracle(oracle, fb):
+    """BASELINE config C2 shape: 4 views 768x576, 40 targets x 100 seeds per view, one batched launch."""
+    w, h, ncam, ntgt, per = 768, 576, 4, 40, 100
+    cams = [synth.Camera(w, h, ntgt, cam=c, low_texture=(c == 3)) for c in range(ncam)]
+    with klt.KLTContext(w, h, n_cameras=ncam, levels=4, fb_thresh=1.0 if fb else -1.0, max_points=1 << 15) as ctx:
+        f0 = [c.frame(0) for c in cams]; f1 = [c.frame(1) for c in cams]
+        ctx.push_frames(f0); ctx.push_frames(f1)
+        jobs, keep = [], []
+        for c in range(ncam):
+            pts, tid = synth.seeds_in_boxes(cams[c].boxes(0), per, w, h, np.random.default_rng(100 + c))
+            n = len(pts)
+            j = dict(cam=c, slot_from=1, slot_to=0, n_pts=n, pts=pts, out=np.zeros((n, 2), np.float32),
+                     status=np.zeros(n, np.uint8), err=np.zeros(n, np.float32), fb_err=np.zeros(n, np.float32))
+            jobs.append(j); keep.append(pts)
+        ctx.track_batch(jobs)
+    agree, within, total = 0, 0, 0
+    for c in range(ncam):
+        pa, pb = oracle.build_pyramid(f0[c], 3), oracle.build_pyramid(f1[c], 3)
+        if fb:
+            g_o, g_st, g_er, g_fb = oracle.track_fb(pa, pb, keep[c], exact_sums=True)
+        else:
+            g_o, g_st, g_er = oracle.lk_track(pa, pb, keep[c], exact_sums=True)
+        j = jobs[c]
+        _tight(j["out"], j["status"], j["err"], g_o, g_st, g_er, ("cam", c))
+        if fb:
+            assert np.abs(j["fb_err"] - g_fb).max() <= 1e-4
+        assert j["status"].mean() > 0.5          # the synthetic texture is trackable
+
+
+def test_reference_faithful_per_target_windows(oracle):
+    """Reference call pattern: window (int)box.w x (int)box.h per target (Tracker2D.cpp:877), default 4 levels."""
+    w, h, ntgt = 768, 576, 12
+    cam = synth.Camera(w, h, ntgt, cam=9)
+    f0, f1 = cam.frame(0), cam.frame(1)
+    boxes = cam.boxes(0)
+    pts, tid = synth.seeds_in_boxes(boxes, 50, w, h, np.random.default_rng(5))
+    win = np.stack([boxes[:, 2].astype(np.int32), boxes[:, 3].astype(np.int32)], 1)
+    with klt.KLTContext(w, h, levels=4, fb_thresh=-1.0) as ctx:
+        ctx.push_frame(f0); ctx.push_frame(f1)
+        o, st, er, _ = ctx.track(pts, target_of_pt=tid, win_wh=win)
+    pa, pb = oracle.build_pyramid(f0, 3), oracle.build_pyramid(f1, 3)
+    for t in range(ntgt):
+        m = tid == t
+        g_o, g_st, g_er = oracle.lk_track(pa, pb, pts[m], (int(win[t, 0]), int(win[t, 1])), 3, exact_sums=True)
+        _tight(o[m], st[m], er[m], g_o, g_st, g_er, ("target", t, win[t]))
+
+
+def test_edge_cases(oracle):
+    w, h = 160, 120
+    rng = np.random.default_rng(0)
+    a = synth.Camera(w, h, 0, cam=1).frame(0)
+    flat = np.full((h, w), 128, np.uint8)
+    with klt.KLTContext(w, h, levels=3, fb_thresh=-1.0) as ctx:
+        ctx.push_frame(a); ctx.push_frame(a)
+        o, st, er, _ = ctx.track(np.zeros((0, 2), np.float32))                   # empty input
+        assert o.shape == (0, 2)
+        far = np.float32([[-500, -500], [1e6, 5], [w + 40, h + 40], [-11, 5], [w + 9.5, h / 2]])
+        o, st, er, _ = ctx.track(far)
+        pa = oracle.build_pyramid(a, 2)
+        g_o, g_st, g_er = oracle.lk_track(pa, pa, far, (21, 21), 2, exact_sums=True)
+        assert np.array_equal(st, g_st) and np.allclose(o, g_o, atol=1e-4)
+        pts = rng.uniform(0, [w, h], size=(64, 2)).astype(np.float32)            # identical frames: zero motion
+        o, st, er, _ = ctx.track(pts)
+        assert np.abs(o - pts)[st == 1].max() < 1e-3
+        ctx.push_frame(flat); ctx.push_frame(flat)                               # no texture: min-eig gate rejects all
+        o, st, er, _ = ctx.track(pts)
+        assert st.sum() == 0
+        with pytest.raises(klt.PsnwError):
+            ctx.track(pts, win_wh=[[w, 5]])                                      # window >= frame
+    with klt.KLTContext(w, h, levels=3) as ctx:
+        with pytest.raises(klt.PsnwError) as e:
+            ctx.track(np.zeros((4, 2), np.float32))                              # ring empty
+        assert e.value.code == klt.ESTATE
+
+
+def test_linearity_property_at_full_size():
+    """Size-independent property at C3 size (1080p, 51 200 seeds): a frame translated by an integer offset must be
+    tracked to p + offset away from the borders, and tracking a frame onto itself must return p."""
+    w, h = 1920, 1080
+    cam = synth.Camera(w, h, 0, cam=2)
+    a = cam.frame(0)
+    dx, dy = 3, -2
+    b = np.roll(np.roll(a, dy, axis=0), dx, axis=1)
+    rng = np.random.default_rng(1)
+    pts = rng.uniform([60, 60], [w - 60, h - 60], size=(51200, 2)).astype(np.float32)
+    with klt.KLTContext(w, h, levels=4, fb_thresh=1.0, max_points=1 << 16) as ctx:
+        ctx.push_frame(a); ctx.push_frame(b)
+        o, st, er, fb = ctx.track(pts)
+        assert st.mean() > 0.97
+        d = o[st == 1] - pts[st == 1] - np.float32([dx, dy])
+        assert np.percentile(np.abs(d), 99) < 0.05
+        assert (fb[st == 1] <= 1.0).all()
+        ctx.push_frame(b)
+        o2, st2, _, _ = ctx.track(pts)
+        assert np.abs(o2 - pts)[st2 == 1].max() < 1e-3

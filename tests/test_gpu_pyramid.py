@@ -1,0 +1,107 @@
+"""GPU tier: K1 (pyrDown + Scharr, TMA-staged) must be BIT-EXACT with the oracle / cv2 fixtures.  All calls go
+through the C ABI (mcmtt_opticalflow_b200.klt -> libpsnw_klt.so)."""
+import numpy as np
+import pytest
+
+from mcmtt_opticalflow_b200 import klt, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_levels(ctx, oracle, img, cam=0, slot=0):
+    cur = img
+    for l in range(ctx.levels):
+        if l:
+            cur = oracle.pyr_down(cur)
+        g_img, g_dxy = ctx.read_level(cam, slot, l)
+        assert g_img.shape == cur.shape
+        assert np.array_equal(g_img, cur), "u8 level %d differs" % l
+        assert np.array_equal(g_dxy, oracle.scharr(cur)), "Scharr level %d differs" % l
+
+
+@pytest.mark.parametrize("w,h,levels", [(768, 576, 4), (767, 575, 4), (129, 33, 3), (16, 16, 2), (130, 70, 3),
+                                        (1920, 1080, 4), (257, 131, 5), (640, 480, 6)])
+def test_bit_exact_vs_oracle(oracle, w, h, levels):
+    rng = np.random.default_rng(w * 1000 + h)
+    img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    with klt.KLTContext(w, h, n_cameras=1, levels=levels) as ctx:
+        ctx.push_frame(img)
+        _check_levels(ctx, oracle, img)
+
+
+def test_golden_fixture(golden):
+    a = golden["a"]
+    with klt.KLTContext(a.shape[1], a.shape[0], levels=4) as ctx:
+        ctx.push_frame(a)
+        for l in range(4):
+            img, dxy = ctx.read_level(0, 0, l)
+            assert np.array_equal(img, golden["pyr_a_%d" % l])
+            assert np.array_equal(dxy[..., 0], golden["dx_a_%d" % l])
+            assert np.array_equal(dxy[..., 1], golden["dy_a_%d" % l])
+    o = golden["pyr_odd_0"]
+    with klt.KLTContext(o.shape[1], o.shape[0], levels=4) as ctx:
+        ctx.push_frame(o)
+        for l in range(4):
+            img, dxy = ctx.read_level(0, 0, l)
+            assert np.array_equal(img, golden["pyr_odd_%d" % l])
+            assert np.array_equal(dxy[..., 0], golden["dx_odd_%d" % l])
+            assert np.array_equal(dxy[..., 1], golden["dy_odd_%d" % l])
+
+
+def test_batched_cameras_and_ring_rotation(oracle):
+    w, h, ncam = 384, 288, 3
+    cams = [synth.Camera(w, h, 4, cam=c) for c in range(ncam)]
+    with klt.KLTContext(w, h, n_cameras=ncam, levels=3) as ctx:
+        frames = {}
+        for t in range(6):                                   # ring of 4: frames 2..5 survive
+            fr = [c.frame(t) for c in cams]
+            frames[t] = fr
+            ctx.push_frames(fr, frame_idx=t)
+            assert ctx.frames_held(0) == min(t + 1, 4)
+        for c in range(ncam):
+            for slot in range(4):                            # slot k == k frames ago (Tracker2D.cpp:311-316)
+                _check_levels(ctx, oracle, frames[5 - slot][c], cam=c, slot=slot)
+        # pushing a subset of cameras only rotates those
+        ctx.push_frames([frames[0][1]], cams=[1])
+        _check_levels(ctx, oracle, frames[0][1], cam=1, slot=0)
+        _check_levels(ctx, oracle, frames[5][1], cam=1, slot=1)
+        _check_levels(ctx, oracle, frames[5][0], cam=0, slot=0)
+
+
+def test_pitched_host_input(oracle):
+    w, h = 200, 100
+    big = np.random.default_rng(1).integers(0, 256, size=(h, 512), dtype=np.uint8)
+    view = big[:, :w]
+    with klt.KLTContext(w, h, levels=2) as ctx:
+        import ctypes as C
+        cams = np.zeros(1, np.int32)
+        ptrs = (C.c_void_p * 1)(view.ctypes.data)
+        assert ctx.lib.psnw_push_frames(ctx._h, 1, cams.ctypes.data, ptrs, 512, 0, klt.MEM_HOST) == 0
+        _check_levels(ctx, oracle, np.ascontiguousarray(view))
+
+
+@pytest.mark.parametrize("bits", [14, 15])
+def test_bgr_intake(oracle, bits):
+    w, h = 321, 123
+    bgr = np.random.default_rng(2).integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    b, g, r = [bgr[..., i].astype(np.int64) for i in range(3)]
+    if bits == 15:
+        gray = (3735 * b + 19235 * g + 9798 * r + (1 << 14)) >> 15
+    else:
+        gray = (1868 * b + 9617 * g + 4899 * r + (1 << 13)) >> 14
+    gray = gray.astype(np.uint8)
+    with klt.KLTContext(w, h, levels=3) as ctx:
+        ctx.push_frames_bgr([bgr], luma_bits=bits)
+        _check_levels(ctx, oracle, gray)
+
+
+def test_errors():
+    with klt.KLTContext(64, 64, levels=2) as ctx:
+        with pytest.raises(klt.PsnwError) as e:
+            ctx.read_level(0, 0, 0)                          # nothing pushed yet
+        assert e.value.code == klt.ESTATE
+        with pytest.raises(klt.PsnwError) as e:
+            ctx.push_frames([np.zeros((64, 64), np.uint8)] * 2, cams=[0, 0])
+        assert e.value.code == klt.EARG
+    with pytest.raises(klt.PsnwError):
+        klt.KLTContext(4, 4)
