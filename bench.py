@@ -164,6 +164,7 @@ class GpuRig:
         self.which = 0
         self.step_idx = 0
         self._job_cache = {}
+        self._det_cache = {}
 
     # -- helpers ---------------------------------------------------------------------------------------
     def _jobs(self, seeds_ptr, out_ptr, st_ptr, err_ptr, fb_ptr, slot_from=1, slot_to=0):
@@ -188,11 +189,18 @@ class GpuRig:
         self.ctx._ck(self.ctx.lib.psnw_push_frames(self.ctx._h, self.ncam, self.cams.ctypes.data, ptrs, self.w, t_idx, mem))
 
     def _detect(self, t_idx, seeds, counts, mem):
-        lib, h = self.ctx.lib, self.ctx._h
-        for c in range(self.ncam):
-            b = self.boxes[c][t_idx]
-            self.ctx._ck(lib.psnw_klt_detect(h, c, 0, b.ctypes.data, self.ntgt, self.per, QUALITY, MIN_DIST,
-                                             seeds.data_ptr() + c * self.npts_cam * 8, counts.data_ptr() + c * self.ntgt * 4, mem))
+        """Shi-Tomasi seeds inside the detection boxes of frame t_idx, all cameras in one batched call."""
+        key = (t_idx, seeds.data_ptr())
+        jobs = self._det_cache.get(key)
+        if jobs is None:
+            jobs = (self.klt.DetectJob * self.ncam)()
+            for c in range(self.ncam):
+                j = jobs[c]
+                j.cam, j.slot, j.boxes, j.n_targets = c, 0, self.boxes[c][t_idx].ctypes.data, self.ntgt
+                j.pts_xy = seeds.data_ptr() + c * self.npts_cam * 8
+                j.counts = counts.data_ptr() + c * self.ntgt * 4
+            self._det_cache[key] = jobs
+        self.ctx._ck(self.ctx.lib.psnw_klt_detect_batch(self.ctx._h, jobs, self.ncam, self.per, QUALITY, MIN_DIST, mem))
 
     def prime(self, host):
         """First frame + first seeds so that every timed step has a previous frame to track from."""

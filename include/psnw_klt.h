@@ -119,6 +119,18 @@ PSNW_API int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *box
                              int max_per_target, float quality, float min_dist,
                              float *pts_xy, int *counts, int mem_flags);
 
+typedef struct psnw_detect_job {
+    int cam, slot;
+    const double *boxes;     /* [n_targets][4], host memory */
+    int n_targets;
+    float *pts_xy;           /* [n_targets][max_per_target][2] */
+    int *counts;             /* [n_targets] */
+} psnw_detect_job;
+
+/* Several psnw_klt_detect calls (different cameras) as one launch: CPSNWhere::TrackPeople's camera loop. */
+PSNW_API int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs, int max_per_target,
+                                   float quality, float min_dist, int mem_flags);
+
 /*
  * Sparse pyramidal LK from ring slot `slot_from` to `slot_to` of camera `cam` (replaces
  * cv::calcOpticalFlowPyrLK at .cpp:776-782 [slot_from = newer frame] and :871-877 [slot_from = 1, slot_to = 0]).

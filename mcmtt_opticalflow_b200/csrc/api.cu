@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -476,6 +477,8 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     P.n_jobs = n_jobs; P.n_pts = total;
     P.max_iters = ctx->p.max_iters;
     P.eps2 = ctx->p.epsilon * ctx->p.epsilon;
+    P.eps2_lo = (float)(P.eps2 * (1.0 - 1e-5));
+    P.eps2_hi = (float)(P.eps2 * (1.0 + 1e-5));
     P.min_eig = ctx->p.min_eig_thresh;
     P.fb_thresh = ctx->p.fb_thresh;
     P.do_fb = do_fb ? 1 : 0;
@@ -560,84 +563,134 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
     return PSNW_OK;
 }
 
-static int ensure_min_eig(psnw_ctx *ctx, int cam, int slot, float **eig_out)
+// min-eigenvalue maps of the (cam, slot) frames in `cs`, computed once per pushed frame (tag = push sequence)
+static int ensure_min_eig(psnw_ctx *ctx, const std::vector<std::pair<int, int>> &cs)
 {
     const LevelGeom &l0 = ctx->pyr.lv[0];
-    const int plane = plane_of(ctx, cam, slot);
-    if (!ctx->eig[cam]) {
-        if (cudaMalloc(&ctx->eig[cam], sizeof(float) * (size_t)l0.plane_px) != cudaSuccess)
-            return fail(ctx, PSNW_ENOMEM, "cudaMalloc min-eig map", cudaGetLastError());
-        ctx->eig_tag[cam] = 0;
+    EigList el;
+    el.n = 0;
+    for (const auto &c : cs) {
+        const int cam = c.first, plane = plane_of(ctx, cam, c.second);
+        if (!ctx->eig[cam]) {
+            if (cudaMalloc(&ctx->eig[cam], sizeof(float) * (size_t)l0.plane_px) != cudaSuccess)
+                return fail(ctx, PSNW_ENOMEM, "cudaMalloc min-eig map", cudaGetLastError());
+            ctx->eig_tag[cam] = 0;
+        }
+        if (ctx->eig_tag[cam] == ctx->plane_seq[plane]) continue;
+        ctx->eig_tag[cam] = ctx->plane_seq[plane];
+        el.plane[el.n] = plane;
+        el.eig[el.n] = ctx->eig[cam];
+        if (++el.n == 24) {
+            const int r = launch_min_eig(l0, el, ctx->stream);
+            if (r < 0) return fail(ctx, PSNW_ECUDA, "min_eig_kernel launch", cudaGetLastError());
+            ctx->launches += r;
+            el.n = 0;
+        }
     }
-    if (ctx->eig_tag[cam] != ctx->plane_seq[plane]) {
-        const int r = launch_min_eig(l0, plane, ctx->eig[cam], ctx->stream);
+    if (el.n) {
+        const int r = launch_min_eig(l0, el, ctx->stream);
         if (r < 0) return fail(ctx, PSNW_ECUDA, "min_eig_kernel launch", cudaGetLastError());
         ctx->launches += r;
-        ctx->eig_tag[cam] = ctx->plane_seq[plane];
     }
-    *eig_out = ctx->eig[cam];
+    return PSNW_OK;
+}
+
+int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs, int max_per_target,
+                          float quality, float min_dist, int mem_flags)
+{
+    if (!ctx) return PSNW_EARG;
+    if (n_jobs <= 0) return PSNW_OK;
+    if (!jobs || max_per_target < 1 || !(quality > 0.f) || min_dist < 0.f) return fail(ctx, PSNW_EARG, "psnw_klt_detect arguments");
+    int total = 0;
+    std::vector<std::pair<int, int>> cs;
+    for (int j = 0; j < n_jobs; ++j) {
+        const psnw_detect_job &J = jobs[j];
+        if (J.n_targets < 0 || (J.n_targets > 0 && (!J.boxes || !J.pts_xy || !J.counts))) return fail(ctx, PSNW_EARG, "psnw_klt_detect: bad job arrays");
+        if (J.n_targets == 0) continue;
+        if (!slot_ok(ctx, J.cam, J.slot)) return fail(ctx, PSNW_ESTATE, "psnw_klt_detect: camera/slot holds no frame");
+        for (int k = 0; k < j; ++k)
+            if (jobs[k].n_targets > 0 && jobs[k].cam == J.cam && jobs[k].slot != J.slot)
+                return fail(ctx, PSNW_EARG, "psnw_klt_detect_batch: one slot per camera per call");
+        total += J.n_targets;
+        cs.emplace_back(J.cam, J.slot);
+    }
+    if (total == 0) return PSNW_OK;
+    if (total > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_klt_detect: max_targets exceeded");
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    int rc = ensure_min_eig(ctx, cs);
+    if (rc) return rc;
+
+    // mask ROI = box.cropWithSize(cols, rows).cv()  (PSNWhere_Types.h:146-153,181; Tracker2D.cpp:735).  `boxes` is
+    // always host memory: detections come from the host-side detector files (PSNWhere.cpp:261).
+    const bool dev = mem_flags == PSNW_MEM_DEVICE;
+    const size_t tb = (sizeof(DetectTarget) * total + 255) & ~(size_t)255;
+    const size_t out_b = dev ? 0 : (((size_t)total * max_per_target * sizeof(float2) + 255) & ~(size_t)255);
+    const size_t cnt_b = dev ? 0 : ((sizeof(int) * total + 255) & ~(size_t)255);
+    rc = ensure(ctx, ctx->desc, tb + out_b + cnt_b);
+    if (rc) return rc;
+    float2 *s_out = reinterpret_cast<float2 *>(ctx->desc.p + tb);
+    int *s_cnt = reinterpret_cast<int *>(ctx->desc.p + tb + out_b);
+
+    std::vector<DetectTarget> T(total);
+    size_t cand_total = 0;
+    int max_area = 1, max_tile = 1, t0 = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const psnw_detect_job &J = jobs[j];
+        for (int t = 0; t < J.n_targets; ++t) {
+            const double x = J.boxes[4 * t], y = J.boxes[4 * t + 1], w = J.boxes[4 * t + 2], h = J.boxes[4 * t + 3];
+            const double nx = std::max(0.0, x), ny = std::max(0.0, y);
+            const double nw = std::min((double)l0.w - nx - 1, w), nh = std::min((double)l0.h - ny - 1, h);
+            DetectTarget &d = T[t0 + t];
+            d.x0 = (int)nx; d.y0 = (int)ny;
+            d.x1 = d.x0 + std::max((int)nw, 0); d.y1 = d.y0 + std::max((int)nh, 0);
+            d.x0 = std::min(d.x0, l0.w); d.y0 = std::min(d.y0, l0.h);
+            d.x1 = std::min(std::max(d.x1, d.x0), l0.w); d.y1 = std::min(std::max(d.y1, d.y0), l0.h);
+            d.cand_begin = (int)cand_total;
+            d.cand_cap = (d.x1 - d.x0) * (d.y1 - d.y0);
+            cand_total += (size_t)d.cand_cap;
+            max_area = std::max(max_area, d.cand_cap);
+            max_tile = std::max(max_tile, (d.x1 - d.x0 + 2) * (d.y1 - d.y0 + 2));
+            d.eig = ctx->eig[J.cam];
+            d.out = dev ? reinterpret_cast<float2 *>(J.pts_xy) + (size_t)t * max_per_target : s_out + (size_t)(t0 + t) * max_per_target;
+            d.count = dev ? J.counts + t : s_cnt + t0 + t;
+        }
+        t0 += J.n_targets;
+    }
+    if (cand_total > ((size_t)1 << 30)) return fail(ctx, PSNW_ENOMEM, "psnw_klt_detect: candidate scratch too large");
+    rc = ensure(ctx, ctx->cand, cand_total * sizeof(unsigned long long) + 256);
+    if (rc) return rc;
+    StageSlot *s;
+    rc = stage_acquire(ctx, tb, &s);
+    if (rc) return rc;
+    memcpy(s->h, T.data(), sizeof(DetectTarget) * total);
+    rc = stage_upload(ctx, s, ctx->desc.p, sizeof(DetectTarget) * total);
+    if (rc) return rc;
+    const int r = launch_detect_select(l0.w, l0.h, l0.pitch, reinterpret_cast<const DetectTarget *>(ctx->desc.p), total,
+                                       max_per_target, quality, min_dist, reinterpret_cast<unsigned long long *>(ctx->cand.p),
+                                       max_area, max_tile, ctx->stream);
+    if (r < 0) return fail(ctx, PSNW_ECUDA, "detect_select_kernel launch", cudaGetLastError());
+    ctx->launches += r;
+    if (!dev) {
+        t0 = 0;
+        for (int j = 0; j < n_jobs; ++j) {
+            const psnw_detect_job &J = jobs[j];
+            if (J.n_targets == 0) continue;
+            CK(cudaMemcpyAsync(J.pts_xy, s_out + (size_t)t0 * max_per_target, (size_t)J.n_targets * max_per_target * sizeof(float2),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(J.counts, s_cnt + t0, sizeof(int) * J.n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+            t0 += J.n_targets;
+        }
+        if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    }
     return PSNW_OK;
 }
 
 int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n_targets, int max_per_target,
                     float quality, float min_dist, float *pts_xy, int *counts, int mem_flags)
 {
-    if (!ctx) return PSNW_EARG;
-    if (n_targets == 0) return PSNW_OK;
-    if (n_targets < 0 || max_per_target < 1 || !boxes || !pts_xy || !counts || !(quality > 0.f) || min_dist < 0.f)
-        return fail(ctx, PSNW_EARG, "psnw_klt_detect arguments");
-    if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_klt_detect: camera/slot holds no frame");
-    if (n_targets > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_klt_detect: max_targets exceeded");
-    const LevelGeom &l0 = ctx->pyr.lv[0];
-    float *eig;
-    int rc = ensure_min_eig(ctx, cam, slot, &eig);
-    if (rc) return rc;
-
-    // mask ROI = box.cropWithSize(cols, rows).cv()  (PSNWhere_Types.h:146-153,181; Tracker2D.cpp:735).  `boxes` is
-    // always host memory: detections come from the host-side detector files (PSNWhere.cpp:261).
-    std::vector<DetectTarget> T(n_targets);
-    size_t cand_total = 0;
-    for (int t = 0; t < n_targets; ++t) {
-        const double x = boxes[4 * t], y = boxes[4 * t + 1], w = boxes[4 * t + 2], h = boxes[4 * t + 3];
-        const double nx = std::max(0.0, x), ny = std::max(0.0, y);
-        const double nw = std::min((double)l0.w - nx - 1, w), nh = std::min((double)l0.h - ny - 1, h);
-        DetectTarget &d = T[t];
-        d.x0 = (int)nx; d.y0 = (int)ny;
-        d.x1 = d.x0 + std::max((int)nw, 0); d.y1 = d.y0 + std::max((int)nh, 0);
-        d.x0 = std::min(d.x0, l0.w); d.y0 = std::min(d.y0, l0.h);
-        d.x1 = std::min(std::max(d.x1, d.x0), l0.w); d.y1 = std::min(std::max(d.y1, d.y0), l0.h);
-        d.cand_begin = (int)cand_total;
-        d.cand_cap = (d.x1 - d.x0) * (d.y1 - d.y0);
-        cand_total += (size_t)d.cand_cap;
-    }
-    if (cand_total > ((size_t)1 << 30)) return fail(ctx, PSNW_ENOMEM, "psnw_klt_detect: candidate scratch too large");
-    rc = ensure(ctx, ctx->cand, cand_total * sizeof(unsigned long long) + 256);
-    if (rc) return rc;
-    const bool dev = mem_flags == PSNW_MEM_DEVICE;
-    const size_t n_out = (size_t)n_targets * max_per_target;
-    const size_t tb = (sizeof(DetectTarget) * n_targets + 255) & ~(size_t)255;
-    const size_t need = tb + (dev ? 0 : n_out * sizeof(float2) + 256 + sizeof(int) * n_targets + 256);
-    rc = ensure(ctx, ctx->desc, need);
-    if (rc) return rc;
-    StageSlot *s;
-    rc = stage_acquire(ctx, tb, &s);
-    if (rc) return rc;
-    memcpy(s->h, T.data(), sizeof(DetectTarget) * n_targets);
-    rc = stage_upload(ctx, s, ctx->desc.p, sizeof(DetectTarget) * n_targets);
-    if (rc) return rc;
-    float2 *d_out = dev ? reinterpret_cast<float2 *>(pts_xy) : reinterpret_cast<float2 *>(ctx->desc.p + tb);
-    int *d_cnt = dev ? counts : reinterpret_cast<int *>(ctx->desc.p + tb + ((n_out * sizeof(float2) + 255) & ~(size_t)255));
-    const int r = launch_detect_select(eig, l0.w, l0.h, l0.pitch, reinterpret_cast<const DetectTarget *>(ctx->desc.p), n_targets,
-                                       max_per_target, quality, min_dist, reinterpret_cast<unsigned long long *>(ctx->cand.p),
-                                       d_out, d_cnt, ctx->stream);
-    if (r < 0) return fail(ctx, PSNW_ECUDA, "detect_select_kernel launch", cudaGetLastError());
-    ctx->launches += r;
-    if (!dev) {
-        CK(cudaMemcpyAsync(pts_xy, d_out, n_out * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(counts, d_cnt, sizeof(int) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
-        if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
-    }
-    return PSNW_OK;
+    psnw_detect_job j;
+    j.cam = cam; j.slot = slot; j.boxes = boxes; j.n_targets = n_targets; j.pts_xy = pts_xy; j.counts = counts;
+    return psnw_klt_detect_batch(ctx, &j, 1, max_per_target, quality, min_dist, mem_flags);
 }
 
 int psnw_sync(psnw_ctx *ctx)
@@ -679,9 +732,9 @@ int psnw_read_min_eig(psnw_ctx *ctx, int cam, int slot, float *eig_out)
     if (!ctx || !eig_out) return PSNW_EARG;
     if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_read_min_eig: camera/slot holds no frame");
     const LevelGeom &l0 = ctx->pyr.lv[0];
-    float *eig;
-    const int rc = ensure_min_eig(ctx, cam, slot, &eig);
+    const int rc = ensure_min_eig(ctx, {{cam, slot}});
     if (rc) return rc;
+    float *eig = ctx->eig[cam];
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy2D(eig_out, (size_t)l0.w * 4, eig, (size_t)l0.pitch * 4, (size_t)l0.w * 4, l0.h, cudaMemcpyDeviceToHost));
     return PSNW_OK;

@@ -54,6 +54,7 @@ struct LkParams {
     int n_jobs, n_pts;
     int max_iters;
     double eps2;
+    float eps2_lo, eps2_hi;   // eps2 * (1 -/+ 1e-5): outside this band the float value decides the epsilon test
     float min_eig;
     float fb_thresh;
     int do_fb;
@@ -68,15 +69,23 @@ int launch_lk(const LkParams &P, int all_21x21, int max_win_px, cudaStream_t str
 int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
                       const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,
                       int *counts, int max_pts_per_target, cudaStream_t stream);
-int launch_min_eig(const LevelGeom &l0, int plane, float *eig, cudaStream_t stream);
+struct EigList {
+    int n;
+    int plane[24];
+    float *eig[24];
+};
+int launch_min_eig(const LevelGeom &l0, const EigList &list, cudaStream_t stream);
 
 struct DetectTarget {
     int x0, y0, x1, y1;        // cropped ROI, half open
     int cand_begin, cand_cap;  // slice of the candidate scratch
+    const float *eig;          // min-eigenvalue map of the target's camera (level-0 pitch)
+    float2 *out;               // [max_per_target]
+    int *count;
 };
-int launch_detect_select(const float *eig, int w, int h, int pitch, const DetectTarget *targets, int n_targets,
+int launch_detect_select(int w, int h, int pitch, const DetectTarget *targets, int n_targets,
                          int max_per_target, float quality, float min_dist, unsigned long long *cand,
-                         float2 *out, int *counts, cudaStream_t stream);
+                         int max_roi_area, int max_tile_px, cudaStream_t stream);
 
 // tile geometry of the pyramid kernel (the TMA box must match on host and device)
 constexpr int kTileW = 128, kTileH = 32;

@@ -9,9 +9,10 @@
 //   min_eig_kernel        dense fp32 map of level 0, HBM-bound: reads N bytes, writes 4N.  Float operations
 //                         are kept in the oracle's order (sequential 3x3 sums, unfused) so the map is
 //                         bit-identical to oracle/klt_oracle.c::psnwo_min_eig_map.
-//   detect_select_kernel  one CTA per target: max-reduce over the ROI, candidate compaction, then
-//                         max_per_target rounds of block-wide arg-max + distance suppression in shared memory
-//                         (equivalent to sort + sequential greedy filter, without the sort).
+//   detect_select_kernel  one CTA per target: max-reduce over the ROI, candidate compaction into shared memory,
+//                         bitonic sort, then one warp walks the sorted list 32 candidates at a time (distance test
+//                         against the accepted list + in-order ballot resolution).  Lists that do not fit take
+//                         max_per_target rounds of block-wide arg-max over a global-memory list instead.
 #include <float.h>
 
 #include "common.cuh"
@@ -32,8 +33,10 @@ __device__ __forceinline__ int refl_clamp(int p, int n)
 }
 
 __global__ void __launch_bounds__(256)
-min_eig_kernel(const uint8_t *__restrict__ img, int w, int h, int pitch, float *__restrict__ eig)
+min_eig_kernel(const uint8_t *__restrict__ img_base, int w, int h, int pitch, int plane_px, const EigList list)
 {
+    const uint8_t *__restrict__ img = img_base + (size_t)list.plane[blockIdx.z] * plane_px;
+    float *__restrict__ eig = list.eig[blockIdx.z];
     __shared__ uint8_t src[kSrcH][kSrcW];
     __shared__ float pxx[kPrH][kPrW], pxy[kPrH][kPrW], pyy[kPrH][kPrW];
     const int tid = threadIdx.x;
@@ -85,7 +88,7 @@ min_eig_kernel(const uint8_t *__restrict__ img, int w, int h, int pitch, float *
 
 constexpr int kSelThreads = 256;
 constexpr float kUnusedSlot = -1.0e6f;
-constexpr int kSmemCand = 4096;
+constexpr int kMaxAccepted = 1024;        // accepted-corner list kept in shared memory by the sorted path
 
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 {
@@ -97,35 +100,57 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
+// key = (float bits of the score << 32) | raster index: scores are positive, so unsigned order == (score, address)
+// order and "largest key first" is exactly cv2's greaterThanPtr (score descending, ties: higher address first).
 __global__ void __launch_bounds__(kSelThreads)
-detect_select_kernel(const float *__restrict__ eig, int w, int h, int pitch, const DetectTarget *__restrict__ targets,
+detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ targets,
                      int max_per_target, float quality, float min_dist, unsigned long long *__restrict__ cand_all,
-                     float2 *__restrict__ out, int *__restrict__ counts)
+                     int smem_cap, int tile_cap)
 {
-    __shared__ unsigned long long s_list[kSmemCand];
+    extern __shared__ __align__(16) unsigned long long s_list[];      // smem_cap keys (power of two), then the ROI tile
     __shared__ unsigned long long s_red[kSelThreads / 32];
     __shared__ float s_maxw[kSelThreads / 32];
-    __shared__ int s_nc;
+    __shared__ unsigned s_acc[kMaxAccepted];
+    __shared__ int s_nc, s_nout;
 
     const DetectTarget T = targets[blockIdx.x];
+    const float *__restrict__ eig = T.eig;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nwarps = kSelThreads / 32;
-    float2 *my_out = out + (size_t)blockIdx.x * max_per_target;
+    float2 *my_out = T.out;
+    float *tile = reinterpret_cast<float *>(s_list + smem_cap);
 
     if (T.x1 <= T.x0 || T.y1 <= T.y0 || max_per_target <= 0) {
-        if (tid == 0) counts[blockIdx.x] = 0;
+        if (tid == 0) *T.count = 0;
         for (int i = tid; i < max_per_target; i += kSelThreads) my_out[i] = make_float2(kUnusedSlot, kUnusedSlot);
         return;
     }
+    if (tid == 0) { s_nc = 0; s_nout = 0; }
+
+    // 0. ROI plus a one-pixel ring (inside the frame) into shared memory: many loads in flight instead of one
+    //    dependent load per loop trip.  ROIs that do not fit read the map through L1 instead.
+    const int tx0 = max(T.x0 - 1, 0), ty0 = max(T.y0 - 1, 0), tx1 = min(T.x1 + 1, w), ty1 = min(T.y1 + 1, h);
+    const int tw = tx1 - tx0, th = ty1 - ty0;
+    const bool tiled = tw * th <= tile_cap;
+    if (tiled) {
+#pragma unroll 4
+        for (int y = warp; y < th; y += nwarps) {
+            const float *src = eig + (size_t)(ty0 + y) * pitch + tx0;
+            for (int x = lane; x < tw; x += 32) tile[y * tw + x] = src[x];
+        }
+    }
+    __syncthreads();
+    const float *mp = tiled ? tile - (ty0 * tw + tx0) : eig;     // map pointer such that mp[y * ms + x] is pixel (x, y)
+    const int ms = tiled ? tw : pitch;
 
     // 1. max of the map under the mask
     float m = -FLT_MAX;
+#pragma unroll 2
     for (int y = T.y0 + warp; y < T.y1; y += nwarps)
-        for (int x = T.x0 + lane; x < T.x1; x += 32) m = fmaxf(m, eig[(size_t)y * pitch + x]);
+        for (int x = T.x0 + lane; x < T.x1; x += 32) m = fmaxf(m, mp[y * ms + x]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) s_maxw[warp] = m;
-    if (tid == 0) s_nc = 0;
     __syncthreads();
     m = s_maxw[0];
 #pragma unroll
@@ -137,7 +162,7 @@ detect_select_kernel(const float *__restrict__ eig, int w, int h, int pitch, con
     const int cx0 = max(T.x0, 1), cx1 = min(T.x1, w - 1), cy0 = max(T.y0, 1), cy1 = min(T.y1, h - 1);
     for (int y = cy0 + warp; y < cy1; y += nwarps)
         for (int x = cx0 + lane; x < cx1; x += 32) {
-            const float *p = eig + (size_t)y * pitch + x;
+            const float *p = mp + y * ms + x;
             const float v = p[0];
             if (!(v > thr)) continue;
             bool is_max = true;
@@ -145,83 +170,160 @@ detect_select_kernel(const float *__restrict__ eig, int w, int h, int pitch, con
             for (int j = -1; j <= 1; ++j)
 #pragma unroll
                 for (int i = -1; i <= 1; ++i) {
-                    float u = p[j * pitch + i];
+                    float u = p[j * ms + i];
                     u = (u > thr) ? u : 0.f;
                     is_max = is_max && !(u > v);
                 }
             if (is_max) {
                 const int pos = atomicAdd(&s_nc, 1);
-                if (pos < T.cand_cap)
-                    glist[pos] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+                if (pos < smem_cap) s_list[pos] = key;
+                if (pos < T.cand_cap) glist[pos] = key;
             }
         }
     __syncthreads();
     const int nc = min(s_nc, T.cand_cap);
-    unsigned long long *list = glist;
-    if (nc <= kSmemCand) {
-        for (int c = tid; c < nc; c += kSelThreads) s_list[c] = glist[c];
-        list = s_list;
-    }
-    __syncthreads();
-
-    // 3. strongest-first greedy selection with min-distance suppression
     const float md2 = __fmul_rn(min_dist, min_dist);
     const bool suppress = min_dist >= 1.f;
     int n_out = 0;
-    unsigned long long last = 0;
-    float lx = 0.f, ly = 0.f;
-    while (n_out < max_per_target) {
-        unsigned long long best = 0;
-        for (int c = tid; c < nc; c += kSelThreads) {
-            unsigned long long key = list[c];
-            if (key == 0) continue;
-            if (last != 0) {
-                bool kill = (key == last);
-                if (suppress && !kill) {
-                    const unsigned idx = (unsigned)key;
-                    const float dx = (float)(int)(idx % (unsigned)w) - lx, dy = (float)(int)(idx / (unsigned)w) - ly;
-                    kill = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2;
+
+    if (nc <= smem_cap && max_per_target <= kMaxAccepted) {
+        // ---- 3a. sorted path: bitonic sort (descending) in shared memory, then one warp walks the sorted list in
+        //          chunks of 32: test against the accepted list, resolve the chunk in order with ballots ----
+        int n2 = kSelThreads;
+        while (n2 < nc) n2 <<= 1;
+        for (int i = nc + tid; i < n2; i += kSelThreads) s_list[i] = 0ull;
+        __syncthreads();
+        // each warp owns a contiguous segment of n2 / 8 keys: compare distances inside a segment only need
+        // __syncwarp; the few stages that cross segments take a block barrier (6 instead of ~60)
+        const int seg = n2 / nwarps, sbase = warp * seg;
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= seg) {
+                    __syncthreads();
+                    for (int i = tid; i < n2; i += kSelThreads) {
+                        const int l = i ^ j;
+                        if (l > i) {
+                            const unsigned long long a = s_list[i], b = s_list[l];
+                            if (((i & k) == 0) ? (a < b) : (a > b)) { s_list[i] = b; s_list[l] = a; }
+                        }
+                    }
+                    __syncthreads();
+                } else {
+                    for (int t = lane; t < seg; t += 32) {
+                        const int i = sbase + t, l = i ^ j;
+                        if (l > i) {
+                            const unsigned long long a = s_list[i], b = s_list[l];
+                            if (((i & k) == 0) ? (a < b) : (a > b)) { s_list[i] = b; s_list[l] = a; }
+                        }
+                    }
+                    __syncwarp();
                 }
-                if (kill) { list[c] = 0; continue; }
             }
-            best = key > best ? key : best;
+        __syncthreads();
+        if (warp == 0) {
+            for (int base = 0; base < nc && n_out < max_per_target; base += 32) {
+                const unsigned long long key = (base + lane < nc) ? s_list[base + lane] : 0ull;
+                const unsigned idx = (unsigned)key;
+                const float x = (float)(int)(idx % (unsigned)w), y = (float)(int)(idx / (unsigned)w);
+                bool alive = key != 0ull;
+                if (suppress)
+                    for (int a = 0; a < n_out; ++a) {
+                        const unsigned q = s_acc[a];
+                        const float dx = x - (float)(int)(q & 0xffffu), dy = y - (float)(int)(q >> 16);
+                        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2) alive = false;
+                    }
+                while (n_out < max_per_target) {
+                    const unsigned msk = __ballot_sync(0xffffffffu, alive);
+                    if (!msk) break;
+                    const int i = __ffs(msk) - 1;
+                    const float bx = __shfl_sync(0xffffffffu, x, i), by = __shfl_sync(0xffffffffu, y, i);
+                    if (lane == i) {
+                        s_acc[n_out] = (unsigned)(int)bx | ((unsigned)(int)by << 16);
+                        my_out[n_out] = make_float2(bx, by);
+                        alive = false;
+                    } else if (suppress && alive) {
+                        const float dx = x - bx, dy = y - by;
+                        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2) alive = false;
+                    }
+                    ++n_out;
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) s_nout = n_out;
         }
-        best = warp_max_u64(best);
-        if (lane == 0) s_red[warp] = best;
         __syncthreads();
-        best = s_red[0];
+        n_out = s_nout;
+    } else {
+        // ---- 3b. any size: max_per_target rounds of block-wide arg-max over the candidate list in global memory,
+        //          killing the candidates within min_dist of the last accepted corner on the way ----
+        unsigned long long last = 0;
+        float lx = 0.f, ly = 0.f;
+        while (n_out < max_per_target) {
+            unsigned long long best = 0;
+            for (int c = tid; c < nc; c += kSelThreads) {
+                unsigned long long key = glist[c];
+                if (key == 0) continue;
+                if (last != 0) {
+                    bool kill = (key == last);
+                    if (suppress && !kill) {
+                        const unsigned idx = (unsigned)key;
+                        const float dx = (float)(int)(idx % (unsigned)w) - lx, dy = (float)(int)(idx / (unsigned)w) - ly;
+                        kill = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2;
+                    }
+                    if (kill) { glist[c] = 0; continue; }
+                }
+                best = key > best ? key : best;
+            }
+            best = warp_max_u64(best);
+            if (lane == 0) s_red[warp] = best;
+            __syncthreads();
+            best = s_red[0];
 #pragma unroll
-        for (int i = 1; i < nwarps; ++i) best = s_red[i] > best ? s_red[i] : best;
-        __syncthreads();
-        if (best == 0) break;
-        const unsigned idx = (unsigned)best;
-        lx = (float)(int)(idx % (unsigned)w);
-        ly = (float)(int)(idx / (unsigned)w);
-        if (tid == 0) my_out[n_out] = make_float2(lx, ly);
-        last = best;
-        ++n_out;
+            for (int i = 1; i < nwarps; ++i) best = s_red[i] > best ? s_red[i] : best;
+            __syncthreads();
+            if (best == 0) break;
+            const unsigned idx = (unsigned)best;
+            lx = (float)(int)(idx % (unsigned)w);
+            ly = (float)(int)(idx / (unsigned)w);
+            if (tid == 0) my_out[n_out] = make_float2(lx, ly);
+            last = best;
+            ++n_out;
+        }
     }
-    if (tid == 0) counts[blockIdx.x] = n_out;
+    if (tid == 0) *T.count = n_out;
     // unused slots get a far-away sentinel: fed to psnw_klt_track they fail the bounds test at once (status 0)
     for (int i = n_out + tid; i < max_per_target; i += kSelThreads) my_out[i] = make_float2(kUnusedSlot, kUnusedSlot);
 }
 
 }  // namespace
 
-int launch_min_eig(const LevelGeom &l0, int plane, float *eig, cudaStream_t stream)
+int launch_min_eig(const LevelGeom &l0, const EigList &list, cudaStream_t stream)
 {
-    dim3 grid((l0.w + kEigTW - 1) / kEigTW, (l0.h + kEigTH - 1) / kEigTH);
-    min_eig_kernel<<<grid, 256, 0, stream>>>(l0.img + (size_t)plane * l0.plane_px, l0.w, l0.h, l0.pitch, eig);
+    if (list.n <= 0) return 0;
+    dim3 grid((l0.w + kEigTW - 1) / kEigTW, (l0.h + kEigTH - 1) / kEigTH, list.n);
+    min_eig_kernel<<<grid, 256, 0, stream>>>(l0.img, l0.w, l0.h, l0.pitch, l0.plane_px, list);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launch_detect_select(const float *eig, int w, int h, int pitch, const DetectTarget *targets, int n_targets,
+int launch_detect_select(int w, int h, int pitch, const DetectTarget *targets, int n_targets,
                          int max_per_target, float quality, float min_dist, unsigned long long *cand,
-                         float2 *out, int *counts, cudaStream_t stream)
+                         int max_roi_area, int max_tile_px, cudaStream_t stream)
 {
     if (n_targets <= 0) return 0;
-    detect_select_kernel<<<n_targets, kSelThreads, 0, stream>>>(eig, w, h, pitch, targets, max_per_target, quality,
-                                                                min_dist, cand, out, counts);
+    // shared-memory candidate capacity: local maxima of a 3x3 NMS are at most ~1/4 of the ROI pixels; larger lists
+    // (or > kMaxAccepted corners per target) take the global-memory path inside the kernel
+    int cap = 1024;
+    while (cap < max_roi_area / 3 && cap < 8192) cap <<= 1;
+    const int tile_cap = max_tile_px <= 16384 ? max_tile_px : 0;          // ROI tile in shared memory when it fits (64 KB)
+    const size_t smem = (size_t)cap * sizeof(unsigned long long) + (size_t)tile_cap * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(detect_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8 + 16384 * 4) != cudaSuccess) return -1;
+        configured = true;
+    }
+    detect_select_kernel<<<n_targets, kSelThreads, smem, stream>>>(w, h, pitch, targets, max_per_target, quality,
+                                                                   min_dist, cand, cap, tile_cap);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 

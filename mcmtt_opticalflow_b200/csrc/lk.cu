@@ -79,9 +79,12 @@ __device__ __forceinline__ bool make_system(long long s11, long long s12, long l
     return true;
 }
 
-// one Gauss-Newton update; returns true when the iteration loop must stop
-__device__ __forceinline__ bool lk_step(long long sb1, long long sb2, float A11, float A12, float A22, float Dinv,
-                                        float half_x, float half_y, double eps2, int j,
+// one Gauss-Newton update; returns true when the iteration loop must stop.
+//   delta.ddot(delta) <= eps^2 is a double comparison in OpenCV; the float value decides it whenever it is further
+//   than 1e-5 (relative) from the threshold, the double product is only formed inside that band.
+//   fabs((double)(float)s) < 0.01 is exactly fabsf(s) <= 0.01f (0.01f is the largest float below the double 0.01).
+__device__ __forceinline__ bool lk_step(const LkParams &P, long long sb1, long long sb2, float A11, float A12, float A22,
+                                        float Dinv, float half_x, float half_y, int j,
                                         float &nx, float &ny, float &pdx, float &pdy, float &next_x, float &next_y)
 {
     const float b1 = __fmul_rn(__ll2float_rn(sb1), kFltScale), b2 = __fmul_rn(__ll2float_rn(sb2), kFltScale);
@@ -91,8 +94,12 @@ __device__ __forceinline__ bool lk_step(long long sb1, long long sb2, float A11,
     ny = __fadd_rn(ny, dy);
     next_x = __fadd_rn(nx, half_x);
     next_y = __fadd_rn(ny, half_y);
-    if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps2) return true;
-    if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    bool small = d2 < P.eps2_lo;
+    if (!small && !(d2 > P.eps2_hi))
+        small = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= P.eps2;
+    if (small) return true;
+    if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
         next_x = __fsub_rn(next_x, __fmul_rn(dx, 0.5f));
         next_y = __fsub_rn(next_y, __fmul_rn(dy, 0.5f));
         return true;
@@ -191,7 +198,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 while (x >= ww) { x -= ww; y++; }
             }
             sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
-            if (lk_step(sb1, sb2, A11, A12, A22, Dinv, half_x, half_y, P.eps2, j, nx, ny, pdx, pdy, next_x, next_y)) break;
+            if (lk_step(P, sb1, sb2, A11, A12, A22, Dinv, half_x, half_y, j, nx, ny, pdx, pdy, next_x, next_y)) break;
         }
 
         if (st && level == 0) {
@@ -266,12 +273,16 @@ lk_generic_kernel(const __grid_constant__ LkParams P, int max_win_px)
 // ------------------------------------------------------------------------------------------------
 // 21 x 21 window
 // ------------------------------------------------------------------------------------------------
-constexpr int kW = 21;                    // window
-constexpr int kPatch = kW + 1;            // 22 x 22 samples
-constexpr int kPatchRowWords = 8;         // u8 patch row = 32 bytes (22 + up to 3 alignment bytes)
-constexpr int kU8Words = kPatch * kPatchRowWords;            // 176 words
-constexpr int kDxyWords = kPatch * kPatch;                   // 484 words (short2 per sample)
-constexpr int kWarpSmemWords = kU8Words + kDxyWords;         // 660 words = 2640 B per warp
+constexpr int kW = 21;                            // window
+constexpr int kPatch = kW + 1;                    // 22 x 22 samples feed the 21 x 21 bilinear window
+constexpr int kMargin = 4;                        // extra samples staged around the target-image patch
+constexpr int kJPatch = kPatch + 2 * kMargin;     // 30 x 30: the window may drift 8 px inside it before a re-stage
+constexpr int kU8Pitch = 13;                      // words per staged u8 row (52 B >= 15 + 30; odd: <= 2-way bank conflicts)
+constexpr int kIWords = 288;                      // 22 rows x 13 words, rounded up to a 16-byte multiple
+constexpr int kJWords = 392;                      // 30 rows x 13 words, rounded up
+constexpr int kDxPitch = 28;                      // words per staged derivative row = 7 groups of 4 pixels
+constexpr int kDxWords = kPatch * kDxPitch;       // 616
+constexpr int kWarpSmemWords = kIWords + kJWords + kDxWords;   // 1296 words = 5184 B per warp
 constexpr int kWarpsPerCta = 8;
 
 __device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c)
@@ -287,56 +298,133 @@ __device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c)
     return d;
 }
 
-// Stage the 22x22 u8 patch whose top-left sample is (ix, iy) into `patch` (row pitch 32 B).  Returns the byte
-// offset of sample column 0 inside a patch row.  Interior patches use aligned 32-bit loads; patches touching
-// the frame border gather bytes through REFLECT_101 (the apron OpenCV keeps around every level).
-__device__ __forceinline__ int stage_u8_patch(const uint8_t *img, int pitch, int w, int h, int ix, int iy,
-                                              uint32_t *patch, int lane)
+__device__ __forceinline__ int refl_clamp(int p, int n)
 {
-    if (ix >= 0 && iy >= 0 && ix + kW < w && iy + kW < h) {
-        const int off = ix & 3;
-        const int nwords = (off + kPatch + 3) >> 2;                    // 6 or 7
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (size_t)iy * pitch + (ix - off));
-        const int pitch_w = pitch >> 2;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            const int wi = lane + 32 * r;                              // 22 rows x 7 words = 154
-            const int row = (wi * 147) >> 10;                          // wi / 7 for wi < 160
-            const int c = wi - row * 7;
-            if (wi < kPatch * 7 && c < nwords) patch[row * kPatchRowWords + c] = __ldg(src + (size_t)row * pitch_w + c);
-        }
-        return off;
-    }
-    uint8_t *pb = reinterpret_cast<uint8_t *>(patch);
-    for (int bi = lane; bi < kPatch * kPatch; bi += 32) {
-        const int row = bi / kPatch, col = bi - row * kPatch;
-        pb[row * (kPatchRowWords * 4) + col] = img[(size_t)refl(iy + row, h) * pitch + refl(ix + col, w)];
-    }
-    return 0;
+    p = p < 0 ? -p : p;
+    p = p >= n ? 2 * (n - 1) - p : p;
+    return min(max(p, 0), n - 1);
 }
 
-// Pre-shift bilinear sums (rounding constant included) of a horizontal run of 7 samples starting at byte
-// column `bc` of patch row `row`; wt/wb = (w_left | w_right << 16) of the top / bottom row.
-__device__ __forceinline__ void bilinear_run7(const uint32_t *patch, int row, int bc, int wt, int wb, int v[7])
+// window origin (ix, iy) rejected by LKTrackerInvoker's bounds test: ix < -win || ix >= cols || ...
+__device__ __forceinline__ bool window_oob(int ix, int iy, int w, int h)
 {
-    const uint32_t *p = patch + row * kPatchRowWords + (bc >> 2);
+    return (unsigned)(ix + kW) >= (unsigned)(w + kW) || (unsigned)(iy + kW) >= (unsigned)(h + kW);
+}
+
+// ---- staging of an N x N u8 patch with top-left sample (x0, y0): loads are issued first (u8_issue) and written to
+// shared memory later (u8_commit) so that the I, dI and J fetches of a level are all in flight together.
+// Patches inside the frame are fetched as aligned 16-byte groups (3 lanes per row, 10 rows per instruction); patches
+// touching the border gather bytes row by row through REFLECT_101, the apron OpenCV keeps around every level.
+struct U8Loads {
+    uint4 v[3];
+    int off;       // byte offset of sample column 0 inside a staged row
+    bool fast;
+};
+
+template <int N>
+__device__ __forceinline__ void u8_issue(const uint8_t *__restrict__ img, int pitch, int w, int h, int x0, int y0,
+                                         int lane, int dr3, int g3, U8Loads &L)
+{
+    L.fast = x0 >= 0 && y0 >= 0 && x0 + N <= w && y0 + N <= h;
+    L.off = L.fast ? (x0 & 15) : 0;
+    if (L.fast) {
+        const int ng = (L.off + N + 15) >> 4;               // 16-byte groups per row: 2 or 3
+        const uint4 *src = reinterpret_cast<const uint4 *>(img + (size_t)(y0 + dr3) * pitch + (x0 - L.off)) + g3;
+        const int rstride = 10 * (pitch >> 4);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (lane < 30 && 10 * i + dr3 < N && g3 < ng) L.v[i] = __ldg(src + (size_t)i * rstride);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void u8_commit(const U8Loads &L, const uint8_t *__restrict__ img, int pitch, int w, int h,
+                                          int x0, int y0, uint32_t *patch, int lane, int dr3, int g3)
+{
+    if (L.fast) {
+        const int ng = (L.off + N + 15) >> 4;
+        uint32_t *dst = patch + dr3 * kU8Pitch + 4 * g3;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            if (lane < 30 && 10 * i + dr3 < N && g3 < ng) {
+                uint32_t *d = dst + 10 * i * kU8Pitch;
+                d[0] = L.v[i].x; d[1] = L.v[i].y; d[2] = L.v[i].z; d[3] = L.v[i].w;
+            }
+    } else if (lane < N) {
+        const uint8_t *col = img + refl_clamp(x0 + lane, w);
+        uint8_t *pb = reinterpret_cast<uint8_t *>(patch) + lane;
+#pragma unroll 2
+        for (int row = 0; row < N; ++row) pb[row * (kU8Pitch * 4)] = col[(size_t)refl_clamp(y0 + row, h) * pitch];
+    }
+}
+
+// ---- staging of the 22 x 22 (dx,dy) samples at (x0, y0) as aligned 16-byte groups (7 lanes per row, 4 rows per
+// instruction).  Outside the frame the derivative apron is zero (BORDER_CONSTANT): groups left of x = 0 or beyond the
+// row pitch and rows outside [0, h) become zeros; columns in [w, pitch) already hold zeros (K1 writes them).
+struct DxLoads {
+    uint4 v[6];
+    int off;       // word offset of sample column 0 inside a staged row
+};
+
+__device__ __forceinline__ void dxy_issue(const short2 *__restrict__ D, int pitch, int h, int x0, int y0,
+                                          int lane, int dr7, int g7, DxLoads &L)
+{
+    L.off = x0 & 3;
+    const int gx = x0 - L.off + 4 * g7;
+    const bool xin = gx >= 0 && gx < pitch;
+    const uint4 *src = reinterpret_cast<const uint4 *>(D + (ptrdiff_t)(y0 + dr7) * pitch + gx);
+    const int rstride = pitch;                              // 4 rows x pitch px x 4 B / 16 B
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        L.v[i] = make_uint4(0u, 0u, 0u, 0u);
+        const int row = 4 * i + dr7;
+        if (lane < 28 && row < kPatch && xin && (unsigned)(y0 + row) < (unsigned)h) L.v[i] = __ldg(src + (ptrdiff_t)i * rstride);
+    }
+}
+
+__device__ __forceinline__ void dxy_commit(const DxLoads &L, uint32_t *dxp, int lane, int dr7, int g7)
+{
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int row = 4 * i + dr7;
+        if (lane < 28 && row < kPatch) *reinterpret_cast<uint4 *>(dxp + row * kDxPitch + 4 * g7) = L.v[i];
+    }
+}
+
+// Bilinear sums of a horizontal run of 7 samples starting at byte column `bc` of patch row `row`:
+//   v[k] = c[k] + w_tl*p(k) + w_tr*p(k+1) + w_bl*q(k) + w_br*q(k+1),  wt/wb = (w_left | w_right << 16) of the top /
+// bottom row.  The 8+8 bytes are aligned with funnel shifts and fed to dp2a without unpacking.
+__device__ __forceinline__ void bilinear_run7(const uint32_t *patch, int row, int bc, int wt, int wb, const int c[7], int v[7])
+{
+    const uint32_t *p = patch + row * kU8Pitch + (bc >> 2);
     const int sh = (bc & 3) * 8;
     const uint32_t t0 = __funnelshift_r(p[0], p[1], sh), t1 = __funnelshift_r(p[1], p[2], sh);
-    const uint32_t u0 = __funnelshift_r(p[kPatchRowWords], p[kPatchRowWords + 1], sh);
-    const uint32_t u1 = __funnelshift_r(p[kPatchRowWords + 1], p[kPatchRowWords + 2], sh);
+    const uint32_t u0 = __funnelshift_r(p[kU8Pitch], p[kU8Pitch + 1], sh);
+    const uint32_t u1 = __funnelshift_r(p[kU8Pitch + 1], p[kU8Pitch + 2], sh);
     const uint32_t ts = __funnelshift_r(t0, t1, 8), us = __funnelshift_r(u0, u1, 8);   // bytes 1..4
     const uint32_t t5 = t1 >> 8, u5 = u1 >> 8;                                         // bytes 5..7
-    v[0] = dp2a_lo_su(wb, u0, dp2a_lo_su(wt, t0, 256));
-    v[1] = dp2a_lo_su(wb, us, dp2a_lo_su(wt, ts, 256));
-    v[2] = dp2a_hi_su(wb, u0, dp2a_hi_su(wt, t0, 256));
-    v[3] = dp2a_hi_su(wb, us, dp2a_hi_su(wt, ts, 256));
-    v[4] = dp2a_lo_su(wb, u1, dp2a_lo_su(wt, t1, 256));
-    v[5] = dp2a_lo_su(wb, u5, dp2a_lo_su(wt, t5, 256));
-    v[6] = dp2a_hi_su(wb, u1, dp2a_hi_su(wt, t1, 256));
+    v[0] = dp2a_lo_su(wb, u0, dp2a_lo_su(wt, t0, c[0]));
+    v[1] = dp2a_lo_su(wb, us, dp2a_lo_su(wt, ts, c[1]));
+    v[2] = dp2a_hi_su(wb, u0, dp2a_hi_su(wt, t0, c[2]));
+    v[3] = dp2a_hi_su(wb, us, dp2a_hi_su(wt, ts, c[3]));
+    v[4] = dp2a_lo_su(wb, u1, dp2a_lo_su(wt, t1, c[4]));
+    v[5] = dp2a_lo_su(wb, u5, dp2a_lo_su(wt, t5, c[5]));
+    v[6] = dp2a_hi_su(wb, u1, dp2a_hi_su(wt, t1, c[6]));
 }
 
-__device__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_level, float px, float py,
-                          uint32_t *u8p, uint32_t *dxp, int lane, Solve &o)
+__device__ __forceinline__ int sext16(uint32_t w) { return (int)(short)(w & 0xffffu); }
+
+// Origin of the staged 30 x 30 target patch for a window at (inx, iny): centred (margin 4 on every side), but slid
+// back inside the frame when the window itself is inside, so that the aligned fast path serves it.
+__device__ __forceinline__ int patch_origin(int ix, int n)
+{
+    int s = ix - kMargin;
+    if (ix >= 0 && ix + kPatch <= n && n >= kJPatch) s = min(max(s, 0), n - kJPatch);
+    return s;
+}
+
+__device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_level, float px, float py,
+                                       uint32_t *ip, uint32_t *jp, uint32_t *dxp, int lane, Solve &o)
 {
     constexpr float half = (kW - 1) * 0.5f;
     float next_x = 0.f, next_y = 0.f, er = 0.f;
@@ -346,9 +434,13 @@ __device__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_l
     const int r0 = lane, r1 = two ? lane + 32 : 62;
     const int row0 = r0 / 3, col0 = 7 * (r0 - 3 * row0);
     const int row1 = r1 / 3, col1 = 7 * (r1 - 3 * row1);
+    const int dr3 = row0, g3 = lane - 3 * row0;             // staging roles: u8 groups (3 per row) ...
+    const int dr7 = lane / 7, g7 = lane - 7 * dr7;          // ... and derivative groups (7 per row)
 
+#pragma unroll 1
     for (int level = max_level; level >= 0; --level) {
         const LevelGeom &L = P.lv[level];
+        const int Lw = L.w, Lh = L.h, Lp = L.pitch;
         const uint8_t *IA = L.img + (size_t)plane_a * L.plane_px;
         const short2 *DA = L.dxy + (size_t)plane_a * L.plane_px;
         const uint8_t *JB = L.img + (size_t)plane_b * L.plane_px;
@@ -361,51 +453,62 @@ __device__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_l
 
         prev_x = __fsub_rn(prev_x, half); prev_y = __fsub_rn(prev_y, half);
         const int ipx = __float2int_rd(prev_x), ipy = __float2int_rd(prev_y);
-        if (ipx < -kW || ipx >= L.w || ipy < -kW || ipy >= L.h) {
+        if (window_oob(ipx, ipy, Lw, Lh)) {
             if (level == 0) { st = 0; er = 0.f; }
             continue;
         }
         int w00, w01, w10, w11;
         bilinear_weights(__fsub_rn(prev_x, (float)ipx), __fsub_rn(prev_y, (float)ipy), w00, w01, w10, w11);
 
-        // ---- template: stage I (u8) and dI (short2) patches, then sample them into registers ----
+        // ---- fetch I, dI around the source point and J around the first target position, all loads in flight ----
+        nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
+        int sx0 = 0, sy0 = 0, offJ = 0;
+        bool staged = !window_oob(__float2int_rd(nx), __float2int_rd(ny), Lw, Lh);
+        if (staged) { sx0 = patch_origin(__float2int_rd(nx), Lw); sy0 = patch_origin(__float2int_rd(ny), Lh); }
         __syncwarp();
-        const int offI = stage_u8_patch(IA, L.pitch, L.w, L.h, ipx, ipy, u8p, lane);
-        for (int wi = lane; wi < kDxyWords; wi += 32) {
-            const int row = wi / kPatch, col = wi - row * kPatch;
-            const int X = ipx + col, Y = ipy + row;
-            uint32_t v = 0;
-            if ((unsigned)X < (unsigned)L.w && (unsigned)Y < (unsigned)L.h)
-                v = __ldg(reinterpret_cast<const uint32_t *>(DA + (size_t)Y * L.pitch + X));
-            dxp[wi] = v;
+        int offI, offD;
+        {
+            U8Loads li;
+            DxLoads ld;
+            u8_issue<kPatch>(IA, Lp, Lw, Lh, ipx, ipy, lane, dr3, g3, li);
+            dxy_issue(DA, Lp, Lh, ipx, ipy, lane, dr7, g7, ld);
+            u8_commit<kPatch>(li, IA, Lp, Lw, Lh, ipx, ipy, ip, lane, dr3, g3);
+            dxy_commit(ld, dxp, lane, dr7, g7);
+            offI = li.off; offD = ld.off;
         }
+        U8Loads lj;                              // J loads stay in flight while the template is computed
+        if (staged) u8_issue<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, lane, dr3, g3, lj);
         __syncwarp();
 
-        int tI[14], tIx[14], tIy[14];
+        // ---- template into registers ----
+        int tC[14], tIx[14], tIy[14];          // tC = 256 - 512 * I: the dp2a chain then yields (J - I) << 9 directly
         int a11 = 0, a12 = 0, a22 = 0;
-        const int wt = (w00 & 0xffff) | (w01 << 16), wb = (w10 & 0xffff) | (w11 << 16);
+        {
+            const int wt = (w00 & 0xffff) | (w01 << 16), wb = (w10 & 0xffff) | (w11 << 16);
+            const int c256[7] = {256, 256, 256, 256, 256, 256, 256};
 #pragma unroll
-        for (int run = 0; run < 2; ++run) {
-            const int row = run ? row1 : row0, col = run ? col1 : col0;
-            int v[7];
-            bilinear_run7(u8p, row, offI + col, wt, wb, v);
-            const uint32_t *d0 = dxp + row * kPatch + col, *d1 = d0 + kPatch;
-            uint32_t q0 = d0[0], q1 = d1[0];
+            for (int run = 0; run < 2; ++run) {
+                const int row = run ? row1 : row0, col = run ? col1 : col0;
+                int v[7];
+                bilinear_run7(ip, row, offI + col, wt, wb, c256, v);
+                const uint32_t *d0 = dxp + row * kDxPitch + offD + col, *d1 = d0 + kDxPitch;
+                uint32_t q0 = d0[0], q1 = d1[0];
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                const uint32_t n0 = d0[k + 1], n1 = d1[k + 1];
-                const int x00 = (int)(q0 << 16) >> 16, y00 = (int)q0 >> 16, x01 = (int)(n0 << 16) >> 16, y01 = (int)n0 >> 16;
-                const int x10 = (int)(q1 << 16) >> 16, y10 = (int)q1 >> 16, x11 = (int)(n1 << 16) >> 16, y11 = (int)n1 >> 16;
-                int ix = (x00 * w00 + x01 * w01 + x10 * w10 + x11 * w11 + (1 << 13)) >> 14;
-                int iy = (y00 * w00 + y01 * w01 + y10 * w10 + y11 * w11 + (1 << 13)) >> 14;
-                if (run && !two) { ix = 0; iy = 0; }
-                tI[run * 7 + k] = v[k] >> 9;
-                tIx[run * 7 + k] = ix;
-                tIy[run * 7 + k] = iy;
-                a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
-                q0 = n0; q1 = n1;
+                for (int k = 0; k < 7; ++k) {
+                    const uint32_t n0 = d0[k + 1], n1 = d1[k + 1];
+                    int ix = (sext16(q0) * w00 + sext16(n0) * w01 + sext16(q1) * w10 + sext16(n1) * w11 + (1 << 13)) >> 14;
+                    int iy = (((int)q0 >> 16) * w00 + ((int)n0 >> 16) * w01 + ((int)q1 >> 16) * w10 + ((int)n1 >> 16) * w11 + (1 << 13)) >> 14;
+                    if (run && !two) { ix = 0; iy = 0; }
+                    tC[run * 7 + k] = 256 - ((v[k] >> 9) << 9);
+                    tIx[run * 7 + k] = ix;
+                    tIy[run * 7 + k] = iy;
+                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                    q0 = n0; q1 = n1;
+                }
             }
         }
+        if (staged) { u8_commit<kJPatch>(lj, JB, Lp, Lw, Lh, sx0, sy0, jp, lane, dr3, g3); offJ = lj.off; }
+        __syncwarp();
         const long long s11 = warp_sum_i32(a11), s12 = warp_sum_i32(a12), s22 = warp_sum_i32(a22);
         float A11, A12, A22, Dinv;
         if (!make_system(s11, s12, s22, kW, kW, P.min_eig, A11, A12, A22, Dinv)) {
@@ -413,53 +516,68 @@ __device__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_l
             continue;
         }
 
-        nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
         float pdx = 0.f, pdy = 0.f;
+#pragma unroll 1
         for (int j = 0; j < P.max_iters; ++j) {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
-            if (inx < -kW || inx >= L.w || iny < -kW || iny >= L.h) {
+            if (window_oob(inx, iny, Lw, Lh)) {
                 if (level == 0) st = 0;
                 break;
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             const int jt = (w00 & 0xffff) | (w01 << 16), jb = (w10 & 0xffff) | (w11 << 16);
-            __syncwarp();
-            const int offJ = stage_u8_patch(JB, L.pitch, L.w, L.h, inx, iny, u8p, lane);
-            __syncwarp();
+            if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
+                sx0 = patch_origin(inx, Lw); sy0 = patch_origin(iny, Lh);
+                U8Loads lj;
+                __syncwarp();
+                u8_issue<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, lane, dr3, g3, lj);
+                u8_commit<kJPatch>(lj, JB, Lp, Lw, Lh, sx0, sy0, jp, lane, dr3, g3);
+                offJ = lj.off;
+                __syncwarp();
+                staged = true;
+            }
+            const int bx = offJ + (inx - sx0), by = iny - sy0;
             int b1 = 0, b2 = 0;
 #pragma unroll
             for (int run = 0; run < 2; ++run) {
                 int v[7];
-                bilinear_run7(u8p, run ? row1 : row0, offJ + (run ? col1 : col0), jt, jb, v);
+                bilinear_run7(jp, by + (run ? row1 : row0), bx + (run ? col1 : col0), jt, jb, &tC[run * 7], v);
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
-                    const int diff = (v[k] >> 9) - tI[run * 7 + k];
+                    const int diff = v[k] >> 9;
                     b1 += diff * tIx[run * 7 + k];
                     b2 += diff * tIy[run * 7 + k];
                 }
             }
             const long long sb1 = warp_sum_i32(b1), sb2 = warp_sum_i32(b2);
-            if (lk_step(sb1, sb2, A11, A12, A22, Dinv, half, half, P.eps2, j, nx, ny, pdx, pdy, next_x, next_y)) break;
+            if (lk_step(P, sb1, sb2, A11, A12, A22, Dinv, half, half, j, nx, ny, pdx, pdy, next_x, next_y)) break;
         }
 
         if (st && level == 0) {
             const float qx = __fsub_rn(next_x, half), qy = __fsub_rn(next_y, half);
             const int inx = __float2int_rd(qx), iny = __float2int_rd(qy);
-            if (inx < -kW || inx >= L.w || iny < -kW || iny >= L.h) { st = 0; continue; }
+            if (window_oob(inx, iny, Lw, Lh)) { st = 0; continue; }
             bilinear_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
             const int jt = (w00 & 0xffff) | (w01 << 16), jb = (w10 & 0xffff) | (w11 << 16);
-            __syncwarp();
-            const int offJ = stage_u8_patch(JB, L.pitch, L.w, L.h, inx, iny, u8p, lane);
-            __syncwarp();
+            if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
+                sx0 = patch_origin(inx, Lw); sy0 = patch_origin(iny, Lh);
+                U8Loads lj;
+                __syncwarp();
+                u8_issue<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, lane, dr3, g3, lj);
+                u8_commit<kJPatch>(lj, JB, Lp, Lw, Lh, sx0, sy0, jp, lane, dr3, g3);
+                offJ = lj.off;
+                __syncwarp();
+            }
+            const int bx = offJ + (inx - sx0), by = iny - sy0;
             int e = 0;
 #pragma unroll
             for (int run = 0; run < 2; ++run) {
                 int v[7];
-                bilinear_run7(u8p, run ? row1 : row0, offJ + (run ? col1 : col0), jt, jb, v);
+                bilinear_run7(jp, by + (run ? row1 : row0), bx + (run ? col1 : col0), jt, jb, &tC[run * 7], v);
                 if (run == 0 || two) {
 #pragma unroll
                     for (int k = 0; k < 7; ++k) {
-                        const int diff = (v[k] >> 9) - tI[run * 7 + k];
+                        const int diff = v[k] >> 9;
                         e += diff < 0 ? -diff : diff;
                     }
                 }
@@ -471,14 +589,14 @@ __device__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_l
     o.x = next_x; o.y = next_y; o.st = st; o.err = st ? er : 0.f;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 lk_w21_kernel(const __grid_constant__ LkParams P)
 {
     __shared__ __align__(16) uint32_t smem[kWarpsPerCta * kWarpSmemWords];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int i = blockIdx.x * kWarpsPerCta + wib;
     if (i >= P.n_pts) return;
-    uint32_t *u8p = smem + wib * kWarpSmemWords, *dxp = u8p + kU8Words;
+    uint32_t *ip = smem + wib * kWarpSmemWords, *jp = ip + kIWords, *dxp = jp + kJWords;
 
     const TrackJob &job = P.jobs[find_job(P.jobs, P.n_jobs, i)];
     const int k = i - job.pt_begin;
@@ -486,10 +604,18 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
     const TrackGroup g = P.groups[job.group_base + min(max(t, 0), job.n_targets - 1)];
     const float2 p0 = job.pts[k];
 
-    Solve f, b;
-    b.x = b.y = b.err = 0.f; b.st = 1;
-    solve_w21(P, g.plane_from, g.plane_to, g.max_level, p0.x, p0.y, u8p, dxp, lane, f);
-    if (P.do_fb) solve_w21(P, g.plane_to, g.plane_from, g.max_level, f.x, f.y, u8p, dxp, lane, b);
+    // forward pass, then (fused forward-backward check) the same solver from the tracked position back into the
+    // source frame; one copy of the solver code keeps the kernel inside the instruction cache
+    Solve f, b, cur;
+    f.x = f.y = f.err = 0.f; f.st = 1;
+    b = f;
+    const int npass = P.do_fb ? 2 : 1;
+#pragma unroll 1
+    for (int pass = 0; pass < npass; ++pass) {
+        const float sx = pass ? f.x : p0.x, sy = pass ? f.y : p0.y;
+        solve_w21(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, lane, cur);
+        if (pass) b = cur; else f = cur;
+    }
     finish_point(P, job, k, p0, f, b, lane);
 }
 

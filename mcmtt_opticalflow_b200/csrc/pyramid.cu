@@ -147,6 +147,7 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
 
     uint4 *dxy_out = reinterpret_cast<uint4 *>(cur.dxy + (size_t)plane * cur.plane_px + (size_t)ybase * cur.pitch + x0) + lane;
     const int dxy_row_u4 = cur.pitch / 4;
+    const bool pad_cols = x0 + kTileW > W;
 
 #pragma unroll
     for (int rr = 0; rr < kRowsPerWarp + 3; ++rr) {
@@ -175,6 +176,7 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
                 const int dx = 3 * (dm[i] + dp[i]) + 10 * d0[i];
                 const int dy = sp[i] - sm[i];
                 o[i] = __byte_perm((uint32_t)dx, (uint32_t)dy, 0x5410);
+                if (pad_cols && x0 + 4 * lane + i >= W) o[i] = 0u;   // columns [w, pitch) stay zero: the LK kernel reads them
             }
             if (ybase + k < H) dxy_out[(size_t)k * dxy_row_u4] = make_uint4(o[0], o[1], o[2], o[3]);
         }

@@ -45,8 +45,13 @@ class TrackJob(C.Structure):
                 ("fb_err", C.c_void_p)]
 
 
+class DetectJob(C.Structure):
+    _fields_ = [("cam", C.c_int), ("slot", C.c_int), ("boxes", C.c_void_p), ("n_targets", C.c_int),
+                ("pts_xy", C.c_void_p), ("counts", C.c_void_p)]
+
+
 EXPORTS = [
-    "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
+    "psnw_klt_detect_batch", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
     "psnw_push_frames_bgr", "psnw_frames_held", "psnw_klt_detect", "psnw_klt_track", "psnw_klt_track_batch",
     "psnw_box_update", "psnw_sync", "psnw_last_error", "psnw_get_stream", "psnw_level_info", "psnw_read_level",
     "psnw_read_min_eig", "psnw_launch_count", "psnw_push_frame_bytes", "psnw_rebuild_pyramids", "psnw_levels_built",
@@ -83,6 +88,7 @@ def load():
         lib.psnw_rebuild_pyramids.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.psnw_klt_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                         C.c_float, C.c_void_p, C.c_void_p, C.c_int]
+        lib.psnw_klt_detect_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
         lib.psnw_klt_track.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_klt_track_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
