@@ -110,7 +110,7 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     extern __shared__ __align__(16) unsigned long long s_list[];      // smem_cap keys (power of two), then the ROI tile
     __shared__ unsigned long long s_red[kSelThreads / 32];
     __shared__ float s_maxw[kSelThreads / 32];
-    __shared__ unsigned s_acc[kMaxAccepted];
+    __shared__ __align__(16) unsigned s_acc[kMaxAccepted + 4];   // accepted corners (x | y << 16), padded with far-away sentinels
     __shared__ int s_nc, s_nout;
 
     const DetectTarget T = targets[blockIdx.x];
@@ -126,6 +126,7 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
         return;
     }
     if (tid == 0) { s_nc = 0; s_nout = 0; }
+    for (int i = tid; i < kMaxAccepted + 4; i += kSelThreads) s_acc[i] = 0xffffffffu;
 
     // 0. ROI plus a one-pixel ring (inside the frame) into shared memory: many loads in flight instead of one
     //    dependent load per loop trip.  ROIs that do not fit read the map through L1 instead.
@@ -222,33 +223,48 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
             }
         __syncthreads();
         if (warp == 0) {
+            // One warp walks the sorted list 32 candidates at a time.  (a) drop candidates closer than min_dist to a
+            // corner accepted in an earlier chunk (4 accepted corners per shared-memory load); (b) every lane builds
+            // the bit mask of EARLIER lanes of the chunk that are too close; (c) the in-order greedy rule becomes a
+            // 32-step bit recurrence that all lanes evaluate identically: lane j is accepted iff it survived (a) and
+            // none of its close predecessors was accepted.
             for (int base = 0; base < nc && n_out < max_per_target; base += 32) {
                 const unsigned long long key = (base + lane < nc) ? s_list[base + lane] : 0ull;
                 const unsigned idx = (unsigned)key;
                 const float x = (float)(int)(idx % (unsigned)w), y = (float)(int)(idx / (unsigned)w);
                 bool alive = key != 0ull;
-                if (suppress)
-                    for (int a = 0; a < n_out; ++a) {
-                        const unsigned q = s_acc[a];
-                        const float dx = x - (float)(int)(q & 0xffffu), dy = y - (float)(int)(q >> 16);
-                        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2) alive = false;
+                unsigned near = 0u;
+                if (suppress) {
+                    for (int a = 0; a < n_out; a += 4) {
+                        const uint4 q = *reinterpret_cast<const uint4 *>(&s_acc[a]);
+                        const unsigned qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float dx = x - (float)(int)(qq[u] & 0xffffu), dy = y - (float)(int)(qq[u] >> 16);
+                            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2) alive = false;
+                        }
                     }
-                while (n_out < max_per_target) {
-                    const unsigned msk = __ballot_sync(0xffffffffu, alive);
-                    if (!msk) break;
-                    const int i = __ffs(msk) - 1;
-                    const float bx = __shfl_sync(0xffffffffu, x, i), by = __shfl_sync(0xffffffffu, y, i);
-                    if (lane == i) {
-                        s_acc[n_out] = (unsigned)(int)bx | ((unsigned)(int)by << 16);
-                        my_out[n_out] = make_float2(bx, by);
-                        alive = false;
-                    } else if (suppress && alive) {
-                        const float dx = x - bx, dy = y - by;
-                        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2) alive = false;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float dx = x - __shfl_sync(0xffffffffu, x, i), dy = y - __shfl_sync(0xffffffffu, y, i);
+                        if (i < lane && __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2) near |= 1u << i;
                     }
-                    ++n_out;
-                    __syncwarp();
                 }
+                const unsigned pre = __ballot_sync(0xffffffffu, alive);
+                unsigned acc = 0u;
+                int room = max_per_target - n_out;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const unsigned nj = __shfl_sync(0xffffffffu, near, j);
+                    if (room > 0 && ((pre >> j) & 1u) && (nj & acc) == 0u) { acc |= 1u << j; --room; }
+                }
+                if ((acc >> lane) & 1u) {
+                    const int slot = n_out + __popc(acc & ((1u << lane) - 1u));
+                    s_acc[slot] = (unsigned)(int)x | ((unsigned)(int)y << 16);
+                    my_out[slot] = make_float2(x, y);
+                }
+                n_out += __popc(acc);
+                __syncwarp();
             }
             if (lane == 0) s_nout = n_out;
         }

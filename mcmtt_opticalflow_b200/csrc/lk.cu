@@ -283,7 +283,13 @@ constexpr int kJWords = 392;                      // 30 rows x 13 words, rounded
 constexpr int kDxPitch = 28;                      // words per staged derivative row = 7 groups of 4 pixels
 constexpr int kDxWords = kPatch * kDxPitch;       // 616
 constexpr int kWarpSmemWords = kIWords + kJWords + kDxWords;   // 1296 words = 5184 B per warp
-constexpr int kWarpsPerCta = 8;
+#ifndef PSNW_LK_WARPS
+#define PSNW_LK_WARPS 4
+#endif
+#ifndef PSNW_LK_MINB
+#define PSNW_LK_MINB 4
+#endif
+constexpr int kWarpsPerCta = PSNW_LK_WARPS;
 
 __device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c)
 {
@@ -589,7 +595,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
     o.x = next_x; o.y = next_y; o.st = st; o.err = st ? er : 0.f;
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, PSNW_LK_MINB)
 lk_w21_kernel(const __grid_constant__ LkParams P)
 {
     __shared__ __align__(16) uint32_t smem[kWarpsPerCta * kWarpSmemWords];

@@ -36,7 +36,9 @@ for a, s, n, sm in inst:
 src = {}
 print("total instructions %d (%.1f per unit)" % (tot, tot / div))
 stot = sum(samp.values()) or 1
-for k, n in agg.most_common(40):
+order = samp.most_common(40) if len(sys.argv) > 5 and sys.argv[5] == "samples" else agg.most_common(40)
+for k, _n in order:
+    n = agg[k]
     f, _, ln = k.partition(":")
     text = ""
     try:
