@@ -205,44 +205,43 @@ class GpuRig:
     def prime(self, host):
         """First frame + first seeds so that every timed step has a previous frame to track from."""
         self._push(pingpong(0), host)
-        seeds = (self.h_seeds if host else self.d_seeds)[self.which]
-        counts = self.h_counts_det if host else self.d_counts_det
-        self._detect(pingpong(0), seeds, counts, self.klt.MEM_PINNED if host else self.klt.MEM_DEVICE)
+        self._detect(pingpong(0), self.d_seeds[self.which], self.d_counts_det, self.klt.MEM_DEVICE)
         boxes0 = np.concatenate([self.boxes[c][pingpong(0)] for c in range(self.ncam)])
-        if host:
-            self.h_boxes_in.copy_(self.torch.from_numpy(boxes0))
-        else:
-            self.d_boxes_in.copy_(self.torch.from_numpy(boxes0).to(self.dev))
+        self.d_boxes_in.copy_(self.torch.from_numpy(boxes0).to(self.dev))
         self.ctx.sync()
         self.step_idx = 1
 
     def step(self, host):
-        """One frame time of the rig.  host=False: device-resident buffers; host=True: pinned host buffers."""
+        """One frame time of the rig.
+        host=False: frames already in HBM.  host=True (end to end): the step's inputs -- the 4 new frames, in pinned
+        host memory, and the detection boxes, in pageable host memory -- are copied in, and the step's results
+        (tracked points, status, updated boxes, inlier counts and mask) are copied out to pinned host memory.
+        Seeds are internal state of the path (detect output -> next step's track input) and stay on the device.
+        Detection of the next step's seeds runs on the auxiliary stream and overlaps with tracking."""
         klt, ctx = self.klt, self.ctx
         t_idx = pingpong(self.step_idx)
-        mem = klt.MEM_PINNED if host else klt.MEM_DEVICE
         cur, nxt = self.which, self.which ^ 1
-        if host:
-            seeds, seeds_next = self.h_seeds[cur], self.h_seeds[nxt]
-            out, st, err, fb = self.h_out, self.h_status, self.h_err, self.h_fb
-            b_in, b_out, mask, cnt, off, cdet = self.h_boxes_in, self.h_boxes_out, self.h_mask, self.h_counts, self.h_off, self.h_counts_det
-        else:
-            seeds, seeds_next = self.d_seeds[cur], self.d_seeds[nxt]
-            out, st, err, fb = self.d_out, self.d_status, self.d_err, self.d_fb
-            b_in, b_out, mask, cnt, off, cdet = self.d_boxes_in, self.d_boxes_out, self.d_mask, self.d_counts, self.d_off, self.d_counts_det
+        seeds, seeds_next = self.d_seeds[cur], self.d_seeds[nxt]
         self._push(t_idx, host)
-        jobs = self._jobs(seeds.data_ptr(), out.data_ptr(), st.data_ptr(), err.data_ptr(), fb.data_ptr())
-        ctx._ck(ctx.lib.psnw_klt_track_batch(ctx._h, jobs, self.ncam, mem))
-        ctx.box_update_raw(b_in.data_ptr(), self.ntargets, seeds.data_ptr(), out.data_ptr(), st.data_ptr(), off.data_ptr(),
-                           b_out.data_ptr(), mask.data_ptr(), cnt.data_ptr(), mem)
-        self._detect(t_idx, seeds_next, cdet, mem)
+        self._detect(t_idx, seeds_next, self.d_counts_det, klt.MEM_DEVICE | klt.MEM_OVERLAP)
+        jobs = self._jobs(seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(), self.d_err.data_ptr(), self.d_fb.data_ptr())
+        ctx._ck(ctx.lib.psnw_klt_track_batch(ctx._h, jobs, self.ncam, klt.MEM_DEVICE))
+        ctx.box_update_raw(self.d_boxes_in.data_ptr(), self.ntargets, seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(),
+                           self.d_off.data_ptr(), self.d_boxes_out.data_ptr(), self.d_mask.data_ptr(), self.d_counts.data_ptr(), klt.MEM_DEVICE)
+        ctx.join()
+        if host:
+            self.h_out.copy_(self.d_out, non_blocking=True)
+            self.h_status.copy_(self.d_status, non_blocking=True)
+            self.h_boxes_out.copy_(self.d_boxes_out, non_blocking=True)
+            self.h_counts.copy_(self.d_counts, non_blocking=True)
+            self.h_mask.copy_(self.d_mask, non_blocking=True)
         self.which = nxt
         self.step_idx += 1
 
     def e2e_bytes(self):
         n, nt = self.npts, self.ntargets
-        h2d = self.ncam * self.w * self.h + n * 8 + (n * 8 * 2 + n + (nt + 1) * 4 + nt * 32)
-        d2h = n * 8 + n + n * 4 + n * 4 + nt * 32 + n + nt * 4 + n * 8 + nt * 4
+        h2d = self.ncam * self.w * self.h + nt * 32          # frames + detection boxes (PSN_Rect)
+        d2h = n * 8 + n + nt * 32 + nt * 4 + n               # points, status, boxes, inlier counts, inlier mask
         return h2d, d2h
 
     def timed(self, steps, warmup, host, sampler=None):

@@ -53,6 +53,11 @@ enum {
 };
 
 enum { PSNW_MEM_HOST = 0, PSNW_MEM_PINNED = 1, PSNW_MEM_DEVICE = 2 };
+/* OR-ed into the mem_flags of psnw_klt_detect(_batch) (PINNED / DEVICE only): the detection runs on an auxiliary
+ * stream forked from the context stream at the call, so the psnw_klt_track / psnw_box_update calls that FOLLOW
+ * overlap with it (they must not consume its outputs).  The outputs are complete after psnw_join (device-side
+ * join, no host block), psnw_sync, or the next push / detect call. */
+#define PSNW_MEM_OVERLAP 0x100
 
 /* psnw_box_update estimators */
 enum {
@@ -182,6 +187,8 @@ PSNW_API int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_target
                              double *boxes_out, uint8_t *inlier_mask, int *inlier_counts, int mem_flags);
 
 PSNW_API int psnw_sync(psnw_ctx *ctx);
+/* Device-side join of an overlapped detect into the context stream (see PSNW_MEM_OVERLAP). */
+PSNW_API int psnw_join(psnw_ctx *ctx);
 PSNW_API const char *psnw_last_error(psnw_ctx *ctx);
 PSNW_API void *psnw_get_stream(psnw_ctx *ctx);
 

@@ -34,6 +34,9 @@ struct psnw_ctx {
     psnw_params p;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t aux = nullptr;           // PSNW_MEM_OVERLAP detect calls run here, forked from / joined to `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool aux_pending = false;
     PyrDesc pyr;
     CUtensorMap maps[PSNW_MAX_LEVELS];
     int planes = 0;
@@ -42,7 +45,8 @@ struct psnw_ctx {
     uint64_t seq = 0;
     DevBuf arena;                         // per-call device scratch (stream ordered)
     size_t arena_off = 0;
-    DevBuf desc;                          // job / group / target descriptors
+    DevBuf desc;                          // job / group descriptors (track)
+    DevBuf det_desc;                      // target descriptors + staged outputs (detect; may run on the aux stream)
     DevBuf cand;                          // detect candidate scratch
     DevBuf bgr;                           // BGR staging for psnw_push_frames_bgr
     std::vector<float *> eig;             // per camera min-eig map (level-0 pitch), lazily allocated
@@ -111,10 +115,11 @@ int stage_acquire(psnw_ctx *ctx, size_t bytes, StageSlot **out)
     return PSNW_OK;
 }
 
-int stage_upload(psnw_ctx *ctx, StageSlot *s, void *dst, size_t bytes)
+int stage_upload(psnw_ctx *ctx, StageSlot *s, void *dst, size_t bytes, cudaStream_t stream = nullptr)
 {
-    CK(cudaMemcpyAsync(dst, s->h, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(s->ev, ctx->stream));
+    if (!stream) stream = ctx->stream;
+    CK(cudaMemcpyAsync(dst, s->h, bytes, cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(s->ev, stream));
     s->pending = true;
     return PSNW_OK;
 }
@@ -159,6 +164,16 @@ bool slot_ok(const psnw_ctx *c, int cam, int slot)
     return cam >= 0 && cam < c->p.n_cameras && slot >= 0 && slot < c->held[cam];
 }
 
+// make the main stream wait for an overlapped detect (no host block)
+int join_aux(psnw_ctx *ctx)
+{
+    if (ctx->aux_pending) {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+        ctx->aux_pending = false;
+    }
+    return PSNW_OK;
+}
+
 // buildOpticalFlowPyramid's truncation: a level is kept while both dimensions stay > window
 int effective_max_level(const psnw_ctx *c, int win_w, int win_h)
 {
@@ -196,6 +211,7 @@ int advance_ring(psnw_ctx *ctx, int n, const int *cams, std::vector<int> &planes
         for (int j = 0; j < i; ++j)
             if (cams[j] == cam) return fail(ctx, PSNW_EARG, "duplicate camera in psnw_push_frames");
     }
+    if (int rc = join_aux(ctx)) return rc;      // a push may recycle the slot an overlapped detect still reads
     planes.resize(n);
     for (int i = 0; i < n; ++i) {
         const int cam = cams[i];
@@ -264,6 +280,11 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
         ctx->own_stream = true;
     }
 
+    if (cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)
+        return bail(PSNW_ECUDA);
+
     // level geometry; levels smaller than 8 px are not built (no window fits them anyway)
     int w = p->width, h = p->height, levels = 0;
     for (int l = 0; l < p->levels; ++l) {
@@ -299,7 +320,12 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
 int psnw_destroy(psnw_ctx *ctx)
 {
     if (!ctx) return PSNW_EARG;
+    if (ctx->aux) cudaStreamSynchronize(ctx->aux);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->det_desc.p) cudaFree(ctx->det_desc.p);
     for (int l = 0; l < PSNW_MAX_LEVELS; ++l) {
         if (ctx->pyr.lv[l].img) cudaFree(ctx->pyr.lv[l].img);
         if (ctx->pyr.lv[l].dxy) cudaFree(ctx->pyr.lv[l].dxy);
@@ -564,7 +590,7 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
 }
 
 // min-eigenvalue maps of the (cam, slot) frames in `cs`, computed once per pushed frame (tag = push sequence)
-static int ensure_min_eig(psnw_ctx *ctx, const std::vector<std::pair<int, int>> &cs)
+static int ensure_min_eig(psnw_ctx *ctx, const std::vector<std::pair<int, int>> &cs, cudaStream_t stream)
 {
     const LevelGeom &l0 = ctx->pyr.lv[0];
     EigList el;
@@ -581,14 +607,14 @@ static int ensure_min_eig(psnw_ctx *ctx, const std::vector<std::pair<int, int>> 
         el.plane[el.n] = plane;
         el.eig[el.n] = ctx->eig[cam];
         if (++el.n == 24) {
-            const int r = launch_min_eig(l0, el, ctx->stream);
+            const int r = launch_min_eig(l0, el, stream);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "min_eig_kernel launch", cudaGetLastError());
             ctx->launches += r;
             el.n = 0;
         }
     }
     if (el.n) {
-        const int r = launch_min_eig(l0, el, ctx->stream);
+        const int r = launch_min_eig(l0, el, stream);
         if (r < 0) return fail(ctx, PSNW_ECUDA, "min_eig_kernel launch", cudaGetLastError());
         ctx->launches += r;
     }
@@ -617,7 +643,19 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
     if (total == 0) return PSNW_OK;
     if (total > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_klt_detect: max_targets exceeded");
     const LevelGeom &l0 = ctx->pyr.lv[0];
-    int rc = ensure_min_eig(ctx, cs);
+    // PSNW_MEM_OVERLAP: run on the auxiliary stream, forked from the main stream here and joined by psnw_join /
+    // psnw_sync / the next push or detect, so that the following track + box_update calls overlap with it
+    const bool overlap = (mem_flags & PSNW_MEM_OVERLAP) != 0 && (mem_flags & 0xff) != PSNW_MEM_HOST;
+    mem_flags &= 0xff;
+    int rc = join_aux(ctx);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    if (overlap) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        st = ctx->aux;
+    }
+    rc = ensure_min_eig(ctx, cs, st);
     if (rc) return rc;
 
     // mask ROI = box.cropWithSize(cols, rows).cv()  (PSNWhere_Types.h:146-153,181; Tracker2D.cpp:735).  `boxes` is
@@ -626,10 +664,10 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
     const size_t tb = (sizeof(DetectTarget) * total + 255) & ~(size_t)255;
     const size_t out_b = dev ? 0 : (((size_t)total * max_per_target * sizeof(float2) + 255) & ~(size_t)255);
     const size_t cnt_b = dev ? 0 : ((sizeof(int) * total + 255) & ~(size_t)255);
-    rc = ensure(ctx, ctx->desc, tb + out_b + cnt_b);
+    rc = ensure(ctx, ctx->det_desc, tb + out_b + cnt_b);
     if (rc) return rc;
-    float2 *s_out = reinterpret_cast<float2 *>(ctx->desc.p + tb);
-    int *s_cnt = reinterpret_cast<int *>(ctx->desc.p + tb + out_b);
+    float2 *s_out = reinterpret_cast<float2 *>(ctx->det_desc.p + tb);
+    int *s_cnt = reinterpret_cast<int *>(ctx->det_desc.p + tb + out_b);
 
     std::vector<DetectTarget> T(total);
     size_t cand_total = 0;
@@ -663,11 +701,11 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
     rc = stage_acquire(ctx, tb, &s);
     if (rc) return rc;
     memcpy(s->h, T.data(), sizeof(DetectTarget) * total);
-    rc = stage_upload(ctx, s, ctx->desc.p, sizeof(DetectTarget) * total);
+    rc = stage_upload(ctx, s, ctx->det_desc.p, sizeof(DetectTarget) * total, st);
     if (rc) return rc;
-    const int r = launch_detect_select(l0.w, l0.h, l0.pitch, reinterpret_cast<const DetectTarget *>(ctx->desc.p), total,
+    const int r = launch_detect_select(l0.w, l0.h, l0.pitch, reinterpret_cast<const DetectTarget *>(ctx->det_desc.p), total,
                                        max_per_target, quality, min_dist, reinterpret_cast<unsigned long long *>(ctx->cand.p),
-                                       max_area, max_tile, ctx->stream);
+                                       max_area, max_tile, st);
     if (r < 0) return fail(ctx, PSNW_ECUDA, "detect_select_kernel launch", cudaGetLastError());
     ctx->launches += r;
     if (!dev) {
@@ -676,11 +714,15 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
             const psnw_detect_job &J = jobs[j];
             if (J.n_targets == 0) continue;
             CK(cudaMemcpyAsync(J.pts_xy, s_out + (size_t)t0 * max_per_target, (size_t)J.n_targets * max_per_target * sizeof(float2),
-                               cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(J.counts, s_cnt + t0, sizeof(int) * J.n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+                               cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(J.counts, s_cnt + t0, sizeof(int) * J.n_targets, cudaMemcpyDeviceToHost, st));
             t0 += J.n_targets;
         }
         if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (overlap) {
+        CK(cudaEventRecord(ctx->ev_join, ctx->aux));
+        ctx->aux_pending = true;
     }
     return PSNW_OK;
 }
@@ -693,9 +735,16 @@ int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n
     return psnw_klt_detect_batch(ctx, &j, 1, max_per_target, quality, min_dist, mem_flags);
 }
 
+int psnw_join(psnw_ctx *ctx)
+{
+    if (!ctx) return PSNW_EARG;
+    return join_aux(ctx);
+}
+
 int psnw_sync(psnw_ctx *ctx)
 {
     if (!ctx) return PSNW_EARG;
+    if (int rc = join_aux(ctx)) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return PSNW_OK;
 }
@@ -732,7 +781,9 @@ int psnw_read_min_eig(psnw_ctx *ctx, int cam, int slot, float *eig_out)
     if (!ctx || !eig_out) return PSNW_EARG;
     if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_read_min_eig: camera/slot holds no frame");
     const LevelGeom &l0 = ctx->pyr.lv[0];
-    const int rc = ensure_min_eig(ctx, {{cam, slot}});
+    int rc = join_aux(ctx);
+    if (rc) return rc;
+    rc = ensure_min_eig(ctx, {{cam, slot}}, ctx->stream);
     if (rc) return rc;
     float *eig = ctx->eig[cam];
     CK(cudaStreamSynchronize(ctx->stream));

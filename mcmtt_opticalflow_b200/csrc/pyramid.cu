@@ -88,8 +88,12 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
     const uint32_t bar_a = smem_u32(&bar);
 
 #ifndef PSNW_DEBUG_NO_TMA
+    // Programmatic dependent launch: let the next level's grid start its prologue now, and wait for the previous
+    // level's grid (which wrote this level's u8 image) to complete before the first read.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) mbar_init(bar_a, 1);
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
         mbar_expect_tx(bar_a, kBoxW * kBoxH);
         tma_load_3d(smem_u32(tile), &map, x0 - kHaloL, y0 - kHaloT, plane, bar_a);
@@ -228,12 +232,19 @@ int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, c
     const LevelGeom &cur = pyr.lv[level];
     const bool has_next = level + 1 < pyr.levels;
     const LevelGeom &nxt = pyr.lv[has_next ? level + 1 : level];
-    dim3 grid((cur.w + kTileW - 1) / kTileW, (cur.h + kTileH - 1) / kTileH, planes.n);
-    if (has_next)
-        pyr_scharr_kernel<true><<<grid, 128, 0, stream>>>(*map_in, cur, nxt, planes);
-    else
-        pyr_scharr_kernel<false><<<grid, 128, 0, stream>>>(*map_in, cur, nxt, planes);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((cur.w + kTileW - 1) / kTileW, (cur.h + kTileH - 1) / kTileH, planes.n);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL: overlap this launch with the previous level's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = has_next ? cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<true>, *map_in, cur, nxt, planes)
+                                   : cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<false>, *map_in, cur, nxt, planes);
+    return e == cudaSuccess ? 1 : -1;
 }
 
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,

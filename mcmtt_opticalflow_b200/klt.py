@@ -20,6 +20,7 @@ LIB_PATH = os.environ.get("PSNW_KLT_LIB") or os.path.join(_HERE, "libpsnw_klt.so
 
 OK, EARG, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4
 MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
+MEM_OVERLAP = 0x100
 BOX_REFERENCE = 0
 _ERR = {EARG: "PSNW_EARG", ECUDA: "PSNW_ECUDA", ENOMEM: "PSNW_ENOMEM", ESTATE: "PSNW_ESTATE"}
 
@@ -51,7 +52,7 @@ class DetectJob(C.Structure):
 
 
 EXPORTS = [
-    "psnw_klt_detect_batch", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
+    "psnw_klt_detect_batch", "psnw_join", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
     "psnw_push_frames_bgr", "psnw_frames_held", "psnw_klt_detect", "psnw_klt_track", "psnw_klt_track_batch",
     "psnw_box_update", "psnw_sync", "psnw_last_error", "psnw_get_stream", "psnw_level_info", "psnw_read_level",
     "psnw_read_min_eig", "psnw_launch_count", "psnw_push_frame_bytes", "psnw_rebuild_pyramids", "psnw_levels_built",
@@ -79,6 +80,7 @@ def load():
         lib.psnw_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params)]
         lib.psnw_destroy.argtypes = [C.c_void_p]
         lib.psnw_sync.argtypes = [C.c_void_p]
+        lib.psnw_join.argtypes = [C.c_void_p]
         lib.psnw_frames_held.argtypes = [C.c_void_p, C.c_int]
         lib.psnw_levels_built.argtypes = [C.c_void_p]
         lib.psnw_push_frames.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int]
@@ -163,6 +165,9 @@ class KLTContext:
 
     def sync(self):
         self._ck(self.lib.psnw_sync(self._h))
+
+    def join(self):
+        self._ck(self.lib.psnw_join(self._h))
 
     @property
     def stream(self):

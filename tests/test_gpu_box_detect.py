@@ -101,3 +101,33 @@ def test_detect_full_rig_vs_oracle(oracle):
         assert np.array_equal(pts[0, :counts[0]], want)
         pts, counts = c.detect(np.zeros((0, 4)), 10)
         assert counts.shape == (0,)
+
+
+def test_overlapped_batched_detect_matches_plain(oracle):
+    """PSNW_MEM_OVERLAP: detect on the auxiliary stream while a track launch runs on the main stream; results must
+    equal the plain call, for several cameras in one batched call."""
+    import ctypes as C
+    import torch
+    w, h, ncam, ntgt, per = 384, 288, 3, 10, 40
+    cams = [synth.Camera(w, h, ntgt, cam=20 + c) for c in range(ncam)]
+    with klt.KLTContext(w, h, n_cameras=ncam, levels=3, fb_thresh=1.0) as c:
+        f0 = [cm.frame(0) for cm in cams]; f1 = [cm.frame(1) for cm in cams]
+        c.push_frames(f0); c.push_frames(f1)
+        plain = [c.detect(cams[k].boxes(1), per, 0.01, 3.0, cam=k) for k in range(ncam)]
+        boxes = [np.ascontiguousarray(cams[k].boxes(1)) for k in range(ncam)]
+        d_pts = torch.zeros((ncam, ntgt, per, 2), dtype=torch.float32, device="cuda")
+        d_cnt = torch.zeros((ncam, ntgt), dtype=torch.int32, device="cuda")
+        jobs = (klt.DetectJob * ncam)()
+        for k in range(ncam):
+            jobs[k].cam, jobs[k].slot, jobs[k].boxes, jobs[k].n_targets = k, 0, boxes[k].ctypes.data, ntgt
+            jobs[k].pts_xy, jobs[k].counts = d_pts[k].data_ptr(), d_cnt[k].data_ptr()
+        torch.cuda.synchronize()
+        c._ck(c.lib.psnw_klt_detect_batch(c._h, jobs, ncam, per, 0.01, 3.0, klt.MEM_DEVICE | klt.MEM_OVERLAP))
+        pts = np.random.default_rng(0).uniform(20, 250, size=(2000, 2)).astype(np.float32)
+        c.track(pts, cam=0)                                   # main-stream work in flight next to the detect
+        c.sync()                                              # joins the auxiliary stream
+        g_pts, g_cnt = d_pts.cpu().numpy(), d_cnt.cpu().numpy()
+        for k in range(ncam):
+            assert np.array_equal(g_cnt[k], plain[k][1])
+            assert np.array_equal(g_pts[k], plain[k][0])
+            assert (g_pts[k][0, g_cnt[k][0]:] == -1e6).all()  # unused slots carry the sentinel
