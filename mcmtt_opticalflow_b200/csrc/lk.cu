@@ -488,7 +488,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
 
         // ---- template into registers ----
         int tC[14], tIx[14], tIy[14];          // tC = 256 - 512 * I: the dp2a chain then yields (J - I) << 9 directly
-        int a11 = 0, a12 = 0, a22 = 0;
+        int a11[2] = {0, 0}, a12[2] = {0, 0}, a22[2] = {0, 0};     // one accumulator chain per run: more ILP
         {
             const int wt = (w00 & 0xffff) | (w01 << 16), wb = (w10 & 0xffff) | (w11 << 16);
             const int c256[7] = {256, 256, 256, 256, 256, 256, 256};
@@ -508,14 +508,14 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                     tC[run * 7 + k] = 256 - ((v[k] >> 9) << 9);
                     tIx[run * 7 + k] = ix;
                     tIy[run * 7 + k] = iy;
-                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                    a11[run] += ix * ix; a12[run] += ix * iy; a22[run] += iy * iy;
                     q0 = n0; q1 = n1;
                 }
             }
         }
         if (staged) { u8_commit<kJPatch>(lj, JB, Lp, Lw, Lh, sx0, sy0, jp, lane, dr3, g3); offJ = lj.off; }
         __syncwarp();
-        const long long s11 = warp_sum_i32(a11), s12 = warp_sum_i32(a12), s22 = warp_sum_i32(a22);
+        const long long s11 = warp_sum_i32(a11[0] + a11[1]), s12 = warp_sum_i32(a12[0] + a12[1]), s22 = warp_sum_i32(a22[0] + a22[1]);
         float A11, A12, A22, Dinv;
         if (!make_system(s11, s12, s22, kW, kW, P.min_eig, A11, A12, A22, Dinv)) {
             if (level == 0) st = 0;
@@ -543,7 +543,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                 staged = true;
             }
             const int bx = offJ + (inx - sx0), by = iny - sy0;
-            int b1 = 0, b2 = 0;
+            int b1[2] = {0, 0}, b2[2] = {0, 0};
 #pragma unroll
             for (int run = 0; run < 2; ++run) {
                 int v[7];
@@ -551,11 +551,11 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
                     const int diff = v[k] >> 9;
-                    b1 += diff * tIx[run * 7 + k];
-                    b2 += diff * tIy[run * 7 + k];
+                    b1[run] += diff * tIx[run * 7 + k];
+                    b2[run] += diff * tIy[run * 7 + k];
                 }
             }
-            const long long sb1 = warp_sum_i32(b1), sb2 = warp_sum_i32(b2);
+            const long long sb1 = warp_sum_i32(b1[0] + b1[1]), sb2 = warp_sum_i32(b2[0] + b2[1]);
             if (lk_step(P, sb1, sb2, A11, A12, A22, Dinv, half, half, j, nx, ny, pdx, pdy, next_x, next_y)) break;
         }
 
