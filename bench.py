@@ -39,6 +39,7 @@ WORKLOADS = {
     "c1": (768, 576, 1, 20, 100, 3),
     "c2": (768, 576, 4, 40, 100, 4),
     "c3": (1920, 1080, 1, 200, 256, 4),
+    "c4": (3840, 2160, 1, 0, 0, 5),     # dense grid KLT, stride 4 px: 959 x 539 = 516 901 seeds, track + FB only
 }
 CYCLE = 6                       # distinct time steps rendered per camera (played ping-pong)
 QUALITY, MIN_DIST = 0.01, 3.0   # psnw_klt_detect / goodFeaturesToTrack parameters
@@ -122,7 +123,11 @@ class GpuRig:
         from mcmtt_opticalflow_b200 import klt
         self.torch, self.klt = torch, klt
         self.w, self.h, self.ncam, self.ntgt, self.per, self.levels = WORKLOADS[wl]
-        self.npts_cam = self.ntgt * self.per
+        self.grid = self.ntgt == 0
+        if self.grid:
+            from mcmtt_opticalflow_b200 import synth as _synth
+            self.grid_pts = _synth.grid_seeds(self.w, self.h, 4, 2)
+        self.npts_cam = len(self.grid_pts) if self.grid else self.ntgt * self.per
         self.npts = self.npts_cam * self.ncam
         self.ntargets = self.ntgt * self.ncam
         self.frames, self.boxes = render_rig(wl, rank)
@@ -147,7 +152,7 @@ class GpuRig:
             self.d_boxes_out = t.zeros((self.ntargets, 4), dtype=t.float64, device=self.dev)
             self.d_mask = t.zeros(self.npts, dtype=t.uint8, device=self.dev)
             self.d_counts = t.zeros(self.ntargets, dtype=t.int32, device=self.dev)
-            off = np.arange(self.ntargets + 1, dtype=np.int32) * self.per
+            off = np.arange(self.ntargets + 1, dtype=np.int32) * max(self.per, 1)
             self.d_off = t.from_numpy(off).to(self.dev)
             self.h_off = t.from_numpy(off).pin_memory()
             # pinned host mirrors for the end-to-end arm
@@ -205,6 +210,12 @@ class GpuRig:
     def prime(self, host):
         """First frame + first seeds so that every timed step has a previous frame to track from."""
         self._push(pingpong(0), host)
+        if self.grid:
+            g = self.torch.from_numpy(np.tile(self.grid_pts, (self.ncam, 1))).to(self.dev)
+            self.d_seeds[0].copy_(g); self.d_seeds[1].copy_(g)
+            self.ctx.sync()
+            self.step_idx = 1
+            return
         self._detect(pingpong(0), self.d_seeds[self.which], self.d_counts_det, self.klt.MEM_DEVICE)
         boxes0 = np.concatenate([self.boxes[c][pingpong(0)] for c in range(self.ncam)])
         self.d_boxes_in.copy_(self.torch.from_numpy(boxes0).to(self.dev))
@@ -223,6 +234,14 @@ class GpuRig:
         cur, nxt = self.which, self.which ^ 1
         seeds, seeds_next = self.d_seeds[cur], self.d_seeds[nxt]
         self._push(t_idx, host)
+        if self.grid:                        # C4: dense grid, forward + backward LK + FB gate only
+            jobs = self._jobs(seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(), self.d_err.data_ptr(), self.d_fb.data_ptr())
+            ctx._ck(ctx.lib.psnw_klt_track_batch(ctx._h, jobs, self.ncam, klt.MEM_DEVICE))
+            if host:
+                self.h_out.copy_(self.d_out, non_blocking=True)
+                self.h_status.copy_(self.d_status, non_blocking=True)
+            self.step_idx += 1
+            return
         self._detect(t_idx, seeds_next, self.d_counts_det, klt.MEM_DEVICE | klt.MEM_OVERLAP)
         jobs = self._jobs(seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(), self.d_err.data_ptr(), self.d_fb.data_ptr())
         ctx._ck(ctx.lib.psnw_klt_track_batch(ctx._h, jobs, self.ncam, klt.MEM_DEVICE))
@@ -240,6 +259,8 @@ class GpuRig:
 
     def e2e_bytes(self):
         n, nt = self.npts, self.ntargets
+        if self.grid:
+            return self.ncam * self.w * self.h, n * 8 + n
         h2d = self.ncam * self.w * self.h + nt * 32          # frames + detection boxes (PSN_Rect)
         d2h = n * 8 + n + nt * 32 + nt * 4 + n               # points, status, boxes, inlier counts, inlier mask
         return h2d, d2h
@@ -289,6 +310,8 @@ class GpuRig:
         """LK kernel alone (forward+backward fused launch): the newest frame's seeds tracked into the previous frame."""
         t = self.torch
         self.step(False)
+        if self.grid:
+            self.step(False)
         seeds = self.d_seeds[self.which]
         jobs = self._jobs(seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(), self.d_err.data_ptr(), self.d_fb.data_ptr(), 0, 1)
         with t.cuda.stream(self.stream):
@@ -318,6 +341,12 @@ class CpuRig:
         self.seeds = [None] * self.ncam
         self.prev_boxes = [None] * self.ncam
         self.t = [0] * self.ncam
+        self.grid = self.ntgt == 0
+        if self.grid:
+            from mcmtt_opticalflow_b200 import synth as _synth
+            self.seeds = [_synth.grid_seeds(self.w, self.h, 4, 2) for _ in range(self.ncam)]
+            self.t = [1] * self.ncam
+            return
         for c in range(self.ncam):
             self.seeds[c], _ = self._detect(c, 0)
             self.prev_boxes[c] = self.boxes[c][0]
@@ -340,6 +369,9 @@ class CpuRig:
         a, b = self.frames[c][t_prev], self.frames[c][t_cur]
         seeds = self.seeds[c]
         out, st, err, fb = self.ref.track_fb(a, b, seeds, (21, 21), self.levels - 1, fb_thresh=1.0)
+        if self.grid:
+            self.t[c] += 1
+            return len(seeds)
         for k in range(self.ntgt):
             s = slice(k * self.per, (k + 1) * self.per)
             self.po.local_search_klt(self.prev_boxes[c][k], seeds[s], out[s], st[s])
@@ -354,16 +386,19 @@ def cpu_measure(wl, steps, warmup, budget_s=20.0):
     rig = CpuRig(wl)
     for i in range(max(warmup, 1)):
         rig.step_cam(i % rig.ncam)
+        if rig.grid:
+            break
     n, pts, t0 = 0, 0, time.perf_counter()
     while n < steps and (time.perf_counter() - t0) < budget_s:
         pts += rig.step_cam(n % rig.ncam)
         n += 1
     dt = time.perf_counter() - t0
     return {"value": pts / dt, "unit": "points/s", "cores": rig.threads, "kind": "port",
-            "sample": "%d camera-frames of %dx%d (%d seeds each, fwd+bwd LK 21x21/%d levels via cv2 %s with %d threads, "
+            "sample": "%d camera-frames of %dx%d (%d seeds each; c4 = stride-4 grid with LK + FB only; fwd+bwd LK 21x21/%d levels via cv2 %s with %d threads, "
                       "FB gate, C port of LocalSearchKLT per target, cornerMinEigenVal once per frame + C port of the GFTT "
-                      "selection per box) in %.2f s" % (n, rig.w, rig.h, rig.ntgt * rig.per, rig.levels, rig.cv2.__version__,
+                      "selection per box) in %.2f s" % (n, rig.w, rig.h, len(rig.seeds[0]), rig.levels, rig.cv2.__version__,
                                                        rig.threads, dt),
+            "seeds_per_camera_frame": len(rig.seeds[0]),
             "frames_per_s": n / dt, "ms_per_camera_frame": 1e3 * dt / max(n, 1), "camera_frames": n}
 
 
@@ -382,9 +417,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     w, h, ncam, ntgt, per, levels = WORKLOADS[args.workload]
-    config = {"workload": "%s: %d-view rig %dx%d gray per GPU, %d targets/view x %d seeds, %d-level pyramid, 21x21 window, "
-                          "fwd+bwd LK + FB gate + LocalSearchKLT box update + Shi-Tomasi re-detect" % (args.workload, ncam, w, h, ntgt, per, levels),
-              "cameras_per_gpu": ncam, "points_per_step_per_gpu": ncam * ntgt * per, "lk_solves_per_step_per_gpu": 2 * ncam * ntgt * per,
+    npts_cfg = ncam * ntgt * per if ntgt else ncam * (((w - 3) // 4) + 1) * (((h - 3) // 4) + 1)
+    config = {"workload": "%s: %d-view rig %dx%d gray per GPU, %s, %d-level pyramid, 21x21 window, fwd+bwd LK + FB gate%s"
+                          % (args.workload, ncam, w, h, ("%d targets/view x %d seeds" % (ntgt, per)) if ntgt else "dense grid stride 4 px",
+                             levels, " + LocalSearchKLT box update + Shi-Tomasi re-detect" if ntgt else ""),
+              "cameras_per_gpu": ncam, "points_per_step_per_gpu": npts_cfg, "lk_solves_per_step_per_gpu": 2 * npts_cfg,
               "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "cameras sharded, %d rig(s), no collective" % world}
 
     if args.impl == "reference":
