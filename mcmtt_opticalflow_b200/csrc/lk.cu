@@ -120,14 +120,31 @@ __device__ __forceinline__ int sample_u8(const uint8_t *img, int pitch, int w, i
     return (r0[X0] * w00 + r0[X1] * w01 + r1[X0] * w10 + r1[X1] * w11 + (1 << 8)) >> 9;
 }
 
+constexpr int kGenThreads = 128;           // generic-window kernel: one CTA per point
+
+// exact block-wide sums of three int64 values, result broadcast to every thread; `sel` alternates between two
+// scratch slots so that one barrier per call is enough
+__device__ __forceinline__ void block_sum3(long long &a, long long &b, long long &c, long long *red, int &sel, int tid)
+{
+    a = warp_sum_ll(a); b = warp_sum_ll(b); c = warp_sum_ll(c);
+    long long *r = red + sel * (3 * (kGenThreads / 32));
+    if ((tid & 31) == 0) { r[(tid >> 5) * 3] = a; r[(tid >> 5) * 3 + 1] = b; r[(tid >> 5) * 3 + 2] = c; }
+    __syncthreads();
+    a = 0; b = 0; c = 0;
+#pragma unroll
+    for (int w = 0; w < kGenThreads / 32; ++w) { a += r[w * 3]; b += r[w * 3 + 1]; c += r[w * 3 + 2]; }
+    sel ^= 1;
+}
+
 __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int ww, int wh, int max_level,
-                              float px, float py, short *Iw, short2 *dIw, int lane, Solve &o)
+                              float px, float py, short *Iw, short2 *dIw, int tid, long long *red, Solve &o)
 {
     const float half_x = (ww - 1) * 0.5f, half_y = (wh - 1) * 0.5f;
     const int npx = ww * wh;
     float next_x = 0.f, next_y = 0.f, er = 0.f;
     int st = 1;
-    int lx0 = lane, ly0 = 0;                   // window coordinates of this lane's first pixel
+    int lx0 = tid, ly0 = 0;                    // window coordinates of this thread's first pixel
+    int rsel = 0;                              // reduction scratch toggles between two slots
     while (lx0 >= ww) { lx0 -= ww; ly0++; }
 
     for (int level = max_level; level >= 0; --level) {
@@ -154,7 +171,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
         long long s11 = 0, s12 = 0, s22 = 0;
         {
             int x = lx0, y = ly0;
-            for (int p = lane; p < npx; p += 32) {
+            for (int p = tid; p < npx; p += kGenThreads) {
                 const int X = ipx + x, Y = ipy + y;
                 const int ival = sample_u8(IA, L.pitch, L.w, L.h, X, Y, w00, w01, w10, w11);
                 const bool xi0 = (unsigned)X < (unsigned)L.w, xi1 = (unsigned)(X + 1) < (unsigned)L.w;
@@ -168,11 +185,11 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 Iw[p] = (short)ival;
                 dIw[p] = make_short2((short)ix, (short)iy);
                 s11 += (long long)(ix * ix); s12 += (long long)(ix * iy); s22 += (long long)(iy * iy);
-                x += 32;
+                x += kGenThreads;
                 while (x >= ww) { x -= ww; y++; }
             }
         }
-        s11 = warp_sum_ll(s11); s12 = warp_sum_ll(s12); s22 = warp_sum_ll(s22);
+        block_sum3(s11, s12, s22, red, rsel, tid);
         float A11, A12, A22, Dinv;
         if (!make_system(s11, s12, s22, ww, wh, P.min_eig, A11, A12, A22, Dinv)) {
             if (level == 0) st = 0;
@@ -190,14 +207,14 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             long long sb1 = 0, sb2 = 0;
             int x = lx0, y = ly0;
-            for (int p = lane; p < npx; p += 32) {
+            for (int p = tid; p < npx; p += kGenThreads) {
                 const int diff = sample_u8(JB, L.pitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
                 const short2 d = dIw[p];
                 sb1 += (long long)(diff * d.x); sb2 += (long long)(diff * d.y);
-                x += 32;
+                x += kGenThreads;
                 while (x >= ww) { x -= ww; y++; }
             }
-            sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
+            { long long z = 0; block_sum3(sb1, sb2, z, red, rsel, tid); }
             if (lk_step(P, sb1, sb2, A11, A12, A22, Dinv, half_x, half_y, j, nx, ny, pdx, pdy, next_x, next_y)) break;
         }
 
@@ -208,13 +225,13 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             bilinear_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
             long long se = 0;
             int x = lx0, y = ly0;
-            for (int p = lane; p < npx; p += 32) {
+            for (int p = tid; p < npx; p += kGenThreads) {
                 const int diff = sample_u8(JB, L.pitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
                 se += diff < 0 ? -diff : diff;
-                x += 32;
+                x += kGenThreads;
                 while (x >= ww) { x -= ww; y++; }
             }
-            se = warp_sum_ll(se);
+            { long long z0 = 0, z1 = 0; block_sum3(se, z0, z1, red, rsel, tid); }
             er = __fdiv_rn(__ll2float_rn(se), (float)(32 * ww * wh));
         }
     }
@@ -246,16 +263,16 @@ __device__ __forceinline__ void finish_point(const LkParams &P, const TrackJob &
     job.err[k] = f.err;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kGenThreads)
 lk_generic_kernel(const __grid_constant__ LkParams P, int max_win_px)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * (blockDim.x >> 5) + wib;
-    if (i >= P.n_pts) return;
-    const int stride = (max_win_px + 7) & ~7;
-    short2 *dIw = reinterpret_cast<short2 *>(smem_raw) + (size_t)wib * stride;
-    short *Iw = reinterpret_cast<short *>(reinterpret_cast<short2 *>(smem_raw) + (size_t)(blockDim.x >> 5) * stride) + (size_t)wib * stride;
+    __shared__ long long red[2 * 3 * (kGenThreads / 32)];
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x;                                   // one CTA per point: the template of a large window
+    const int stride = (max_win_px + 7) & ~7;                   // (6 B per pixel) is shared by 128 threads
+    short2 *dIw = reinterpret_cast<short2 *>(smem_raw);
+    short *Iw = reinterpret_cast<short *>(dIw + stride);
 
     const TrackJob &job = P.jobs[find_job(P.jobs, P.n_jobs, i)];
     const int k = i - job.pt_begin;
@@ -265,9 +282,9 @@ lk_generic_kernel(const __grid_constant__ LkParams P, int max_win_px)
 
     Solve f, b;
     b.x = b.y = b.err = 0.f; b.st = 1;
-    solve_generic(P, g.plane_from, g.plane_to, g.win_w, g.win_h, g.max_level, p0.x, p0.y, Iw, dIw, lane, f);
-    if (P.do_fb) solve_generic(P, g.plane_to, g.plane_from, g.win_w, g.win_h, g.max_level, f.x, f.y, Iw, dIw, lane, b);
-    finish_point(P, job, k, p0, f, b, lane);
+    solve_generic(P, g.plane_from, g.plane_to, g.win_w, g.win_h, g.max_level, p0.x, p0.y, Iw, dIw, tid, red, f);
+    if (P.do_fb) solve_generic(P, g.plane_to, g.plane_from, g.win_w, g.win_h, g.max_level, f.x, f.y, Iw, dIw, tid, red, b);
+    finish_point(P, job, k, p0, f, b, tid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -635,17 +652,14 @@ int launch_lk(const LkParams &P, int all_21x21, int max_win_px, cudaStream_t str
         lk_w21_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(P);
     } else {
         const int stride = (max_win_px + 7) & ~7;
-        int warps = 4;
-        size_t smem = (size_t)warps * stride * 6;
-        while (warps > 1 && smem > 200 * 1024) { warps >>= 1; smem = (size_t)warps * stride * 6; }
+        const size_t smem = (size_t)stride * 6;
         if (smem > 200 * 1024) return -2;
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
+        static bool configured = false;
+        if (smem > 48 * 1024 && !configured) {
             if (cudaFuncSetAttribute(lk_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
-            configured = 200 * 1024;
+            configured = true;
         }
-        const int grid = (P.n_pts + warps - 1) / warps;
-        lk_generic_kernel<<<grid, warps * 32, smem, stream>>>(P, max_win_px);
+        lk_generic_kernel<<<P.n_pts, kGenThreads, smem, stream>>>(P, max_win_px);
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
