@@ -145,6 +145,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
     int st = 1;
     int lx0 = tid, ly0 = 0;                    // window coordinates of this thread's first pixel
     int rsel = 0;                              // reduction scratch toggles between two slots
+    const bool acc32 = npx <= 60 * kGenThreads;   // 60 * 8160 * 4080 < 2^31: per-thread partial sums fit 32 bits
     while (lx0 >= ww) { lx0 -= ww; ly0++; }
 
     for (int level = max_level; level >= 0; --level) {
@@ -207,12 +208,26 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             long long sb1 = 0, sb2 = 0;
             int x = lx0, y = ly0;
-            for (int p = tid; p < npx; p += kGenThreads) {
-                const int diff = sample_u8(JB, L.pitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
-                const short2 d = dIw[p];
-                sb1 += (long long)(diff * d.x); sb2 += (long long)(diff * d.y);
-                x += kGenThreads;
-                while (x >= ww) { x -= ww; y++; }
+            if (acc32 && inx >= 0 && iny >= 0 && inx + ww < L.w && iny + wh < L.h) {
+                // window inside the frame and <= 60 pixels per thread: no border arithmetic, 32-bit partial sums
+                int a1 = 0, a2 = 0;
+                for (int p = tid; p < npx; p += kGenThreads) {
+                    const uint8_t *r0 = JB + (iny + y) * L.pitch + (inx + x), *r1 = r0 + L.pitch;
+                    const int diff = ((r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9) - Iw[p];
+                    const short2 d = dIw[p];
+                    a1 += diff * d.x; a2 += diff * d.y;
+                    x += kGenThreads;
+                    while (x >= ww) { x -= ww; y++; }
+                }
+                sb1 = a1; sb2 = a2;
+            } else {
+                for (int p = tid; p < npx; p += kGenThreads) {
+                    const int diff = sample_u8(JB, L.pitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
+                    const short2 d = dIw[p];
+                    sb1 += (long long)(diff * d.x); sb2 += (long long)(diff * d.y);
+                    x += kGenThreads;
+                    while (x >= ww) { x -= ww; y++; }
+                }
             }
             { long long z = 0; block_sum3(sb1, sb2, z, red, rsel, tid); }
             if (lk_step(P, sb1, sb2, A11, A12, A22, Dinv, half_x, half_y, j, nx, ny, pdx, pdy, next_x, next_y)) break;
