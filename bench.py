@@ -402,6 +402,36 @@ def cpu_measure(wl, steps, warmup, budget_s=20.0):
             "frames_per_s": n / dt, "ms_per_camera_frame": 1e3 * dt / max(n, 1), "camera_frames": n}
 
 
+def pyramid_sweep(rig, peak):
+    """Same K1 launch group with more camera-frames per launch (BASELINE config 5: frames in flight): the kernel is
+    latency-bound at 4 small frames and approaches the HBM roofline as the batch grows."""
+    import torch
+    from mcmtt_opticalflow_b200 import klt
+    out = []
+    for (w, h, levels, frames) in [(768, 576, 4, 16), (768, 576, 4, 64), (1920, 1080, 4, 32), (3840, 2160, 5, 16)]:
+        ctx = klt.KLTContext(w, h, n_cameras=frames, levels=levels, ring_slots=1, stream=rig.stream.cuda_stream, max_points=1024, max_targets=64)
+        rng = np.random.default_rng(0)
+        base = [rng.integers(0, 256, size=(h, w), dtype=np.uint8) for _ in range(2)]
+        ctx.push_frames([base[i % 2] for i in range(frames)])
+        cams = np.arange(frames, dtype=np.int32)
+        with torch.cuda.stream(rig.stream):
+            for _ in range(3):
+                ctx.rebuild_pyramids(cams)
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+            for a, b in ev:
+                rig.flush.zero_()
+                a.record(rig.stream)
+                ctx.rebuild_pyramids(cams)
+                b.record(rig.stream)
+            rig.stream.synchronize()
+        ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+        alg = ctx.push_frame_bytes * frames
+        out.append({"frame": "%dx%d" % (w, h), "levels": levels, "frames_per_launch": frames, "algorithmic_bytes": alg,
+                    "ms": ms, "achieved": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak})
+        ctx.close()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -491,9 +521,16 @@ def main():
         pyr_mean, pyr_best = rig.time_pyramid()
         alg = rig.ctx.push_frame_bytes * ncam
         ach = alg / pyr_mean / 1e9
-        roofline = {"kernel": "pyr_scharr_kernel (%d launches = one per level, %d frames batched in grid.z)" % (levels, ncam),
-                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None
+        if args.workload == "c2":
+            try:      # DRAM bytes of the same launch group from the committed ncu --set full capture
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_pyr_traffic.json")))["traffic_bytes_per_group"]
+            except Exception:
+                pass
+        roofline = {"kernel": "pyr_scharr_kernel (%d PDL-chained launches = one per level, %d frames batched in grid.z)" % (levels, ncam),
+                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "algorithmic_bytes": alg, "ms": 1e3 * pyr_mean, "best_ms": 1e3 * pyr_best, "peak_source": peak_src}
+        roofline["frames_in_flight_sweep"] = pyramid_sweep(rig, peak) if args.workload == "c2" else None
         lk_sec, st_frac = rig.time_track()
         lk = {"kernel": "lk_w21_kernel (fwd+bwd fused)", "ms": 1e3 * lk_sec, "lk_solves_per_s": 2 * rig.npts / lk_sec,
               "status_ok_frac": st_frac, "bound": "SM issue / shared memory (not HBM, not tensor) -- see DESIGN.md"}
