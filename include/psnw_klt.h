@@ -137,6 +137,20 @@ PSNW_API int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, i
                                    float quality, float min_dist, int mem_flags);
 
 /*
+ * GridFAST detection ("next" row): the detector the reference actually creates at
+ * Tracker2D.cpp:142 -- OpenCV 2.4 GridAdaptedFeatureDetector(FastFeatureDetector(threshold, NMS), max_total, grid_rows x
+ * grid_cols), reference values (10, 1000, 4, 4) -- applied under the detection-box mask of :735-742.  Each cell keeps
+ * its max_total/(rows*cols) strongest keypoints including ties; if more than max_per_target survive, the strongest are
+ * kept (ties in raster order; the reference draws a random subset with std::random_shuffle, :752-757).  Output in
+ * raster order, unused slots (-1e6,-1e6).  `boxes` is host memory.
+ */
+PSNW_API int psnw_gridfast_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n_targets,
+                                  int max_per_target, int threshold, int grid_rows, int grid_cols, int max_total,
+                                  float *pts_xy, int *counts, int mem_flags);
+/* Copies the NMS'd FAST score map last computed for `cam` to host u8[h][w] (inspection). */
+PSNW_API int psnw_read_fast_map(psnw_ctx *ctx, int cam, uint8_t *map_out);
+
+/*
  * Sparse pyramidal LK from ring slot `slot_from` to `slot_to` of camera `cam` (replaces
  * cv::calcOpticalFlowPyrLK at .cpp:776-782 [slot_from = newer frame] and :871-877 [slot_from = 1, slot_to = 0]).
  *   pts_xy[n_pts][2]      seed points in slot_from

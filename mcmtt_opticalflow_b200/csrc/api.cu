@@ -51,6 +51,9 @@ struct psnw_ctx {
     DevBuf bgr;                           // BGR staging for psnw_push_frames_bgr
     std::vector<float *> eig;             // per camera min-eig map (level-0 pitch), lazily allocated
     std::vector<uint64_t> eig_tag;
+    std::vector<uint8_t *> fmap;          // per camera NMS'd FAST score map (GridFAST), lazily allocated
+    std::vector<uint64_t> fmap_tag;
+    int fmap_cfg[3] = {-1, -1, -1};       // (threshold, grid_rows, grid_cols) the cached maps were built with
     StageSlot stage[kStageSlots];
     int stage_next = 0;
     uint64_t launches = 0;
@@ -269,6 +272,8 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     ctx->plane_seq.assign(ctx->planes, 0);
     ctx->eig.assign(p->n_cameras, nullptr);
     ctx->eig_tag.assign(p->n_cameras, 0);
+    ctx->fmap.assign(p->n_cameras, nullptr);
+    ctx->fmap_tag.assign(p->n_cameras, 0);
     memset(&ctx->pyr, 0, sizeof ctx->pyr);
 
     auto bail = [&](int code) { psnw_destroy(ctx); return code; };
@@ -331,6 +336,7 @@ int psnw_destroy(psnw_ctx *ctx)
         if (ctx->pyr.lv[l].dxy) cudaFree(ctx->pyr.lv[l].dxy);
     }
     for (float *e : ctx->eig) if (e) cudaFree(e);
+    for (uint8_t *e : ctx->fmap) if (e) cudaFree(e);
     if (ctx->arena.p) cudaFree(ctx->arena.p);
     if (ctx->desc.p) cudaFree(ctx->desc.p);
     if (ctx->cand.p) cudaFree(ctx->cand.p);
@@ -733,6 +739,85 @@ int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n
     psnw_detect_job j;
     j.cam = cam; j.slot = slot; j.boxes = boxes; j.n_targets = n_targets; j.pts_xy = pts_xy; j.counts = counts;
     return psnw_klt_detect_batch(ctx, &j, 1, max_per_target, quality, min_dist, mem_flags);
+}
+
+// GridFAST detect ("next" row f-1): the reference's own detector, Tracker2D.cpp:142 / :735-757
+int psnw_gridfast_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n_targets, int max_per_target,
+                         int threshold, int grid_rows, int grid_cols, int max_total, float *pts_xy, int *counts, int mem_flags)
+{
+    if (!ctx) return PSNW_EARG;
+    if (n_targets == 0) return PSNW_OK;
+    if (n_targets < 0 || max_per_target < 1 || !boxes || !pts_xy || !counts || grid_rows < 1 || grid_cols < 1 ||
+        grid_rows * grid_cols > 64 || max_total < 0)
+        return fail(ctx, PSNW_EARG, "psnw_gridfast_detect arguments");
+    if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_gridfast_detect: camera/slot holds no frame");
+    if (n_targets > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_gridfast_detect: max_targets exceeded");
+    int rc = join_aux(ctx);
+    if (rc) return rc;
+    threshold = std::min(std::max(threshold, 0), 255);
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    const int plane = plane_of(ctx, cam, slot);
+    if (!ctx->fmap[cam]) {
+        if (cudaMalloc(&ctx->fmap[cam], (size_t)l0.plane_px) != cudaSuccess) return fail(ctx, PSNW_ENOMEM, "cudaMalloc FAST map", cudaGetLastError());
+        ctx->fmap_tag[cam] = 0;
+    }
+    if (ctx->fmap_cfg[0] != threshold || ctx->fmap_cfg[1] != grid_rows || ctx->fmap_cfg[2] != grid_cols) {
+        std::fill(ctx->fmap_tag.begin(), ctx->fmap_tag.end(), 0);
+        ctx->fmap_cfg[0] = threshold; ctx->fmap_cfg[1] = grid_rows; ctx->fmap_cfg[2] = grid_cols;
+    }
+    if (ctx->fmap_tag[cam] != ctx->plane_seq[plane]) {
+        const int r = launch_fast_map(l0, plane, threshold, grid_rows, grid_cols, ctx->fmap[cam], ctx->stream);
+        if (r < 0) return fail(ctx, PSNW_ECUDA, "fast_map_kernel launch", cudaGetLastError());
+        ctx->launches += r;
+        ctx->fmap_tag[cam] = ctx->plane_seq[plane];
+    }
+    const bool dev = mem_flags == PSNW_MEM_DEVICE;
+    const size_t tb = (sizeof(GridFastTarget) * n_targets + 255) & ~(size_t)255;
+    const size_t out_b = dev ? 0 : (((size_t)n_targets * max_per_target * sizeof(float2) + 255) & ~(size_t)255);
+    const size_t cnt_b = dev ? 0 : ((sizeof(int) * n_targets + 255) & ~(size_t)255);
+    rc = ensure(ctx, ctx->det_desc, tb + out_b + cnt_b);
+    if (rc) return rc;
+    float2 *s_out = reinterpret_cast<float2 *>(ctx->det_desc.p + tb);
+    int *s_cnt = reinterpret_cast<int *>(ctx->det_desc.p + tb + out_b);
+    std::vector<GridFastTarget> T(n_targets);
+    for (int t = 0; t < n_targets; ++t) {                         // mask ROI = box.cropWithSize(cols, rows).cv(), :735
+        const double x = boxes[4 * t], y = boxes[4 * t + 1], w = boxes[4 * t + 2], h = boxes[4 * t + 3];
+        const double nx = std::max(0.0, x), ny = std::max(0.0, y);
+        const double nw = std::min((double)l0.w - nx - 1, w), nh = std::min((double)l0.h - ny - 1, h);
+        GridFastTarget &d = T[t];
+        d.x0 = std::min((int)nx, l0.w); d.y0 = std::min((int)ny, l0.h);
+        d.x1 = std::min(std::max((int)nx + std::max((int)nw, 0), d.x0), l0.w);
+        d.y1 = std::min(std::max((int)ny + std::max((int)nh, 0), d.y0), l0.h);
+        d.map = ctx->fmap[cam];
+        d.out = dev ? reinterpret_cast<float2 *>(pts_xy) + (size_t)t * max_per_target : s_out + (size_t)t * max_per_target;
+        d.count = dev ? counts + t : s_cnt + t;
+    }
+    StageSlot *s;
+    rc = stage_acquire(ctx, tb, &s);
+    if (rc) return rc;
+    memcpy(s->h, T.data(), sizeof(GridFastTarget) * n_targets);
+    rc = stage_upload(ctx, s, ctx->det_desc.p, sizeof(GridFastTarget) * n_targets);
+    if (rc) return rc;
+    const int r = launch_gridfast_select(l0.w, l0.h, l0.pitch, reinterpret_cast<const GridFastTarget *>(ctx->det_desc.p), n_targets,
+                                         max_per_target, grid_rows, grid_cols, max_total / (grid_rows * grid_cols), ctx->stream);
+    if (r < 0) return fail(ctx, PSNW_ECUDA, "gridfast_select_kernel launch", cudaGetLastError());
+    ctx->launches += r;
+    if (!dev) {
+        CK(cudaMemcpyAsync(pts_xy, s_out, (size_t)n_targets * max_per_target * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(counts, s_cnt, sizeof(int) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+        if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return PSNW_OK;
+}
+
+int psnw_read_fast_map(psnw_ctx *ctx, int cam, uint8_t *map_out)
+{
+    if (!ctx || !map_out || cam < 0 || cam >= ctx->p.n_cameras) return PSNW_EARG;
+    if (!ctx->fmap[cam] || !ctx->fmap_tag[cam]) return fail(ctx, PSNW_ESTATE, "psnw_read_fast_map: no map computed yet");
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy2D(map_out, l0.w, ctx->fmap[cam], l0.pitch, l0.w, l0.h, cudaMemcpyDeviceToHost));
+    return PSNW_OK;
 }
 
 int psnw_join(psnw_ctx *ctx)

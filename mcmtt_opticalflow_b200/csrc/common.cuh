@@ -87,6 +87,16 @@ int launch_detect_select(int w, int h, int pitch, const DetectTarget *targets, i
                          int max_per_target, float quality, float min_dist, unsigned long long *cand,
                          int max_roi_area, int max_tile_px, cudaStream_t stream);
 
+struct GridFastTarget {
+    int x0, y0, x1, y1;        // cropped ROI, half open
+    const uint8_t *map;        // NMS'd FAST score map of the target's camera (level-0 pitch)
+    float2 *out;               // [max_per_target]
+    int *count;
+};
+int launch_fast_map(const LevelGeom &l0, int plane, int threshold, int grid_rows, int grid_cols, uint8_t *out, cudaStream_t stream);
+int launch_gridfast_select(int w, int h, int pitch, const GridFastTarget *targets, int n_targets, int max_per_target,
+                           int grid_rows, int grid_cols, int per_cell, cudaStream_t stream);
+
 // tile geometry of the pyramid kernel (the TMA box must match on host and device)
 constexpr int kTileW = 128, kTileH = 32;
 // The innermost TMA start coordinate must be 16-byte aligned (u8 elements: a multiple of 16 pixels; a start at

@@ -52,7 +52,7 @@ class DetectJob(C.Structure):
 
 
 EXPORTS = [
-    "psnw_klt_detect_batch", "psnw_join", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
+    "psnw_klt_detect_batch", "psnw_join", "psnw_gridfast_detect", "psnw_read_fast_map", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
     "psnw_push_frames_bgr", "psnw_frames_held", "psnw_klt_detect", "psnw_klt_track", "psnw_klt_track_batch",
     "psnw_box_update", "psnw_sync", "psnw_last_error", "psnw_get_stream", "psnw_level_info", "psnw_read_level",
     "psnw_read_min_eig", "psnw_launch_count", "psnw_push_frame_bytes", "psnw_rebuild_pyramids", "psnw_levels_built",
@@ -91,6 +91,9 @@ def load():
         lib.psnw_klt_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                         C.c_float, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_klt_detect_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
+        lib.psnw_gridfast_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        lib.psnw_read_fast_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.psnw_klt_track.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_klt_track_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -244,6 +247,21 @@ class KLTContext:
         self._ck(self.lib.psnw_klt_detect(self._h, cam, slot, boxes.ctypes.data, n, max_per_target, quality, min_dist,
                                           pts.ctypes.data, counts.ctypes.data, MEM_HOST))
         return pts, counts
+
+    def gridfast_detect(self, boxes, max_per_target=100, threshold=10, grid=(4, 4), max_total=1000, cam=0, slot=0):
+        """GridFAST keypoints (the reference's detector) -> (pts float32 [n_targets, max_per_target, 2], counts)."""
+        boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
+        n = boxes.shape[0]
+        pts = np.zeros((n, max_per_target, 2), np.float32)
+        counts = np.zeros(n, np.int32)
+        self._ck(self.lib.psnw_gridfast_detect(self._h, cam, slot, boxes.ctypes.data, n, max_per_target, threshold, grid[0], grid[1],
+                                               max_total, pts.ctypes.data, counts.ctypes.data, MEM_HOST))
+        return pts, counts
+
+    def read_fast_map(self, cam=0):
+        out = np.empty((self.height, self.width), np.uint8)
+        self._ck(self.lib.psnw_read_fast_map(self._h, cam, out.ctypes.data))
+        return out
 
     def track(self, pts, cam=0, slot_from=1, slot_to=0, target_of_pt=None, win_wh=None):
         """-> (out [n,2] f32, status [n] u8, err [n] f32, fb_err [n] f32 or None)."""

@@ -54,3 +54,27 @@ def box_iou(a, b):
         return 0.0
     inter = ow * oh
     return inter / (a[2] * a[3] + b[2] * b[3] - inter)
+
+
+def gridfast(img, box, threshold=10, grid=(4, 4), max_total=1000):
+    """OpenCV 2.4.x GridAdaptedFeatureDetector(FAST(threshold, nms), max_total, grid) under the reference's box mask,
+    rebuilt from cv2 4.13's FastFeatureDetector run on every cell's sub-image (the class itself left OpenCV in 3.0).
+    -> (points float32 [k,2] in raster order, responses) of the keypoints that survive keepStrongest per cell."""
+    h, w = img.shape
+    x0, y0, x1, y1 = po.crop_roi(box, w, h)
+    fast = cv2.FastFeatureDetector_create(threshold=threshold, nonmaxSuppression=True)
+    per_cell = max_total // (grid[0] * grid[1])
+    pts = []
+    for i in range(grid[0]):
+        r0, r1 = (i * h) // grid[0], ((i + 1) * h) // grid[0]
+        for j in range(grid[1]):
+            c0, c1 = (j * w) // grid[1], ((j + 1) * w) // grid[1]
+            kps = fast.detect(np.ascontiguousarray(img[r0:r1, c0:c1]), None)
+            cell = [(int(k.pt[0]) + c0, int(k.pt[1]) + r0, k.response) for k in kps]
+            cell = [p for p in cell if x0 <= p[0] < x1 and y0 <= p[1] < y1]            # runByPixelsMask
+            if len(cell) > per_cell:                                                   # retainBest keeps boundary ties
+                thr = sorted((p[2] for p in cell), reverse=True)[per_cell - 1]
+                cell = [p for p in cell if p[2] >= thr]
+            pts += cell
+    pts.sort(key=lambda p: (p[1], p[0]))
+    return (np.array([[p[0], p[1]] for p in pts], np.float32).reshape(-1, 2), np.array([p[2] for p in pts], np.float32))

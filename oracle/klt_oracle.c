@@ -465,3 +465,139 @@ PSNWO_API int psnwo_gftt_select(const float *eig, int w, int h, int estride_px,
     free(cands);
     return n_out;
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* A.6  GridFAST -- the reference's actual detector (next row f-1):                                  */
+/*      cv::FeatureDetector::create("GridFAST"), psn_where/PSNWhere_Tracker2D.cpp:142, used at :741  */
+/*      = GridAdaptedFeatureDetector(FastFeatureDetector(threshold 10, NMS), 1000 keypoints, 4 x 4). */
+/*      OpenCV 2.4.6 is not vendored; FAST-9/16 is restated from features2d/fast.cpp + fast_score.cpp */
+/*      and pinned against cv2 4.13's FastFeatureDetector run per grid cell (tests/test_gridfast.py). */
+/* ------------------------------------------------------------------------------------------------ */
+static const int fast_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+static const int fast_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+/* score of pixel (x, y): 0 when it is not a FAST-9/16 corner at `threshold`, else cornerScore<16> (>= threshold) */
+static int fast_score_at(const uint8_t *img, int stride, int x, int y, int threshold)
+{
+    const int v = img[(size_t)y * stride + x];
+    int d[25];
+    for (int k = 0; k < 25; k++) d[k] = v - img[(size_t)(y + fast_dy[k & 15]) * stride + (x + fast_dx[k & 15])];
+    /* corner test: 9 contiguous circle pixels all darker than v - t or all brighter than v + t */
+    int is_corner = 0, run_d = 0, run_b = 0;
+    for (int k = 0; k < 25 && !is_corner; k++) {
+        run_d = d[k] > threshold ? run_d + 1 : 0;
+        run_b = d[k] < -threshold ? run_b + 1 : 0;
+        if (run_d >= 9 || run_b >= 9) is_corner = 1;
+    }
+    if (!is_corner) return 0;
+    int a0 = threshold;
+    for (int k = 0; k < 16; k += 2) {
+        int a = d[k + 1] < d[k + 2] ? d[k + 1] : d[k + 2];
+        if (d[k + 3] < a) a = d[k + 3];
+        if (a <= a0) continue;
+        for (int q = 4; q <= 8; q++) if (d[k + q] < a) a = d[k + q];
+        int m = a < d[k] ? a : d[k];
+        if (m > a0) a0 = m;
+        m = a < d[k + 9] ? a : d[k + 9];
+        if (m > a0) a0 = m;
+    }
+    int b0 = -a0;
+    for (int k = 0; k < 16; k += 2) {
+        int b = d[k + 1] > d[k + 2] ? d[k + 1] : d[k + 2];
+        if (d[k + 3] > b) b = d[k + 3];
+        if (b >= b0) continue;
+        for (int q = 4; q <= 8; q++) if (d[k + q] > b) b = d[k + q];
+        int m = b > d[k] ? b : d[k];
+        if (m < b0) b0 = m;
+        m = b > d[k + 9] ? b : d[k + 9];
+        if (m < b0) b0 = m;
+    }
+    return -b0 - 1;
+}
+
+/*
+ * Dense map of non-max-suppressed FAST scores with the grid-cell semantics of GridAdaptedFeatureDetector: every
+ * cell is detected as its own sub-image, so pixels within 3 px of a cell edge are never corners and NMS never
+ * looks across a cell edge.  out[y][x] = score (1..255) for a kept keypoint, 0 otherwise.
+ */
+PSNWO_API void psnwo_gridfast_map(const uint8_t *img, int w, int h, int stride, int threshold, int grid_rows, int grid_cols,
+                                  uint8_t *out, int ostride)
+{
+    int *raw = (int *)calloc((size_t)w * h, sizeof(int));
+    for (int i = 0; i < grid_rows; i++) {
+        const int r0 = (i * h) / grid_rows, r1 = ((i + 1) * h) / grid_rows;
+        for (int j = 0; j < grid_cols; j++) {
+            const int c0 = (j * w) / grid_cols, c1 = ((j + 1) * w) / grid_cols;
+            for (int y = r0 + 3; y < r1 - 3; y++)
+                for (int x = c0 + 3; x < c1 - 3; x++) raw[(size_t)y * w + x] = fast_score_at(img, stride, x, y, threshold);
+        }
+    }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const int s = raw[(size_t)y * w + x];
+            int keep = s > 0;
+            for (int dy = -1; dy <= 1 && keep; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (!dx && !dy) continue;
+                    const int yy = y + dy, xx = x + dx;
+                    const int u = (yy < 0 || xx < 0 || yy >= h || xx >= w) ? 0 : raw[(size_t)yy * w + xx];
+                    if (!(s > u)) { keep = 0; break; }
+                }
+            out[(size_t)y * ostride + x] = (uint8_t)(keep ? (s > 255 ? 255 : s) : 0);
+        }
+    free(raw);
+}
+
+/*
+ * Keypoints of one detection box from the NMS'd score map: per grid cell keep the keypoints inside the ROI mask,
+ * then keepStrongest(max_total / cells) INCLUDING every tie of the boundary response (KeyPointsFilter::retainBest).
+ * If more than max_out survive over all cells, the strongest max_out are returned (ties cut in raster order) -- the
+ * reference instead draws a random subset (std::random_shuffle, :752-757).  Output in raster order.
+ */
+PSNWO_API int psnwo_gridfast_select(const uint8_t *map, int w, int h, int mstride, int grid_rows, int grid_cols, int max_total,
+                                    int x0, int y0, int x1, int y1, int max_out, float *out_xy)
+{
+    if (x0 < 0) x0 = 0; if (y0 < 0) y0 = 0; if (x1 > w) x1 = w; if (y1 > h) y1 = h;
+    if (x1 <= x0 || y1 <= y0 || max_out <= 0) return 0;
+    const int per_cell = max_total / (grid_rows * grid_cols);
+    uint8_t *keep = (uint8_t *)calloc((size_t)w * h, 1);
+    int hist_all[256] = {0}, total = 0;
+    for (int i = 0; i < grid_rows; i++) {
+        const int r0 = (i * h) / grid_rows, r1 = ((i + 1) * h) / grid_rows;
+        for (int j = 0; j < grid_cols; j++) {
+            const int c0 = (j * w) / grid_cols, c1 = ((j + 1) * w) / grid_cols;
+            const int ya = r0 > y0 ? r0 : y0, yb = r1 < y1 ? r1 : y1, xa = c0 > x0 ? c0 : x0, xb = c1 < x1 ? c1 : x1;
+            if (ya >= yb || xa >= xb) continue;
+            int hist[256] = {0}, n = 0;
+            for (int y = ya; y < yb; y++)
+                for (int x = xa; x < xb; x++) { const int s = map[(size_t)y * mstride + x]; if (s) { hist[s]++; n++; } }
+            int thr = 1;
+            if (n > per_cell) {                      /* boundary response = the per_cell-th strongest; keep >= it */
+                int acc = 0;
+                for (thr = 255; thr >= 1; thr--) { acc += hist[thr]; if (acc >= per_cell) break; }
+                if (per_cell <= 0) thr = 256;
+            }
+            for (int y = ya; y < yb; y++)
+                for (int x = xa; x < xb; x++) {
+                    const int s = map[(size_t)y * mstride + x];
+                    if (s && s >= thr) { keep[(size_t)y * w + x] = (uint8_t)s; hist_all[s]++; total++; }
+                }
+        }
+    }
+    int thr = 1, room_at_thr = 1 << 30;
+    if (total > max_out) {
+        int acc = 0;
+        for (thr = 255; thr >= 1; thr--) { if (acc + hist_all[thr] >= max_out) break; acc += hist_all[thr]; }
+        room_at_thr = max_out - acc;                 /* how many keypoints of response == thr still fit */
+    }
+    int n_out = 0;
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) {
+            const int s = keep[(size_t)y * w + x];
+            if (!s || s < thr) continue;
+            if (s == thr) { if (room_at_thr <= 0) continue; room_at_thr--; }
+            out_xy[2 * n_out] = (float)x; out_xy[2 * n_out + 1] = (float)y; n_out++;
+        }
+    free(keep);
+    return n_out;
+}

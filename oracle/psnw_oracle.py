@@ -164,3 +164,26 @@ def detect(img, box, max_corners=100, quality=0.01, min_dist=3.0, eig=None):
     k = lib().psnwo_gftt_select(_p(eig), w, h, eig.shape[1], x0, y0, x1, y1, C.c_int(max_corners),
                                 C.c_float(quality), C.c_float(min_dist), _p(out))
     return out[:k].copy()
+
+
+def gridfast_map(img, threshold=10, grid=(4, 4)):
+    """NMS'd FAST-9/16 score map with GridAdaptedFeatureDetector cell semantics -> u8 [h, w]."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().psnwo_gridfast_map(_p(img), w, h, img.strides[0], int(threshold), int(grid[0]), int(grid[1]), _p(out), w)
+    return out
+
+
+def gridfast_detect(img, box, max_out=100, threshold=10, grid=(4, 4), max_total=1000, fmap=None):
+    """GridFAST keypoints inside one detection box (Tracker2D.cpp:735-757 without the random shuffle) -> f32 [k,2]."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    if fmap is None:
+        fmap = gridfast_map(img, threshold, grid)
+    x0, y0, x1, y1 = crop_roi(box, w, h)
+    out = np.zeros((max(max_out, 1), 2), np.float32)
+    lib().psnwo_gridfast_select.restype = C.c_int
+    k = lib().psnwo_gridfast_select(_p(fmap), w, h, fmap.shape[1], int(grid[0]), int(grid[1]), int(max_total),
+                                    x0, y0, x1, y1, int(max_out), _p(out))
+    return out[:k].copy()
