@@ -200,6 +200,16 @@ PSNW_API int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_target
                              const int *target_offsets, int mode,
                              double *boxes_out, uint8_t *inlier_mask, int *inlier_counts, int mem_flags);
 
+/*
+ * "Next" row: counts[d][t] = number of tracker t's tracked points inside detection box d
+ * (PSN_Rect::contain) -- the per-pair counts behind the reference's optical-flow majority check
+ * (Tracker2D.cpp:939-944, :981-1022) -- computed next to the LK output so the points need not leave the device.
+ * pts_xy: all trackers' tracked points, CSR by tracker_offsets[n_trackers + 1]; det_boxes[n_detections][4];
+ * counts[n_detections][n_trackers] (the layout of matchingCostArray, :859).
+ */
+PSNW_API int psnw_points_in_boxes(psnw_ctx *ctx, const float *pts_xy, const int *tracker_offsets, int n_trackers,
+                                  const double *det_boxes, int n_detections, int *counts, int mem_flags);
+
 PSNW_API int psnw_sync(psnw_ctx *ctx);
 /* Device-side join of an overlapped detect into the context stream (see PSNW_MEM_OVERLAP). */
 PSNW_API int psnw_join(psnw_ctx *ctx);

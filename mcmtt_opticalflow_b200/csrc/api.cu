@@ -741,6 +741,43 @@ int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n
     return psnw_klt_detect_batch(ctx, &j, 1, max_per_target, quality, min_dist, mem_flags);
 }
 
+// "next" row f-3: per (detection, tracker) count of tracked points inside the detection box (Tracker2D.cpp:939-944)
+int psnw_points_in_boxes(psnw_ctx *ctx, const float *pts_xy, const int *tracker_offsets, int n_trackers,
+                         const double *det_boxes, int n_detections, int *counts, int mem_flags)
+{
+    if (!ctx) return PSNW_EARG;
+    if (n_trackers == 0 || n_detections == 0) return PSNW_OK;
+    if (n_trackers < 0 || n_detections < 0 || !tracker_offsets || !det_boxes || !counts)
+        return fail(ctx, PSNW_EARG, "psnw_points_in_boxes arguments");
+    if (n_trackers > ctx->p.max_targets || n_detections > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_points_in_boxes: max_targets exceeded");
+    int r;
+    if (mem_flags == PSNW_MEM_DEVICE) {
+        r = launch_points_in_boxes(reinterpret_cast<const float2 *>(pts_xy), tracker_offsets, n_trackers, det_boxes, n_detections, counts, ctx->stream);
+        if (r < 0) return fail(ctx, PSNW_ECUDA, "points_in_boxes_kernel launch", cudaGetLastError());
+        ctx->launches += r;
+        return PSNW_OK;
+    }
+    const int n_pts = tracker_offsets[n_trackers];
+    if (n_pts < 0 || n_pts > ctx->p.max_points) return fail(ctx, PSNW_ENOMEM, "psnw_points_in_boxes: max_points exceeded");
+    if (n_pts > 0 && !pts_xy) return fail(ctx, PSNW_EARG, "psnw_points_in_boxes: null points");
+    const size_t ncnt = (size_t)n_trackers * n_detections;
+    int rc = ensure(ctx, ctx->arena, (size_t)n_pts * 8 + (size_t)(n_trackers + 1) * 4 + (size_t)n_detections * 32 + ncnt * 4 + 4096);
+    if (rc) return rc;
+    ctx->arena_off = 0;
+    float2 *d_pts = take<float2>(ctx, n_pts);
+    int *d_off = take<int>(ctx, n_trackers + 1), *d_cnt = take<int>(ctx, ncnt);
+    double *d_box = take<double>(ctx, (size_t)n_detections * 4);
+    if (n_pts > 0) CK(cudaMemcpyAsync(d_pts, pts_xy, sizeof(float2) * n_pts, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_off, tracker_offsets, sizeof(int) * (n_trackers + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_box, det_boxes, sizeof(double) * 4 * n_detections, cudaMemcpyHostToDevice, ctx->stream));
+    r = launch_points_in_boxes(d_pts, d_off, n_trackers, d_box, n_detections, d_cnt, ctx->stream);
+    if (r < 0) return fail(ctx, PSNW_ECUDA, "points_in_boxes_kernel launch", cudaGetLastError());
+    ctx->launches += r;
+    CK(cudaMemcpyAsync(counts, d_cnt, sizeof(int) * ncnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return PSNW_OK;
+}
+
 // GridFAST detect ("next" row f-1): the reference's own detector, Tracker2D.cpp:142 / :735-757
 int psnw_gridfast_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n_targets, int max_per_target,
                          int threshold, int grid_rows, int grid_cols, int max_total, float *pts_xy, int *counts, int mem_flags)

@@ -115,7 +115,41 @@ box_update_kernel(const double *__restrict__ boxes_in, const float2 *__restrict_
     }
 }
 
+// "next" row f-3: tracked points of every tracker inside every detection box -- the counts the reference accumulates in
+// featuresInDetectionBox (Tracker2D.cpp:939-944) for its optical-flow majority check (:981-1022), here a by-product on the
+// device so that the tracked points need not travel to the host.  PSN_Rect::contain (PSNWhere_Types.h:157) in double.
+__global__ void __launch_bounds__(128)
+points_in_boxes_kernel(const float2 *__restrict__ pts, const int *__restrict__ offsets, const double *__restrict__ det_boxes,
+                       int n_det, int n_trk, int *__restrict__ counts)
+{
+    __shared__ int s_cnt;
+    const int t = blockIdx.x, d = blockIdx.y, tid = threadIdx.x;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const double bx = det_boxes[4 * d], by = det_boxes[4 * d + 1], bw = det_boxes[4 * d + 2], bh = det_boxes[4 * d + 3];
+    const double x1 = __dadd_rn(bx, bw), y1 = __dadd_rn(by, bh);
+    int c = 0;
+    for (int i = offsets[t] + tid; i < offsets[t + 1]; i += 128) {
+        const float2 p = pts[i];
+        const double x = (double)p.x, y = (double)p.y;
+        c += (x >= bx && x < x1 && y >= by && y < y1) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (tid == 0) counts[(size_t)d * n_trk + t] = s_cnt;
+}
+
 }  // namespace
+
+int launch_points_in_boxes(const float2 *pts, const int *offsets, int n_trk, const double *det_boxes, int n_det, int *counts,
+                           cudaStream_t stream)
+{
+    if (n_trk <= 0 || n_det <= 0) return 0;
+    points_in_boxes_kernel<<<dim3(n_trk, n_det), 128, 0, stream>>>(pts, offsets, det_boxes, n_det, n_trk, counts);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
 
 int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
                       const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,

@@ -74,6 +74,8 @@ struct EigList {
     int plane[24];
     float *eig[24];
 };
+int launch_points_in_boxes(const float2 *pts, const int *offsets, int n_trk, const double *det_boxes, int n_det, int *counts,
+                           cudaStream_t stream);
 int launch_min_eig(const LevelGeom &l0, const EigList &list, cudaStream_t stream);
 
 struct DetectTarget {

@@ -116,4 +116,9 @@ private:
 // psn_where/helpers/PSNWhere_Hungarian.cpp:212-359): returns matched (row, col) pairs, min(rows, cols) of them.
 void HungarianMatch(const std::vector<float> &cost, int rows, int cols, std::vector<int> &matchRows, std::vector<int> &matchCols);
 
+// on-disk formats (psnw_formats.cpp)
+std::vector<stDetection> ReadDetectionResultWithTxt(const std::string &path);
+bool FilePrintResult(const std::string &path, const stTrack2DResult &result);
+bool Read2DTrackResultWithTxt(const std::string &path, stTrack2DResult &result);
+
 }  // namespace psn

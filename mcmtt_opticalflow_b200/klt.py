@@ -52,7 +52,7 @@ class DetectJob(C.Structure):
 
 
 EXPORTS = [
-    "psnw_klt_detect_batch", "psnw_join", "psnw_gridfast_detect", "psnw_read_fast_map", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
+    "psnw_klt_detect_batch", "psnw_join", "psnw_gridfast_detect", "psnw_read_fast_map", "psnw_points_in_boxes", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
     "psnw_push_frames_bgr", "psnw_frames_held", "psnw_klt_detect", "psnw_klt_track", "psnw_klt_track_batch",
     "psnw_box_update", "psnw_sync", "psnw_last_error", "psnw_get_stream", "psnw_level_info", "psnw_read_level",
     "psnw_read_min_eig", "psnw_launch_count", "psnw_push_frame_bytes", "psnw_rebuild_pyramids", "psnw_levels_built",
@@ -94,6 +94,7 @@ def load():
         lib.psnw_gridfast_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_read_fast_map.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.psnw_points_in_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         lib.psnw_klt_track.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_klt_track_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -304,6 +305,16 @@ class KLTContext:
         self._ck(self.lib.psnw_box_update(self._h, _ptr(boxes), n, _ptr(pre), _ptr(cur), _ptr(st), _ptr(offsets),
                                           BOX_REFERENCE, _ptr(out), _ptr(mask), _ptr(counts), MEM_HOST))
         return out, mask[:pre.shape[0]], counts[:n]
+
+    def points_in_boxes(self, pts, tracker_offsets, det_boxes):
+        """-> int32 [n_detections, n_trackers]: tracked points of each tracker inside each detection box."""
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        off = np.ascontiguousarray(tracker_offsets, np.int32)
+        boxes = np.ascontiguousarray(det_boxes, np.float64).reshape(-1, 4)
+        nt, nd = len(off) - 1, len(boxes)
+        counts = np.zeros((max(nd, 1), max(nt, 1)), np.int32)
+        self._ck(self.lib.psnw_points_in_boxes(self._h, _ptr(pts), _ptr(off), nt, _ptr(boxes), nd, _ptr(counts), MEM_HOST))
+        return counts[:nd, :nt]
 
     def box_update_raw(self, boxes_in, n_targets, pre, cur, status, offsets, boxes_out, mask, counts, mem):
         self._ck(self.lib.psnw_box_update(self._h, _ptr(boxes_in), n_targets, _ptr(pre), _ptr(cur), _ptr(status),

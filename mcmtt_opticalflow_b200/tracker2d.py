@@ -30,6 +30,10 @@ def load():
         lib.psnt_get_objects.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnt_get_detection_boxes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnt_hungarian.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.psnt_read_detections.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.psnt_write_result.argtypes = [C.c_void_p, C.c_char_p]
+        lib.psnt_result_roundtrip.argtypes = [C.c_char_p, C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -41,6 +45,14 @@ def hungarian(cost):
     mr, mc = np.zeros(max(r, c), np.int32), np.zeros(max(r, c), np.int32)
     n = load().psnt_hungarian(cost.ctypes.data, r, c, mr.ctypes.data, mc.ctypes.data)
     return mr[:n].copy(), mc[:n].copy()
+
+
+def read_detections(path, cap=256):
+    """PETS.S2.L1 full-body detection file (psn::ReadDetectionResultWithTxt, psn_where/PSNWhere_Utils.cpp:996-1088)
+    -> (boxes float64 [n,4], heads float64 [n,4]); a missing file gives empty arrays."""
+    boxes, heads = np.zeros((cap, 4), np.float64), np.zeros((cap, 4), np.float64)
+    n = load().psnt_read_detections(os.fsencode(path), boxes.ctypes.data, heads.ctypes.data, cap)
+    return boxes[:n].copy(), heads[:n].copy()
 
 
 class Tracker2D:
@@ -67,6 +79,11 @@ class Tracker2D:
         ids, ob, nf = np.zeros(max(n, 1), np.uint32), np.zeros((max(n, 1), 4), np.float64), np.zeros(max(n, 1), np.int32)
         self.lib.psnt_get_objects(self._h, ids.ctypes.data, ob.ctypes.data, nf.ctypes.data, n)
         return ids[:n], ob[:n], nf[:n]
+
+    def write_result(self, path):
+        """track2D_result_cam%d_frame%04d.txt of the last run (CPSNWhere_Tracker2D::FilePrintResult, Tracker2D.cpp:1268-1342)."""
+        if self.lib.psnt_write_result(self._h, os.fsencode(path)) != 0:
+            raise OSError("cannot write %s" % path)
 
     def detection_boxes(self, cap=512):
         """Backward-chain boxes (current -> past) of the detections kept by the last run."""

@@ -131,3 +131,23 @@ def test_overlapped_batched_detect_matches_plain(oracle):
             assert np.array_equal(g_cnt[k], plain[k][1])
             assert np.array_equal(g_pts[k], plain[k][0])
             assert (g_pts[k][0, g_cnt[k][0]:] == -1e6).all()  # unused slots carry the sentinel
+
+
+def test_points_in_boxes(ctx):
+    """Next row f-3: per (detection, tracker) contain counts, PSN_Rect::contain semantics in double."""
+    rng = np.random.default_rng(9)
+    nt, nd = 37, 23
+    ns = rng.integers(0, 120, size=nt); ns[0] = 0
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    pts = rng.uniform(-20, 800, size=(off[-1], 2)).astype(np.float32)
+    boxes = np.stack([rng.uniform(-10, 700, nd), rng.uniform(-10, 500, nd), rng.uniform(5, 200, nd), rng.uniform(5, 300, nd)], 1)
+    pts[:5] = [boxes[0, 0], boxes[0, 1]]                           # exactly on the inclusive edge
+    pts[5:9] = np.float32([boxes[0, 0] + boxes[0, 2], boxes[0, 1]])  # near the exclusive edge (float32-rounded)
+    got = ctx.points_in_boxes(pts, off, boxes)
+    want = np.zeros((nd, nt), np.int32)
+    for d, (x, y, w, h) in enumerate(boxes):
+        px, py = pts[:, 0].astype(np.float64), pts[:, 1].astype(np.float64)
+        inside = (px >= x) & (px < x + w) & (py >= y) & (py < y + h)
+        for t in range(nt):
+            want[d, t] = inside[off[t]:off[t + 1]].sum()
+    assert np.array_equal(got, want)

@@ -83,3 +83,42 @@ def test_run_keeps_ids_and_matches_oracle_chain(oracle):
         assert all(cur[k] == first[k] for k in iso), (t, cur, first)
     later = by_box(4)
     assert all(later[k] != first[k] for k in first) and min(later.values()) >= ntgt
+
+
+def test_detection_file_reader(tmp_path):
+    """PETS.S2.L1 full-body detection dump, the format psn::ReadDetectionResultWithTxt parses (Utils.cpp:1021-1080)."""
+    parts = ["HEAD", "F1", "S1", "GR", "S2", "A1", "A2", "F2"]
+    rng = np.random.default_rng(5)
+    boxes = rng.uniform(0, 500, size=(3, 4)).round(3)
+    pb = rng.uniform(0, 500, size=(3, 8, 4)).round(3)
+    txt = "numBoxes:3\n"
+    for d in range(3):
+        txt += "{\n\tROOT:{%f,%f,%f,%f}\n" % tuple(boxes[d])
+        for p, name in enumerate(parts):
+            txt += "\t%s:{%f,%f,%f,%f}\n" % ((name,) + tuple(pb[d, p]))
+        txt += "}\n"
+    f = tmp_path / "frame_0001.txt"
+    f.write_text(txt)
+    b, hd = tracker2d.read_detections(str(f))
+    assert np.allclose(b, boxes, atol=1e-3) and np.allclose(hd, pb[:, 0], atol=1e-3)
+    b, hd = tracker2d.read_detections(str(tmp_path / "missing.txt"))
+    assert b.shape == (0, 4)
+
+
+def test_result_file_roundtrip(tmp_path):
+    """track2D_result_cam%d_frame%04d.txt: FilePrintResult (Tracker2D.cpp:1268-1342) -> Read2DTrackResultWithTxt (Utils.cpp:1148-1240)."""
+    import ctypes as C
+    lib = tracker2d.load()
+    rng = np.random.default_rng(6)
+    n, k = 5, 7
+    ids = np.arange(10, 10 + n, dtype=np.uint32)
+    boxes = rng.uniform(0, 700, size=(n, 4))
+    pts = rng.uniform(0, 700, size=(n, k, 2)).astype(np.float32)
+    ids_o, boxes_o, pts_o = np.zeros(n, np.uint32), np.zeros((n, 4)), np.zeros((n, k, 2), np.float32)
+    path = str(tmp_path / "track2D_result_cam1_frame0042.txt")
+    got = lib.psnt_result_roundtrip(path.encode(), 1, 42, n, ids.ctypes.data, boxes.ctypes.data, pts.ctypes.data, k,
+                                    ids_o.ctypes.data, boxes_o.ctypes.data, pts_o.ctypes.data)
+    assert got == n and np.array_equal(ids_o, ids)
+    assert np.allclose(boxes_o, boxes, atol=1e-5) and np.allclose(pts_o, pts, atol=1e-4)        # %f keeps 6 decimals
+    head = open(path).read().splitlines()[:3]
+    assert head == ["camIdx:1", "frameIdx:42", "numObjectInfos:5{"]
