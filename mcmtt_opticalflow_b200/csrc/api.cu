@@ -167,6 +167,15 @@ bool slot_ok(const psnw_ctx *c, int cam, int slot)
     return cam >= 0 && cam < c->p.n_cameras && slot >= 0 && slot < c->held[cam];
 }
 
+// every entry point runs on the context's device, whatever device the calling thread had current
+int enter(psnw_ctx *ctx)
+{
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur == ctx->p.device) return PSNW_OK;
+    CK(cudaSetDevice(ctx->p.device));
+    return PSNW_OK;
+}
+
 // make the main stream wait for an overlapped detect (no host block)
 int join_aux(psnw_ctx *ctx)
 {
@@ -285,6 +294,7 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
         ctx->own_stream = true;
     }
 
+    if (configure_lk_kernels() || configure_box_kernels() || configure_detect_kernels()) return bail(PSNW_ECUDA);
     if (cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)
@@ -325,6 +335,7 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
 int psnw_destroy(psnw_ctx *ctx)
 {
     if (!ctx) return PSNW_EARG;
+    cudaSetDevice(ctx->p.device);
     if (ctx->aux) cudaStreamSynchronize(ctx->aux);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -355,6 +366,7 @@ int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const
 {
     (void)frame_idx;
     if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (n <= 0 || !cams || !grays || pitch < (size_t)ctx->p.width) return fail(ctx, PSNW_EARG, "psnw_push_frames arguments");
     for (int i = 0; i < n; ++i)
         if (!grays[i]) return fail(ctx, PSNW_EARG, "null frame pointer");
@@ -381,6 +393,7 @@ int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *c
 {
     (void)frame_idx;
     if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (n <= 0 || !cams || !bgr || pitch < (size_t)ctx->p.width * 3 || (luma_bits != 14 && luma_bits != 15))
         return fail(ctx, PSNW_EARG, "psnw_push_frames_bgr arguments");
     const LevelGeom &l0 = ctx->pyr.lv[0];
@@ -415,6 +428,7 @@ int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *c
 int psnw_rebuild_pyramids(psnw_ctx *ctx, int n, const int *cams)
 {
     if (!ctx || n <= 0 || !cams) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     std::vector<int> planes(n);
     for (int i = 0; i < n; ++i) {
         if (!slot_ok(ctx, cams[i], 0)) return fail(ctx, PSNW_ESTATE, "psnw_rebuild_pyramids: camera holds no frame");
@@ -432,6 +446,7 @@ int psnw_frames_held(psnw_ctx *ctx, int cam)
 int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, int mem_flags)
 {
     if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (!jobs || n_jobs <= 0) return fail(ctx, PSNW_EARG, "psnw_klt_track_batch: no jobs");
     const bool dev = mem_flags == PSNW_MEM_DEVICE;
     int total = 0, total_groups = 0;
@@ -551,6 +566,7 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
                     uint8_t *inlier_mask, int *inlier_counts, int mem_flags)
 {
     if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (n_targets == 0) return PSNW_OK;
     if (n_targets < 0 || !boxes_in || !target_offsets || !boxes_out || !inlier_mask || !inlier_counts || mode != PSNW_BOX_REFERENCE)
         return fail(ctx, PSNW_EARG, "psnw_box_update arguments");
@@ -631,6 +647,7 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
                           float quality, float min_dist, int mem_flags)
 {
     if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (n_jobs <= 0) return PSNW_OK;
     if (!jobs || max_per_target < 1 || !(quality > 0.f) || min_dist < 0.f) return fail(ctx, PSNW_EARG, "psnw_klt_detect arguments");
     int total = 0;
@@ -746,6 +763,7 @@ int psnw_points_in_boxes(psnw_ctx *ctx, const float *pts_xy, const int *tracker_
                          const double *det_boxes, int n_detections, int *counts, int mem_flags)
 {
     if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (n_trackers == 0 || n_detections == 0) return PSNW_OK;
     if (n_trackers < 0 || n_detections < 0 || !tracker_offsets || !det_boxes || !counts)
         return fail(ctx, PSNW_EARG, "psnw_points_in_boxes arguments");
@@ -783,6 +801,7 @@ int psnw_gridfast_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, 
                          int threshold, int grid_rows, int grid_cols, int max_total, float *pts_xy, int *counts, int mem_flags)
 {
     if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (n_targets == 0) return PSNW_OK;
     if (n_targets < 0 || max_per_target < 1 || !boxes || !pts_xy || !counts || grid_rows < 1 || grid_cols < 1 ||
         grid_rows * grid_cols > 64 || max_total < 0)
@@ -850,6 +869,7 @@ int psnw_gridfast_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, 
 int psnw_read_fast_map(psnw_ctx *ctx, int cam, uint8_t *map_out)
 {
     if (!ctx || !map_out || cam < 0 || cam >= ctx->p.n_cameras) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (!ctx->fmap[cam] || !ctx->fmap_tag[cam]) return fail(ctx, PSNW_ESTATE, "psnw_read_fast_map: no map computed yet");
     const LevelGeom &l0 = ctx->pyr.lv[0];
     CK(cudaStreamSynchronize(ctx->stream));
@@ -860,12 +880,14 @@ int psnw_read_fast_map(psnw_ctx *ctx, int cam, uint8_t *map_out)
 int psnw_join(psnw_ctx *ctx)
 {
     if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     return join_aux(ctx);
 }
 
 int psnw_sync(psnw_ctx *ctx)
 {
     if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (int rc = join_aux(ctx)) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return PSNW_OK;
@@ -889,6 +911,7 @@ int psnw_levels_built(psnw_ctx *ctx) { return ctx ? ctx->pyr.levels : PSNW_EARG;
 int psnw_read_level(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *img_out, int16_t *dxy_out)
 {
     if (!ctx || level < 0 || level >= ctx->pyr.levels) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_read_level: camera/slot holds no frame");
     const LevelGeom &g = ctx->pyr.lv[level];
     const int plane = plane_of(ctx, cam, slot);
@@ -901,6 +924,7 @@ int psnw_read_level(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *img_ou
 int psnw_read_min_eig(psnw_ctx *ctx, int cam, int slot, float *eig_out)
 {
     if (!ctx || !eig_out) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
     if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_read_min_eig: camera/slot holds no frame");
     const LevelGeom &l0 = ctx->pyr.lv[0];
     int rc = join_aux(ctx);

@@ -151,6 +151,12 @@ int launch_points_in_boxes(const float2 *pts, const int *offsets, int n_trk, con
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+// opt-in shared-memory sizes are a per-device attribute: psnw_create calls this for the context's device
+int configure_box_kernels()
+{
+    return cudaFuncSetAttribute(box_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPts * 17 + 16) == cudaSuccess ? 0 : -1;
+}
+
 int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
                       const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,
                       int *counts, int max_pts_per_target, cudaStream_t stream)
@@ -158,11 +164,6 @@ int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, 
     if (n_targets <= 0) return 0;
     const int cap = std::min(std::max(max_pts_per_target, 1), kMaxPts);
     const size_t smem = (size_t)cap * 17 + 16;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(box_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPts * 17 + 16) != cudaSuccess) return -1;
-        configured = true;
-    }
     box_update_kernel<<<n_targets, kBoxThreads, smem, stream>>>(boxes_in, pre, cur, status, offsets, boxes_out, mask, counts, cap);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

@@ -60,6 +60,11 @@ struct LkParams {
     int do_fb;
 };
 
+// per-device kernel attributes (opt-in dynamic shared memory); called by psnw_create on the context's device
+int configure_lk_kernels();
+int configure_box_kernels();
+int configure_detect_kernels();
+
 // --- launchers (each returns the number of kernels it enqueued, or -1 with cudaGetLastError set) ---
 int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes,
                      cudaStream_t stream);

@@ -322,6 +322,11 @@ int launch_min_eig(const LevelGeom &l0, const EigList &list, cudaStream_t stream
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
+int configure_detect_kernels()
+{
+    return cudaFuncSetAttribute(detect_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8 + 16384 * 4) == cudaSuccess ? 0 : -1;
+}
+
 int launch_detect_select(int w, int h, int pitch, const DetectTarget *targets, int n_targets,
                          int max_per_target, float quality, float min_dist, unsigned long long *cand,
                          int max_roi_area, int max_tile_px, cudaStream_t stream)
@@ -333,11 +338,6 @@ int launch_detect_select(int w, int h, int pitch, const DetectTarget *targets, i
     while (cap < max_roi_area / 3 && cap < 8192) cap <<= 1;
     const int tile_cap = max_tile_px <= 16384 ? max_tile_px : 0;          // ROI tile in shared memory when it fits (64 KB)
     const size_t smem = (size_t)cap * sizeof(unsigned long long) + (size_t)tile_cap * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(detect_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8 + 16384 * 4) != cudaSuccess) return -1;
-        configured = true;
-    }
     detect_select_kernel<<<n_targets, kSelThreads, smem, stream>>>(w, h, pitch, targets, max_per_target, quality,
                                                                    min_dist, cand, cap, tile_cap);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

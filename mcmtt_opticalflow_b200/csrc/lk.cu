@@ -659,6 +659,11 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
 
 }  // namespace
 
+int configure_lk_kernels()
+{
+    return cudaFuncSetAttribute(lk_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess ? 0 : -1;
+}
+
 int launch_lk(const LkParams &P, int all_21x21, int max_win_px, cudaStream_t stream)
 {
     if (P.n_pts <= 0) return 0;
@@ -669,11 +674,6 @@ int launch_lk(const LkParams &P, int all_21x21, int max_win_px, cudaStream_t str
         const int stride = (max_win_px + 7) & ~7;
         const size_t smem = (size_t)stride * 6;
         if (smem > 200 * 1024) return -2;
-        static bool configured = false;
-        if (smem > 48 * 1024 && !configured) {
-            if (cudaFuncSetAttribute(lk_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -1;
-            configured = true;
-        }
         lk_generic_kernel<<<P.n_pts, kGenThreads, smem, stream>>>(P, max_win_px);
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

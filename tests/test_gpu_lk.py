@@ -174,3 +174,41 @@ def test_linearity_property_at_full_size():
         ctx.push_frame(b)
         o2, st2, _, _ = ctx.track(pts)
         assert np.abs(o2 - pts)[st2 == 1].max() < 1e-3
+
+
+def test_c4_dense_grid_properties_at_4k():
+    """BASELINE config C4 at full size (4K, stride-4 grid = 518 400 seeds, 5 levels): size-independent properties --
+    a frame tracked onto itself returns the seeds (idempotence), an integer-translated frame returns seeds + offset,
+    the FB error of validated points respects the gate, and the batched result does not depend on how the seeds are
+    split into jobs (sharding invariance)."""
+    w, h = 3840, 2160
+    cam = synth.Camera(w, h, 0, cam=4)
+    a = cam.frame(0)
+    dx, dy = -2, 3
+    b = np.roll(np.roll(a, dy, axis=0), dx, axis=1)
+    pts = synth.grid_seeds(w, h, 4, 2)
+    n = len(pts)
+    assert n == 518400
+    with klt.KLTContext(w, h, levels=5, fb_thresh=1.0, max_points=n + 16) as ctx:
+        ctx.push_frame(a); ctx.push_frame(a)
+        o, st, er, fb = ctx.track(pts)
+        assert st.mean() > 0.99 and np.abs(o - pts)[st == 1].max() < 1e-3 and er[st == 1].max() < 1e-3
+        ctx.push_frame(b)
+        o, st, er, fb = ctx.track(pts)
+        inner = (pts[:, 0] > 40) & (pts[:, 0] < w - 40) & (pts[:, 1] > 40) & (pts[:, 1] < h - 40)
+        ok = (st == 1) & inner
+        assert ok.sum() > 0.95 * inner.sum()
+        d = o[ok] - pts[ok] - np.float32([dx, dy])
+        assert np.percentile(np.abs(d), 99.5) < 0.05
+        assert (fb[st == 1] <= 1.0).all()
+        # the same seeds as three jobs of unequal size in one batched launch: bit-identical outputs
+        cuts = [0, 100001, 350000, n]
+        jobs = []
+        for i in range(3):
+            m = cuts[i + 1] - cuts[i]
+            jobs.append(dict(cam=0, slot_from=1, slot_to=0, n_pts=m, pts=np.ascontiguousarray(pts[cuts[i]:cuts[i + 1]]),
+                             out=np.zeros((m, 2), np.float32), status=np.zeros(m, np.uint8), err=np.zeros(m, np.float32),
+                             fb_err=np.zeros(m, np.float32)))
+        ctx.track_batch(jobs)
+        assert np.array_equal(np.concatenate([j["out"] for j in jobs]), o)
+        assert np.array_equal(np.concatenate([j["status"] for j in jobs]), st)
