@@ -139,19 +139,31 @@ class GpuRig:
         t = torch
         with t.cuda.stream(self.stream):
             # frames: device copies and pinned host copies
-            self.d_frames = [[t.from_numpy(f).to(self.dev) for f in cam] for cam in self.frames]
-            self.h_frames = [[t.from_numpy(f).pin_memory() for f in cam] for cam in self.frames]
+            blk = np.stack([np.stack([self.frames[c][k] for c in range(self.ncam)]) for k in range(CYCLE)])   # [cycle][cam][h][w]
+            self.h_block = t.from_numpy(blk).pin_memory()
+            self.d_block = self.h_block.to(self.dev)
+            self.h_frames = [[self.h_block[k, c] for k in range(CYCLE)] for c in range(self.ncam)]
+            self.d_frames = [[self.d_block[k, c] for k in range(CYCLE)] for c in range(self.ncam)]
             # device state
             self.d_seeds = [t.zeros((self.npts, 2), dtype=t.float32, device=self.dev) for _ in range(2)]
-            self.d_out = t.zeros((self.npts, 2), dtype=t.float32, device=self.dev)
-            self.d_status = t.zeros(self.npts, dtype=t.uint8, device=self.dev)
+            # results of a step live in ONE device blob (points | boxes | counts | status | mask) so that the end-to-end
+            # arm reads them back with a single copy
+            n8 = (self.npts + 7) // 8 * 8
+            sizes = [self.npts * 8, self.ntargets * 32, (self.ntargets * 4 + 7) // 8 * 8, n8, n8]
+            offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            self.d_blob = t.zeros(int(offs[-1]), dtype=t.uint8, device=self.dev)
+            self.h_blob = t.zeros(int(offs[-1]), dtype=t.uint8).pin_memory()
+            view = lambda o, nbytes, dt, shape: self.d_blob[int(o):int(o) + nbytes].view(dt).view(shape)
+            self.d_out = view(offs[0], self.npts * 8, t.float32, (self.npts, 2))
+            self.d_boxes_out = view(offs[1], self.ntargets * 32, t.float64, (self.ntargets, 4))
+            self.d_counts = view(offs[2], self.ntargets * 4, t.int32, (self.ntargets,))
+            self.d_status = view(offs[3], self.npts, t.uint8, (self.npts,))
+            self.d_mask = view(offs[4], self.npts, t.uint8, (self.npts,))
+            self.blob_bytes = int(offs[-1])
             self.d_err = t.zeros(self.npts, dtype=t.float32, device=self.dev)
             self.d_fb = t.zeros(self.npts, dtype=t.float32, device=self.dev)
             self.d_counts_det = t.zeros(self.ntargets, dtype=t.int32, device=self.dev)
             self.d_boxes_in = t.zeros((self.ntargets, 4), dtype=t.float64, device=self.dev)
-            self.d_boxes_out = t.zeros((self.ntargets, 4), dtype=t.float64, device=self.dev)
-            self.d_mask = t.zeros(self.npts, dtype=t.uint8, device=self.dev)
-            self.d_counts = t.zeros(self.ntargets, dtype=t.int32, device=self.dev)
             off = np.arange(self.ntargets + 1, dtype=np.int32) * max(self.per, 1)
             self.d_off = t.from_numpy(off).to(self.dev)
             self.h_off = t.from_numpy(off).pin_memory()
@@ -238,8 +250,7 @@ class GpuRig:
             jobs = self._jobs(seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(), self.d_err.data_ptr(), self.d_fb.data_ptr())
             ctx._ck(ctx.lib.psnw_klt_track_batch(ctx._h, jobs, self.ncam, klt.MEM_DEVICE))
             if host:
-                self.h_out.copy_(self.d_out, non_blocking=True)
-                self.h_status.copy_(self.d_status, non_blocking=True)
+                self.h_blob.copy_(self.d_blob, non_blocking=True)
             self.step_idx += 1
             return
         self._detect(t_idx, seeds_next, self.d_counts_det, klt.MEM_DEVICE | klt.MEM_OVERLAP)
@@ -249,21 +260,16 @@ class GpuRig:
                            self.d_off.data_ptr(), self.d_boxes_out.data_ptr(), self.d_mask.data_ptr(), self.d_counts.data_ptr(), klt.MEM_DEVICE)
         ctx.join()
         if host:
-            self.h_out.copy_(self.d_out, non_blocking=True)
-            self.h_status.copy_(self.d_status, non_blocking=True)
-            self.h_boxes_out.copy_(self.d_boxes_out, non_blocking=True)
-            self.h_counts.copy_(self.d_counts, non_blocking=True)
-            self.h_mask.copy_(self.d_mask, non_blocking=True)
+            self.h_blob.copy_(self.d_blob, non_blocking=True)
         self.which = nxt
         self.step_idx += 1
 
     def e2e_bytes(self):
         n, nt = self.npts, self.ntargets
         if self.grid:
-            return self.ncam * self.w * self.h, n * 8 + n
+            return self.ncam * self.w * self.h, self.blob_bytes
         h2d = self.ncam * self.w * self.h + nt * 32          # frames + detection boxes (PSN_Rect)
-        d2h = n * 8 + n + nt * 32 + nt * 4 + n               # points, status, boxes, inlier counts, inlier mask
-        return h2d, d2h
+        return h2d, self.blob_bytes                          # points, boxes, inlier counts, status, inlier mask (one blob)
 
     def timed(self, steps, warmup, host, sampler=None):
         """-> (total seconds over `steps`, launches) with L2 flushed between steps; events on the context stream."""

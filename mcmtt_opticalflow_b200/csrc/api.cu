@@ -374,9 +374,25 @@ int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const
     int rc = advance_ring(ctx, n, cams, planes);
     if (rc) return rc;
     const LevelGeom &l0 = ctx->pyr.lv[0];
-    for (int i = 0; i < n; ++i)
-        CK(cudaMemcpy2DAsync(l0.img + (size_t)planes[i] * l0.plane_px, l0.pitch, grays[i], pitch, l0.w, l0.h,
-                             h2d(mem_flags), ctx->stream));
+    // Frames that sit at a constant stride in the caller's memory and go to planes at a constant stride (the usual
+    // case: a [cameras][h][w] block, all rings in lockstep) travel as ONE copy, each frame being one "row" of it.
+    bool one_copy = n > 1 && pitch == (size_t)l0.pitch && l0.w == l0.pitch;
+    ptrdiff_t sstride = 0, dstride = 0;
+    if (one_copy) {
+        sstride = grays[1] - grays[0];
+        dstride = ((ptrdiff_t)planes[1] - planes[0]) * l0.plane_px;
+        one_copy = sstride >= (ptrdiff_t)l0.plane_px && dstride >= (ptrdiff_t)l0.plane_px;
+        for (int i = 2; one_copy && i < n; ++i)
+            one_copy = (grays[i] - grays[i - 1]) == sstride && ((ptrdiff_t)planes[i] - planes[i - 1]) * l0.plane_px == dstride;
+    }
+    if (one_copy) {
+        CK(cudaMemcpy2DAsync(l0.img + (size_t)planes[0] * l0.plane_px, (size_t)dstride, grays[0], (size_t)sstride,
+                             (size_t)l0.plane_px, n, h2d(mem_flags), ctx->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            CK(cudaMemcpy2DAsync(l0.img + (size_t)planes[i] * l0.plane_px, l0.pitch, grays[i], pitch, l0.w, l0.h,
+                                 h2d(mem_flags), ctx->stream));
+    }
     rc = build_pyramids(ctx, planes);
     if (rc) return rc;
     if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));

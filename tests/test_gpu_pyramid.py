@@ -105,3 +105,17 @@ def test_errors():
         assert e.value.code == klt.EARG
     with pytest.raises(klt.PsnwError):
         klt.KLTContext(4, 4)
+
+
+def test_contiguous_block_takes_the_single_copy_path(oracle):
+    """[cameras][h][w] block with w == pitch: psnw_push_frames moves all frames with one strided copy."""
+    w, h, ncam = 256, 96, 5
+    blk = np.random.default_rng(3).integers(0, 256, size=(ncam, h, w), dtype=np.uint8)
+    with klt.KLTContext(w, h, n_cameras=ncam, levels=3) as ctx:
+        for rep in range(2):                                   # twice: the ring advances in lockstep
+            ctx.push_frames([blk[c] for c in range(ncam)])
+            for c in range(ncam):
+                _check_levels(ctx, oracle, blk[c], cam=c, slot=0)
+        ctx.push_frames([blk[c] for c in (4, 2, 0)], cams=[4, 2, 0])     # negative source stride, non-unit camera step
+        for c in (4, 2, 0):
+            _check_levels(ctx, oracle, blk[c], cam=c, slot=0)
