@@ -3,6 +3,7 @@
 // device every entry point fails with PSNW_ECUDA (there is no CPU fallback).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <utility>
@@ -39,6 +40,10 @@ struct psnw_ctx {
     bool aux_pending = false;
     PyrDesc pyr;
     CUtensorMap maps[PSNW_MAX_LEVELS];
+    CUtensorMap map_fused;                // level-0 map with the box of the fused multi-level kernel
+    int fused_levels = 0;                 // 3 or 4 when the fused kernel is usable, else 0
+    size_t fused_max_px = 2200000;   // auto mode: fused kernel up to this many level-0 pixels per launch
+    int pyr_mode = 0;                     // 0 auto, 1 per-level kernels only, 2 fused whenever possible (PSNW_PYR_MODE, bring-up)
     int planes = 0;
     std::vector<int> head, held;
     std::vector<uint64_t> plane_seq;     // push counter per plane (min-eig cache tag)
@@ -153,6 +158,20 @@ int make_tensor_maps(psnw_ctx *ctx)
             return fail(ctx, PSNW_ECUDA, msg);
         }
     }
+    ctx->fused_levels = ctx->pyr.levels >= 4 ? 4 : ctx->pyr.levels == 3 ? 3 : 0;
+    if (ctx->fused_levels) {
+        int bw = 0, bh = 0;
+        fused_box(ctx->fused_levels, &bw, &bh);
+        const LevelGeom &g = ctx->pyr.lv[0];
+        const cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)ctx->planes};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.plane_px};
+        const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = encode(&ctx->map_fused, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, PSNW_ECUDA, "cuTensorMapEncodeTiled(fused level-0 map)");
+    }
     return PSNW_OK;
 }
 
@@ -206,7 +225,19 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes)
         PlaneList pl;
         pl.n = (int)std::min<size_t>(63, planes.size() - b);
         for (int i = 0; i < pl.n; ++i) pl.plane[i] = planes[b + i];
-        for (int l = 0; l < ctx->pyr.levels; ++l) {
+        // Small launches (a rig frame of a few small cameras) are latency-bound with one launch per level: there the
+        // fused kernel builds levels 0..3 in one launch.  Large launches keep the per-level kernels, which run at
+        // 70-90 % of the HBM roofline and do not recompute halos.
+        int first = 0;
+        const size_t px = (size_t)ctx->pyr.lv[0].w * ctx->pyr.lv[0].h * pl.n;
+        const bool fused = ctx->fused_levels && (ctx->pyr_mode == 2 || (ctx->pyr_mode == 0 && px <= ctx->fused_max_px));
+        if (fused) {
+            const int r = launch_pyr_fused(ctx->pyr, ctx->fused_levels, &ctx->map_fused, pl, ctx->stream);
+            if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_fused_kernel launch", cudaGetLastError());
+            ctx->launches += r;
+            first = ctx->fused_levels < ctx->pyr.levels ? ctx->fused_levels - 1 : ctx->pyr.levels;   // level 3 again to feed level 4
+        }
+        for (int l = first; l < ctx->pyr.levels; ++l) {
             const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, ctx->stream);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_scharr_kernel launch", cudaGetLastError());
             ctx->launches += r;
@@ -294,7 +325,8 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
         ctx->own_stream = true;
     }
 
-    if (configure_lk_kernels() || configure_box_kernels() || configure_detect_kernels()) return bail(PSNW_ECUDA);
+    if (configure_lk_kernels() || configure_box_kernels() || configure_detect_kernels() || configure_fused_kernels()) return bail(PSNW_ECUDA);
+    if (const char *m = getenv("PSNW_PYR_MODE")) ctx->pyr_mode = !strcmp(m, "level") ? 1 : !strcmp(m, "fused") ? 2 : 0;
     if (cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)

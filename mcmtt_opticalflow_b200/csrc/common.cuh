@@ -68,6 +68,10 @@ int configure_detect_kernels();
 // --- launchers (each returns the number of kernels it enqueued, or -1 with cudaGetLastError set) ---
 int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes,
                      cudaStream_t stream);
+// fused multi-level variant (pyramid_fused.cu): levels 0..nl-1 in one launch; fused_box = TMA box of its level-0 map
+void fused_box(int nl, int *box_w, int *box_h);
+int configure_fused_kernels();
+int launch_pyr_fused(const PyrDesc &pyr, int nl, const CUtensorMap *map0, const PlaneList &planes, cudaStream_t stream);
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,
                     int luma_bits, cudaStream_t stream);
 int launch_lk(const LkParams &P, int all_21x21, int max_win_px, cudaStream_t stream);

@@ -19,9 +19,13 @@ def _check_levels(ctx, oracle, img, cam=0, slot=0):
         assert np.array_equal(g_dxy, oracle.scharr(cur)), "Scharr level %d differs" % l
 
 
+@pytest.mark.parametrize("mode", ["level", "fused"])
 @pytest.mark.parametrize("w,h,levels", [(768, 576, 4), (767, 575, 4), (129, 33, 3), (16, 16, 2), (130, 70, 3),
-                                        (1920, 1080, 4), (257, 131, 5), (640, 480, 6)])
-def test_bit_exact_vs_oracle(oracle, w, h, levels):
+                                        (1920, 1080, 4), (257, 131, 5), (640, 480, 6), (193, 65, 4), (385, 129, 3)])
+def test_bit_exact_vs_oracle(oracle, monkeypatch, w, h, levels, mode):
+    """Both pyramid builders -- one launch per level (pyramid.cu) and the fused multi-level kernel (pyramid_fused.cu) --
+    are forced in turn (PSNW_PYR_MODE is read at psnw_create); the default picks by launch size."""
+    monkeypatch.setenv("PSNW_PYR_MODE", mode)
     rng = np.random.default_rng(w * 1000 + h)
     img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
     with klt.KLTContext(w, h, n_cameras=1, levels=levels) as ctx:
@@ -48,7 +52,9 @@ def test_golden_fixture(golden):
             assert np.array_equal(dxy[..., 1], golden["dy_odd_%d" % l])
 
 
-def test_batched_cameras_and_ring_rotation(oracle):
+@pytest.mark.parametrize("mode", ["level", "fused"])
+def test_batched_cameras_and_ring_rotation(oracle, monkeypatch, mode):
+    monkeypatch.setenv("PSNW_PYR_MODE", mode)
     w, h, ncam = 384, 288, 3
     cams = [synth.Camera(w, h, 4, cam=c) for c in range(ncam)]
     with klt.KLTContext(w, h, n_cameras=ncam, levels=3) as ctx:
