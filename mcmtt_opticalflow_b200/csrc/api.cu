@@ -51,6 +51,8 @@ struct psnw_ctx {
     DevBuf arena;                         // per-call device scratch (stream ordered)
     size_t arena_off = 0;
     DevBuf desc;                          // job / group descriptors (track)
+    unsigned *lk_work = nullptr;          // [2] work counters of the persistent 21x21 LK kernel (self-resetting)
+    int lk_ctas = 0;                      // resident CTAs of that kernel on this device
     DevBuf det_desc;                      // target descriptors + staged outputs (detect; may run on the aux stream)
     DevBuf cand;                          // detect candidate scratch
     DevBuf bgr;                           // BGR staging for psnw_push_frames_bgr
@@ -326,6 +328,10 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     }
 
     if (configure_lk_kernels() || configure_box_kernels() || configure_detect_kernels() || configure_fused_kernels()) return bail(PSNW_ECUDA);
+    ctx->lk_ctas = lk_w21_resident_ctas();
+    if (ctx->lk_ctas <= 0) return bail(PSNW_ECUDA);
+    if (cudaMalloc(&ctx->lk_work, 2 * sizeof(unsigned)) != cudaSuccess) return bail(PSNW_ENOMEM);
+    cudaMemsetAsync(ctx->lk_work, 0, 2 * sizeof(unsigned), ctx->stream);
     if (const char *m = getenv("PSNW_PYR_MODE")) ctx->pyr_mode = !strcmp(m, "level") ? 1 : !strcmp(m, "fused") ? 2 : 0;
     if (cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -382,6 +388,7 @@ int psnw_destroy(psnw_ctx *ctx)
     for (uint8_t *e : ctx->fmap) if (e) cudaFree(e);
     if (ctx->arena.p) cudaFree(ctx->arena.p);
     if (ctx->desc.p) cudaFree(ctx->desc.p);
+    if (ctx->lk_work) cudaFree(ctx->lk_work);
     if (ctx->cand.p) cudaFree(ctx->cand.p);
     if (ctx->bgr.p) cudaFree(ctx->bgr.p);
     for (StageSlot &s : ctx->stage) {
@@ -577,7 +584,8 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     P.min_eig = ctx->p.min_eig_thresh;
     P.fb_thresh = ctx->p.fb_thresh;
     P.do_fb = do_fb ? 1 : 0;
-    const int r = launch_lk(P, all21 ? 1 : 0, max_win_px, ctx->stream);
+    P.work = ctx->lk_work;
+    const int r = launch_lk(P, all21 ? 1 : 0, max_win_px, ctx->lk_ctas, ctx->stream);
     if (r == -2) return fail(ctx, PSNW_EARG, "psnw_klt_track: window too large for shared memory");
     if (r < 0) return fail(ctx, PSNW_ECUDA, "lk kernel launch", cudaGetLastError());
     ctx->launches += r;

@@ -58,6 +58,7 @@ struct LkParams {
     float min_eig;
     float fb_thresh;
     int do_fb;
+    unsigned *work;           // [2] point counter / finished-warp counter of the persistent 21x21 kernel (zero between launches)
 };
 
 // per-device kernel attributes (opt-in dynamic shared memory); called by psnw_create on the context's device
@@ -74,7 +75,8 @@ int configure_fused_kernels();
 int launch_pyr_fused(const PyrDesc &pyr, int nl, const CUtensorMap *map0, const PlaneList &planes, cudaStream_t stream);
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,
                     int luma_bits, cudaStream_t stream);
-int launch_lk(const LkParams &P, int all_21x21, int max_win_px, cudaStream_t stream);
+int lk_w21_resident_ctas();   // CTAs of the persistent 21x21 kernel resident at once on the current device, or -1
+int launch_lk(const LkParams &P, int all_21x21, int max_win_px, int resident_ctas, cudaStream_t stream);
 int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
                       const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,
                       int *counts, int max_pts_per_target, cudaStream_t stream);

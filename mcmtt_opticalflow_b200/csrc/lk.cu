@@ -13,10 +13,11 @@
 // Two kernels:
 //   lk_generic_kernel   any window size (reference-faithful (int)box.w x (int)box.h windows): template patch
 //                       in shared memory, image reads through L1 with on-the-fly REFLECT_101 / zero borders.
-//   lk_w21_kernel       21x21 window (BASELINE configs): the 441 pixels are 63 horizontal runs of 7, two runs
-//                       per lane; the template (I, Ix, Iy) lives in registers; the 22x22 u8 patch of the
-//                       target image is staged per iteration into shared memory with aligned 32-bit loads
-//                       and bilinearly sampled with dp2a on packed bytes; reductions use REDUX.
+//   lk_w21_kernel       21x21 window (BASELINE configs): persistent warps draw points from a device counter; the
+//                       441 pixels are 63 horizontal runs of 7, two runs per lane; the template (I, Ix, Iy) lives in
+//                       registers; patches are staged with cp.async (source patches one level ahead, the target
+//                       patch once per level with a 4-px margin) and bilinearly sampled with dp2a on packed
+//                       bytes; reductions use REDUX.
 #include <float.h>
 
 #include "common.cuh"
@@ -309,12 +310,12 @@ constexpr int kW = 21;                            // window
 constexpr int kPatch = kW + 1;                    // 22 x 22 samples feed the 21 x 21 bilinear window
 constexpr int kMargin = 4;                        // extra samples staged around the target-image patch
 constexpr int kJPatch = kPatch + 2 * kMargin;     // 30 x 30: the window may drift 8 px inside it before a re-stage
-constexpr int kU8Pitch = 13;                      // words per staged u8 row (52 B >= 15 + 30; odd: <= 2-way bank conflicts)
-constexpr int kIWords = 288;                      // 22 rows x 13 words, rounded up to a 16-byte multiple
-constexpr int kJWords = 392;                      // 30 rows x 13 words, rounded up
+constexpr int kU8Pitch = 12;                      // words per staged u8 row: 48 B >= 15 + 30, rows stay 16-byte aligned (cp.async)
+constexpr int kIWords = kPatch * kU8Pitch;        // 264
+constexpr int kJWords = kJPatch * kU8Pitch;       // 360
 constexpr int kDxPitch = 28;                      // words per staged derivative row = 7 groups of 4 pixels
 constexpr int kDxWords = kPatch * kDxPitch;       // 616
-constexpr int kWarpSmemWords = kIWords + kJWords + kDxWords;   // 1296 words = 5184 B per warp
+constexpr int kWarpSmemWords = kIWords + kJWords + kDxWords;   // 1240 words = 4960 B per warp
 #ifndef PSNW_LK_WARPS
 #define PSNW_LK_WARPS 4
 #endif
@@ -336,6 +337,20 @@ __device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c)
     return d;
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS): no staging registers, completion tracked per commit group ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, int src_bytes)   // src_bytes 0: zeros
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ int refl_clamp(int p, int n)
 {
     p = p < 0 ? -p : p;
@@ -349,83 +364,65 @@ __device__ __forceinline__ bool window_oob(int ix, int iy, int w, int h)
     return (unsigned)(ix + kW) >= (unsigned)(w + kW) || (unsigned)(iy + kW) >= (unsigned)(h + kW);
 }
 
-// ---- staging of an N x N u8 patch with top-left sample (x0, y0): loads are issued first (u8_issue) and written to
-// shared memory later (u8_commit) so that the I, dI and J fetches of a level are all in flight together.
-// Patches inside the frame are fetched as aligned 16-byte groups (3 lanes per row, 10 rows per instruction); patches
-// touching the border gather bytes row by row through REFLECT_101, the apron OpenCV keeps around every level.
-struct U8Loads {
-    uint4 v[3];
-    int off;       // byte offset of sample column 0 inside a staged row
-    bool fast;
+// per-lane roles, fixed for the whole kernel
+struct WarpRole {
+    int lane;
+    int row0, col0, row1, col1;   // the lane's two runs: run r -> (row r / 3, first column 7 * (r % 3)); lane 31 owns one
+    int dr3, g3;                  // u8 staging: 16-byte group g3 of row dr3 (+10, +20)
+    int dr7, g7;                  // derivative staging: 16-byte group g7 of row dr7 (+4, +8, ...)
+    bool two;
 };
 
+// ---- staging of an N x N u8 patch with top-left sample (x0, y0) into rows of kU8Pitch words; returns the byte offset
+// of sample column 0 inside a staged row.  Patches inside the frame are copied as aligned 16-byte groups with cp.async
+// (3 lanes per row, 10 rows per instruction; the caller commits and waits); patches touching the border gather bytes
+// row by row through REFLECT_101, the apron OpenCV keeps around every level (plain stores, visible after __syncwarp).
 template <int N>
-__device__ __forceinline__ void u8_issue(const uint8_t *__restrict__ img, int pitch, int w, int h, int x0, int y0,
-                                         int lane, int dr3, int g3, U8Loads &L)
+__device__ __forceinline__ int stage_u8(const uint8_t *__restrict__ img, int pitch, int w, int h, int x0, int y0,
+                                        uint32_t *patch, const WarpRole &R)
 {
-    L.fast = x0 >= 0 && y0 >= 0 && x0 + N <= w && y0 + N <= h;
-    L.off = L.fast ? (x0 & 15) : 0;
-    if (L.fast) {
-        const int ng = (L.off + N + 15) >> 4;               // 16-byte groups per row: 2 or 3
-        const uint4 *src = reinterpret_cast<const uint4 *>(img + (size_t)(y0 + dr3) * pitch + (x0 - L.off)) + g3;
-        const int rstride = 10 * (pitch >> 4);
+    const bool fast = x0 >= 0 && y0 >= 0 && x0 + N <= w && y0 + N <= h;
+    if (fast) {
+        const int off = x0 & 15;
+        const int ng = (off + N + 15) >> 4;               // 16-byte groups per row: 2 or 3
+        if (R.lane < 30 && R.g3 < ng) {
+            const uint8_t *src = img + (size_t)(y0 + R.dr3) * pitch + (x0 - off) + 16 * R.g3;
+            const uint32_t dst = smem_u32(patch + R.dr3 * kU8Pitch + 4 * R.g3);
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-            if (lane < 30 && 10 * i + dr3 < N && g3 < ng) L.v[i] = __ldg(src + (size_t)i * rstride);
+            for (int i = 0; i < 3; ++i)
+                if (10 * i + R.dr3 < N) cp_async16(dst + i * (10 * kU8Pitch * 4), src + (size_t)i * 10 * pitch);
+        }
+        return off;
     }
-}
-
-template <int N>
-__device__ __forceinline__ void u8_commit(const U8Loads &L, const uint8_t *__restrict__ img, int pitch, int w, int h,
-                                          int x0, int y0, uint32_t *patch, int lane, int dr3, int g3)
-{
-    if (L.fast) {
-        const int ng = (L.off + N + 15) >> 4;
-        uint32_t *dst = patch + dr3 * kU8Pitch + 4 * g3;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-            if (lane < 30 && 10 * i + dr3 < N && g3 < ng) {
-                uint32_t *d = dst + 10 * i * kU8Pitch;
-                d[0] = L.v[i].x; d[1] = L.v[i].y; d[2] = L.v[i].z; d[3] = L.v[i].w;
-            }
-    } else if (lane < N) {
-        const uint8_t *col = img + refl_clamp(x0 + lane, w);
-        uint8_t *pb = reinterpret_cast<uint8_t *>(patch) + lane;
+    if (R.lane < N) {
+        const uint8_t *col = img + refl_clamp(x0 + R.lane, w);
+        uint8_t *pb = reinterpret_cast<uint8_t *>(patch) + R.lane;
 #pragma unroll 2
         for (int row = 0; row < N; ++row) pb[row * (kU8Pitch * 4)] = col[(size_t)refl_clamp(y0 + row, h) * pitch];
     }
+    return 0;
 }
 
 // ---- staging of the 22 x 22 (dx,dy) samples at (x0, y0) as aligned 16-byte groups (7 lanes per row, 4 rows per
-// instruction).  Outside the frame the derivative apron is zero (BORDER_CONSTANT): groups left of x = 0 or beyond the
-// row pitch and rows outside [0, h) become zeros; columns in [w, pitch) already hold zeros (K1 writes them).
-struct DxLoads {
-    uint4 v[6];
-    int off;       // word offset of sample column 0 inside a staged row
-};
-
-__device__ __forceinline__ void dxy_issue(const short2 *__restrict__ D, int pitch, int h, int x0, int y0,
-                                          int lane, int dr7, int g7, DxLoads &L)
+// instruction); the word offset of sample column 0 inside a staged row is x0 & 3.  Outside the frame the derivative
+// apron is zero (BORDER_CONSTANT): groups left of x = 0 or beyond the row pitch and rows outside [0, h) are zero-filled;
+// columns in [w, pitch) already hold zeros (K1 writes them).
+__device__ __forceinline__ void stage_dxy(const short2 *__restrict__ D, int pitch, int h, int x0, int y0, uint32_t *dxp,
+                                          const WarpRole &R)
 {
-    L.off = x0 & 3;
-    const int gx = x0 - L.off + 4 * g7;
+    const int gx = x0 - (x0 & 3) + 4 * R.g7;
     const bool xin = gx >= 0 && gx < pitch;
-    const uint4 *src = reinterpret_cast<const uint4 *>(D + (ptrdiff_t)(y0 + dr7) * pitch + gx);
-    const int rstride = pitch;                              // 4 rows x pitch px x 4 B / 16 B
+    if (R.lane < 28) {
+        const uint32_t dst = smem_u32(dxp + R.dr7 * kDxPitch + 4 * R.g7);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        L.v[i] = make_uint4(0u, 0u, 0u, 0u);
-        const int row = 4 * i + dr7;
-        if (lane < 28 && row < kPatch && xin && (unsigned)(y0 + row) < (unsigned)h) L.v[i] = __ldg(src + (ptrdiff_t)i * rstride);
-    }
-}
-
-__device__ __forceinline__ void dxy_commit(const DxLoads &L, uint32_t *dxp, int lane, int dr7, int g7)
-{
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const int row = 4 * i + dr7;
-        if (lane < 28 && row < kPatch) *reinterpret_cast<uint4 *>(dxp + row * kDxPitch + 4 * g7) = L.v[i];
+        for (int i = 0; i < 6; ++i) {
+            const int row = 4 * i + R.dr7;
+            if (row < kPatch) {
+                const bool ok = xin && (unsigned)(y0 + row) < (unsigned)h;
+                const short2 *src = ok ? D + (ptrdiff_t)(y0 + row) * pitch + gx : D;
+                cp_async16_zfill(dst + i * (4 * kDxPitch * 4), src, ok ? 16 : 0);
+            }
+        }
     }
 }
 
@@ -461,62 +458,79 @@ __device__ __forceinline__ int patch_origin(int ix, int n)
     return s;
 }
 
+// Source point at `level`: (sx, sy) = prevPt * 2^-level, window origin (ix, iy) = floor((sx, sy) - halfWin);
+// false when LKTrackerInvoker skips the level (window outside the frame).
+__device__ __forceinline__ bool src_origin(float px, float py, int level, int Lw, int Lh, float &sx, float &sy, int &ix, int &iy)
+{
+    constexpr float half = (kW - 1) * 0.5f;
+    const float sc = __int_as_float((127 - level) << 23);
+    sx = __fmul_rn(px, sc);
+    sy = __fmul_rn(py, sc);
+    ix = __float2int_rd(__fsub_rn(sx, half));
+    iy = __float2int_rd(__fsub_rn(sy, half));
+    return !window_oob(ix, iy, Lw, Lh);
+}
+
+// Stages the source-frame patches (I and its derivatives) of `level` -- always one commit group, possibly empty.
+// Called one level ahead: by then the template of the current level is in registers, so the copies land while the
+// current level iterates and the next level starts without waiting for memory.
+__device__ __forceinline__ void prefetch_src(const LkParams &P, int plane_a, int level, float px, float py,
+                                             uint32_t *ip, uint32_t *dxp, const WarpRole &R)
+{
+    if (level >= 0) {
+        const LevelGeom &L = P.lv[level];
+        float sx, sy;
+        int ix, iy;
+        if (src_origin(px, py, level, L.w, L.h, sx, sy, ix, iy)) {
+            stage_u8<kPatch>(L.img + (size_t)plane_a * L.plane_px, L.pitch, L.w, L.h, ix, iy, ip, R);
+            stage_dxy(L.dxy + (size_t)plane_a * L.plane_px, L.pitch, L.h, ix, iy, dxp, R);
+        }
+    }
+    cp_async_commit();
+}
+
 __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_level, float px, float py,
-                                       uint32_t *ip, uint32_t *jp, uint32_t *dxp, int lane, Solve &o)
+                                       uint32_t *ip, uint32_t *jp, uint32_t *dxp, const WarpRole &R, Solve &o)
 {
     constexpr float half = (kW - 1) * 0.5f;
     float next_x = 0.f, next_y = 0.f, er = 0.f;
     int st = 1;
-    // this lane's two runs: run r -> (row r / 3, first column 7 * (r % 3)); lane 31 owns a single run
-    const bool two = lane < 31;
-    const int r0 = lane, r1 = two ? lane + 32 : 62;
-    const int row0 = r0 / 3, col0 = 7 * (r0 - 3 * row0);
-    const int row1 = r1 / 3, col1 = 7 * (r1 - 3 * row1);
-    const int dr3 = row0, g3 = lane - 3 * row0;             // staging roles: u8 groups (3 per row) ...
-    const int dr7 = lane / 7, g7 = lane - 7 * dr7;          // ... and derivative groups (7 per row)
 
+    prefetch_src(P, plane_a, max_level, px, py, ip, dxp, R);
 #pragma unroll 1
     for (int level = max_level; level >= 0; --level) {
         const LevelGeom &L = P.lv[level];
         const int Lw = L.w, Lh = L.h, Lp = L.pitch;
-        const uint8_t *IA = L.img + (size_t)plane_a * L.plane_px;
-        const short2 *DA = L.dxy + (size_t)plane_a * L.plane_px;
         const uint8_t *JB = L.img + (size_t)plane_b * L.plane_px;
-        const float sc = __int_as_float((127 - level) << 23);
-        float prev_x = __fmul_rn(px, sc), prev_y = __fmul_rn(py, sc);
-        float nx, ny;
+        cp_async_wait<0>();                      // this level's I / dI patches (and every older copy) have landed
+        __syncwarp();
+
+        float prev_x, prev_y, nx, ny;
+        int ipx, ipy;
+        const bool src_ok = src_origin(px, py, level, Lw, Lh, prev_x, prev_y, ipx, ipy);
         if (level == max_level) { nx = prev_x; ny = prev_y; }
         else                    { nx = __fmul_rn(next_x, 2.f); ny = __fmul_rn(next_y, 2.f); }
         next_x = nx; next_y = ny;
-
-        prev_x = __fsub_rn(prev_x, half); prev_y = __fsub_rn(prev_y, half);
-        const int ipx = __float2int_rd(prev_x), ipy = __float2int_rd(prev_y);
-        if (window_oob(ipx, ipy, Lw, Lh)) {
+        if (!src_ok) {
             if (level == 0) { st = 0; er = 0.f; }
+            prefetch_src(P, plane_a, level - 1, px, py, ip, dxp, R);
             continue;
         }
+        prev_x = __fsub_rn(prev_x, half); prev_y = __fsub_rn(prev_y, half);
         int w00, w01, w10, w11;
         bilinear_weights(__fsub_rn(prev_x, (float)ipx), __fsub_rn(prev_y, (float)ipy), w00, w01, w10, w11);
+        const bool fastI = ipx >= 0 && ipy >= 0 && ipx + kPatch <= Lw && ipy + kPatch <= Lh;
+        const int offI = fastI ? (ipx & 15) : 0, offD = ipx & 3;
 
-        // ---- fetch I, dI around the source point and J around the first target position, all loads in flight ----
+        // ---- target patch around the first position: in flight while the template is computed ----
         nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
         int sx0 = 0, sy0 = 0, offJ = 0;
         bool staged = !window_oob(__float2int_rd(nx), __float2int_rd(ny), Lw, Lh);
-        if (staged) { sx0 = patch_origin(__float2int_rd(nx), Lw); sy0 = patch_origin(__float2int_rd(ny), Lh); }
-        __syncwarp();
-        int offI, offD;
-        {
-            U8Loads li;
-            DxLoads ld;
-            u8_issue<kPatch>(IA, Lp, Lw, Lh, ipx, ipy, lane, dr3, g3, li);
-            dxy_issue(DA, Lp, Lh, ipx, ipy, lane, dr7, g7, ld);
-            u8_commit<kPatch>(li, IA, Lp, Lw, Lh, ipx, ipy, ip, lane, dr3, g3);
-            dxy_commit(ld, dxp, lane, dr7, g7);
-            offI = li.off; offD = ld.off;
+        if (staged) {
+            sx0 = patch_origin(__float2int_rd(nx), Lw); sy0 = patch_origin(__float2int_rd(ny), Lh);
+            offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, jp, R);
         }
-        U8Loads lj;                              // J loads stay in flight while the template is computed
-        if (staged) u8_issue<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, lane, dr3, g3, lj);
-        __syncwarp();
+        cp_async_commit();
 
         // ---- template into registers ----
         int tC[14], tIx[14], tIy[14];          // tC = 256 - 512 * I: the dp2a chain then yields (J - I) << 9 directly
@@ -526,7 +540,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             const int c256[7] = {256, 256, 256, 256, 256, 256, 256};
 #pragma unroll
             for (int run = 0; run < 2; ++run) {
-                const int row = run ? row1 : row0, col = run ? col1 : col0;
+                const int row = run ? R.row1 : R.row0, col = run ? R.col1 : R.col0;
                 int v[7];
                 bilinear_run7(ip, row, offI + col, wt, wb, c256, v);
                 const uint32_t *d0 = dxp + row * kDxPitch + offD + col, *d1 = d0 + kDxPitch;
@@ -536,7 +550,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                     const uint32_t n0 = d0[k + 1], n1 = d1[k + 1];
                     int ix = (sext16(q0) * w00 + sext16(n0) * w01 + sext16(q1) * w10 + sext16(n1) * w11 + (1 << 13)) >> 14;
                     int iy = (((int)q0 >> 16) * w00 + ((int)n0 >> 16) * w01 + ((int)q1 >> 16) * w10 + ((int)n1 >> 16) * w11 + (1 << 13)) >> 14;
-                    if (run && !two) { ix = 0; iy = 0; }
+                    if (run && !R.two) { ix = 0; iy = 0; }
                     tC[run * 7 + k] = 256 - ((v[k] >> 9) << 9);
                     tIx[run * 7 + k] = ix;
                     tIy[run * 7 + k] = iy;
@@ -545,7 +559,9 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                 }
             }
         }
-        if (staged) { u8_commit<kJPatch>(lj, JB, Lp, Lw, Lh, sx0, sy0, jp, lane, dr3, g3); offJ = lj.off; }
+        __syncwarp();                            // every lane is done with the I / dI patches ...
+        prefetch_src(P, plane_a, level - 1, px, py, ip, dxp, R);   // ... so the next level's copies may overwrite them
+        cp_async_wait<1>();                      // the target patch (the older group) has landed
         __syncwarp();
         const long long s11 = warp_sum_i32(a11[0] + a11[1]), s12 = warp_sum_i32(a12[0] + a12[1]), s22 = warp_sum_i32(a22[0] + a22[1]);
         float A11, A12, A22, Dinv;
@@ -566,11 +582,10 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             const int jt = (w00 & 0xffff) | (w01 << 16), jb = (w10 & 0xffff) | (w11 << 16);
             if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
                 sx0 = patch_origin(inx, Lw); sy0 = patch_origin(iny, Lh);
-                U8Loads lj;
                 __syncwarp();
-                u8_issue<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, lane, dr3, g3, lj);
-                u8_commit<kJPatch>(lj, JB, Lp, Lw, Lh, sx0, sy0, jp, lane, dr3, g3);
-                offJ = lj.off;
+                offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, jp, R);
+                cp_async_commit();
+                cp_async_wait<0>();
                 __syncwarp();
                 staged = true;
             }
@@ -579,7 +594,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
 #pragma unroll
             for (int run = 0; run < 2; ++run) {
                 int v[7];
-                bilinear_run7(jp, by + (run ? row1 : row0), bx + (run ? col1 : col0), jt, jb, &tC[run * 7], v);
+                bilinear_run7(jp, by + (run ? R.row1 : R.row0), bx + (run ? R.col1 : R.col0), jt, jb, &tC[run * 7], v);
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
                     const int diff = v[k] >> 9;
@@ -599,11 +614,10 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             const int jt = (w00 & 0xffff) | (w01 << 16), jb = (w10 & 0xffff) | (w11 << 16);
             if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
                 sx0 = patch_origin(inx, Lw); sy0 = patch_origin(iny, Lh);
-                U8Loads lj;
                 __syncwarp();
-                u8_issue<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, lane, dr3, g3, lj);
-                u8_commit<kJPatch>(lj, JB, Lp, Lw, Lh, sx0, sy0, jp, lane, dr3, g3);
-                offJ = lj.off;
+                offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, jp, R);
+                cp_async_commit();
+                cp_async_wait<0>();
                 __syncwarp();
             }
             const int bx = offJ + (inx - sx0), by = iny - sy0;
@@ -611,8 +625,8 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
 #pragma unroll
             for (int run = 0; run < 2; ++run) {
                 int v[7];
-                bilinear_run7(jp, by + (run ? row1 : row0), bx + (run ? col1 : col0), jt, jb, &tC[run * 7], v);
-                if (run == 0 || two) {
+                bilinear_run7(jp, by + (run ? R.row1 : R.row0), bx + (run ? R.col1 : R.col0), jt, jb, &tC[run * 7], v);
+                if (run == 0 || R.two) {
 #pragma unroll
                     for (int k = 0; k < 7; ++k) {
                         const int diff = v[k] >> 9;
@@ -624,37 +638,62 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             er = __fdiv_rn(__ll2float_rn(se), (float)(32 * kW * kW));
         }
     }
+    cp_async_wait<0>();
+    __syncwarp();                                // the patches are free for the next solve
     o.x = next_x; o.y = next_y; o.st = st; o.err = st ? er : 0.f;
 }
 
+// Persistent warps: every warp draws point indices from a device counter until the batch is exhausted, so a slow point
+// (many iterations, re-staging) never holds three idle warps of its CTA and the last wave has no tail of empty slots.
+// The last warp to finish resets the two counters, which keeps launches on one context self-contained.
 __global__ void __launch_bounds__(kWarpsPerCta * 32, PSNW_LK_MINB)
 lk_w21_kernel(const __grid_constant__ LkParams P)
 {
     __shared__ __align__(16) uint32_t smem[kWarpsPerCta * kWarpSmemWords];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int i = blockIdx.x * kWarpsPerCta + wib;
-    if (i >= P.n_pts) return;
     uint32_t *ip = smem + wib * kWarpSmemWords, *jp = ip + kIWords, *dxp = jp + kJWords;
 
-    const TrackJob &job = P.jobs[find_job(P.jobs, P.n_jobs, i)];
-    const int k = i - job.pt_begin;
-    const int t = job.target_of_pt ? job.target_of_pt[k] : 0;
-    const TrackGroup g = P.groups[job.group_base + min(max(t, 0), job.n_targets - 1)];
-    const float2 p0 = job.pts[k];
-
-    // forward pass, then (fused forward-backward check) the same solver from the tracked position back into the
-    // source frame; one copy of the solver code keeps the kernel inside the instruction cache
-    Solve f, b, cur;
-    f.x = f.y = f.err = 0.f; f.st = 1;
-    b = f;
-    const int npass = P.do_fb ? 2 : 1;
-#pragma unroll 1
-    for (int pass = 0; pass < npass; ++pass) {
-        const float sx = pass ? f.x : p0.x, sy = pass ? f.y : p0.y;
-        solve_w21(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, lane, cur);
-        if (pass) b = cur; else f = cur;
+    WarpRole R;
+    R.lane = lane;
+    R.two = lane < 31;
+    {
+        const int r0 = lane, r1 = R.two ? lane + 32 : 62;
+        R.row0 = r0 / 3; R.col0 = 7 * (r0 - 3 * R.row0);
+        R.row1 = r1 / 3; R.col1 = 7 * (r1 - 3 * R.row1);
+        R.dr3 = R.row0; R.g3 = lane - 3 * R.row0;
+        R.dr7 = lane / 7; R.g7 = lane - 7 * R.dr7;
     }
-    finish_point(P, job, k, p0, f, b, lane);
+
+    for (;;) {
+        int i = 0;
+        if (lane == 0) i = (int)atomicAdd(P.work, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= P.n_pts) break;
+
+        const TrackJob &job = P.jobs[find_job(P.jobs, P.n_jobs, i)];
+        const int k = i - job.pt_begin;
+        const int t = job.target_of_pt ? job.target_of_pt[k] : 0;
+        const TrackGroup g = P.groups[job.group_base + min(max(t, 0), job.n_targets - 1)];
+        const float2 p0 = job.pts[k];
+
+        // forward pass, then (fused forward-backward check) the same solver from the tracked position back into the
+        // source frame; one copy of the solver code keeps the kernel inside the instruction cache
+        Solve f, b, cur;
+        f.x = f.y = f.err = 0.f; f.st = 1;
+        b = f;
+        const int npass = P.do_fb ? 2 : 1;
+#pragma unroll 1
+        for (int pass = 0; pass < npass; ++pass) {
+            const float sx = pass ? f.x : p0.x, sy = pass ? f.y : p0.y;
+            solve_w21(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, R, cur);
+            if (pass) b = cur; else f = cur;
+        }
+        finish_point(P, job, k, p0, f, b, lane);
+    }
+    if (lane == 0) {
+        const unsigned total = gridDim.x * kWarpsPerCta;
+        if (atomicAdd(P.work + 1, 1u) + 1 == total) { P.work[0] = 0; P.work[1] = 0; }
+    }
 }
 
 }  // namespace
@@ -664,11 +703,21 @@ int configure_lk_kernels()
     return cudaFuncSetAttribute(lk_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess ? 0 : -1;
 }
 
-int launch_lk(const LkParams &P, int all_21x21, int max_win_px, cudaStream_t stream)
+// CTAs of the persistent 21x21 kernel that are resident at once on the current device (SM count x occupancy)
+int lk_w21_resident_ctas()
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk_w21_kernel, kWarpsPerCta * 32, 0) != cudaSuccess)
+        return -1;
+    return sms * per_sm;
+}
+
+int launch_lk(const LkParams &P, int all_21x21, int max_win_px, int resident_ctas, cudaStream_t stream)
 {
     if (P.n_pts <= 0) return 0;
     if (all_21x21) {
-        const int grid = (P.n_pts + kWarpsPerCta - 1) / kWarpsPerCta;
+        const int grid = min((P.n_pts + kWarpsPerCta - 1) / kWarpsPerCta, max(resident_ctas, 1));
         lk_w21_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(P);
     } else {
         const int stride = (max_win_px + 7) & ~7;
