@@ -221,6 +221,10 @@ PSNW_API void *psnw_get_stream(psnw_ctx *ctx);
 PSNW_API int psnw_level_info(psnw_ctx *ctx, int level, int *w, int *h, int *pitch);
 /* Copies one level of (cam, slot) to host: img_out[h][w] u8 and/or dxy_out[h][w][2] int16 (NULL to skip). */
 PSNW_API int psnw_read_level(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *img_out, int16_t *dxy_out);
+/* Levels >= 1 are kept in HBM with a REFLECT_101 apron (the border cv::calcOpticalFlowPyrLK builds around every pyramid
+ * level with copyMakeBorder): *apron receives its width in pixels (0 for a level stored bare) and, when `out` is not NULL,
+ * out[h + 2a][w + 2a] the image including the apron. */
+PSNW_API int psnw_read_level_apron(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *out, int *apron);
 /* Copies the Shi-Tomasi min-eigenvalue map of (cam, slot) level 0 to host float[h][w] (computes it if needed). */
 PSNW_API int psnw_read_min_eig(psnw_ctx *ctx, int cam, int slot, float *eig_out);
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */

@@ -39,6 +39,7 @@ struct psnw_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool aux_pending = false;
     PyrDesc pyr;
+    uint8_t *img_alloc[PSNW_MAX_LEVELS] = {};   // allocation behind pyr.lv[l].img (which points at pixel (0,0) of plane 0)
     CUtensorMap maps[PSNW_MAX_LEVELS];
     CUtensorMap map_fused;                // level-0 map with the box of the fused multi-level kernel
     int fused_levels = 0;                 // 3 or 4 when the fused kernel is usable, else 0
@@ -148,7 +149,7 @@ int make_tensor_maps(psnw_ctx *ctx)
     for (int l = 0; l < ctx->pyr.levels; ++l) {
         const LevelGeom &g = ctx->pyr.lv[l];
         const cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)ctx->planes};
-        const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.plane_px};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.ipitch, (cuuint64_t)g.iplane_px};
         const cuuint32_t box[3] = {(cuuint32_t)kBoxW, (cuuint32_t)kBoxH, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
         const CUresult r = encode(&ctx->maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box, estr,
@@ -166,7 +167,7 @@ int make_tensor_maps(psnw_ctx *ctx)
         fused_box(ctx->fused_levels, &bw, &bh);
         const LevelGeom &g = ctx->pyr.lv[0];
         const cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)ctx->planes};
-        const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)g.plane_px};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.ipitch, (cuuint64_t)g.iplane_px};
         const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
         const CUresult r = encode(&ctx->map_fused, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box, estr,
@@ -239,8 +240,20 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes)
             ctx->launches += r;
             first = ctx->fused_levels < ctx->pyr.levels ? ctx->fused_levels - 1 : ctx->pyr.levels;   // level 3 again to feed level 4
         }
+        // Aprons (REFLECT_101 border of the levels >= 1, read by the LK kernel): a per-level launch writes the apron of its
+        // own input level with extra CTAs; the levels only the fused kernel produced get one apron launch.  When level
+        // `first` is re-run only to feed the next level (5-level pyramids) it carries its apron as well.
+        if (fused && first >= ctx->pyr.levels) {
+            const int r = launch_apron(ctx->pyr, 1, ctx->pyr.levels - 1, pl, ctx->stream);
+            if (r < 0) return fail(ctx, PSNW_ECUDA, "apron_kernel launch", cudaGetLastError());
+            ctx->launches += r;
+        } else if (fused && first > 1) {
+            const int r = launch_apron(ctx->pyr, 1, first - 1, pl, ctx->stream);
+            if (r < 0) return fail(ctx, PSNW_ECUDA, "apron_kernel launch", cudaGetLastError());
+            ctx->launches += r;
+        }
         for (int l = first; l < ctx->pyr.levels; ++l) {
-            const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, ctx->stream);
+            const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, 1, ctx->stream);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_scharr_kernel launch", cudaGetLastError());
             ctx->launches += r;
         }
@@ -347,12 +360,18 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
         g.w = w; g.h = h;
         g.pitch = (w + 127) & ~127;
         g.plane_px = g.pitch * h;
-        const size_t px = (size_t)g.plane_px * ctx->planes;
-        if (cudaMalloc(&g.img, px) != cudaSuccess || cudaMalloc(&g.dxy, px * sizeof(short2)) != cudaSuccess) {
+        // level 0 is stored bare (one linear upload per frame); levels >= 1 with a REFLECT_101 apron (common.cuh)
+        g.apron = l > 0 ? 1 : 0;
+        g.ipitch = g.apron ? (kApronL + w + kApronR + 63) & ~63 : g.pitch;
+        g.iplane_px = g.apron ? g.ipitch * (h + 2 * kApron) : g.plane_px;
+        const size_t front = g.apron ? (size_t)kApron * g.ipitch + kApronL : 0;
+        const size_t px = (size_t)g.plane_px * ctx->planes, ipx = (size_t)g.iplane_px * ctx->planes;
+        if (cudaMalloc(&ctx->img_alloc[l], ipx) != cudaSuccess || cudaMalloc(&g.dxy, px * sizeof(short2)) != cudaSuccess) {
             *out = nullptr;
             return bail(PSNW_ENOMEM);
         }
-        cudaMemsetAsync(g.img, 0, px, ctx->stream);
+        g.img = ctx->img_alloc[l] + front;
+        cudaMemsetAsync(ctx->img_alloc[l], 0, ipx, ctx->stream);
         cudaMemsetAsync(g.dxy, 0, px * sizeof(short2), ctx->stream);
         ++levels;
     }
@@ -381,7 +400,7 @@ int psnw_destroy(psnw_ctx *ctx)
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     if (ctx->det_desc.p) cudaFree(ctx->det_desc.p);
     for (int l = 0; l < PSNW_MAX_LEVELS; ++l) {
-        if (ctx->pyr.lv[l].img) cudaFree(ctx->pyr.lv[l].img);
+        if (ctx->img_alloc[l]) cudaFree(ctx->img_alloc[l]);
         if (ctx->pyr.lv[l].dxy) cudaFree(ctx->pyr.lv[l].dxy);
     }
     for (float *e : ctx->eig) if (e) cudaFree(e);
@@ -972,8 +991,23 @@ int psnw_read_level(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *img_ou
     const LevelGeom &g = ctx->pyr.lv[level];
     const int plane = plane_of(ctx, cam, slot);
     CK(cudaStreamSynchronize(ctx->stream));
-    if (img_out) CK(cudaMemcpy2D(img_out, g.w, g.img + (size_t)plane * g.plane_px, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+    if (img_out) CK(cudaMemcpy2D(img_out, g.w, g.img + (size_t)plane * g.iplane_px, g.ipitch, g.w, g.h, cudaMemcpyDeviceToHost));
     if (dxy_out) CK(cudaMemcpy2D(dxy_out, (size_t)g.w * 4, g.dxy + (size_t)plane * g.plane_px, (size_t)g.pitch * 4, (size_t)g.w * 4, g.h, cudaMemcpyDeviceToHost));
+    return PSNW_OK;
+}
+
+int psnw_read_level_apron(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *out, int *apron)
+{
+    if (!ctx || level < 0 || level >= ctx->pyr.levels) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
+    if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_read_level_apron: camera/slot holds no frame");
+    const LevelGeom &g = ctx->pyr.lv[level];
+    const int a = g.apron ? kApron : 0;
+    if (apron) *apron = a;
+    if (!out) return PSNW_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint8_t *src = g.img + (size_t)plane_of(ctx, cam, slot) * g.iplane_px - (ptrdiff_t)a * g.ipitch - a;
+    CK(cudaMemcpy2D(out, g.w + 2 * a, src, g.ipitch, g.w + 2 * a, g.h + 2 * a, cudaMemcpyDeviceToHost));
     return PSNW_OK;
 }
 

@@ -11,11 +11,22 @@ namespace psnw {
 // One pyramid level of the whole context: planes are [camera][ring slot], row pitch in u8 bytes ==
 // row pitch of the derivative image in short2 elements.
 struct LevelGeom {
-    uint8_t *img;      // [planes][h][pitch] u8
+    uint8_t *img;      // pixel (0,0) of plane 0; plane p, pixel (x,y) at img[p * iplane_px + y * ipitch + x]
     short2 *dxy;       // [planes][h][pitch] (dx,dy) int16, Scharr x32 (calcSharrDeriv layout)
-    int w, h, pitch;
+    int w, h, pitch;   // pitch: derivative row pitch in short2 elements (also the pitch of per-camera level-0 maps)
     int plane_px;      // h * pitch
+    int ipitch;        // image row pitch in bytes
+    int iplane_px;     // image plane stride in bytes
+    int apron;         // 1: a REFLECT_101 apron of kApron pixels surrounds every image plane in HBM (levels >= 1)
+    int pad_;
 };
+
+// Levels >= 1 are stored with a physical REFLECT_101 apron (written by the pyramid kernels together with the pixels they
+// mirror), so the 21x21 LK kernel stages every coarse-level patch with aligned 16-byte copies and no border arithmetic.
+// kApron pixels are mirrored on each side; kApronL / kApronR are the physical left / right margins of a row (the left one
+// keeps pixel (0,0) 16-byte aligned, the right one covers the round-up of a staged row to 16 bytes).  Level 0 is stored
+// bare: frames are uploaded into it with one linear copy.
+constexpr int kApron = 26, kApronL = 32, kApronR = 48;
 
 struct PyrDesc {
     LevelGeom lv[PSNW_MAX_LEVELS];
@@ -67,8 +78,11 @@ int configure_box_kernels();
 int configure_detect_kernels();
 
 // --- launchers (each returns the number of kernels it enqueued, or -1 with cudaGetLastError set) ---
-int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes,
+// with_apron: the launch also writes the REFLECT_101 apron of its input level (levels >= 1) with extra CTAs
+int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron,
                      cudaStream_t stream);
+// REFLECT_101 apron of levels first..last (clamped to >= 1) of the listed planes in one launch (after the fused kernel)
+int launch_apron(const PyrDesc &pyr, int first_level, int last_level, const PlaneList &planes, cudaStream_t stream);
 // fused multi-level variant (pyramid_fused.cu): levels 0..nl-1 in one launch; fused_box = TMA box of its level-0 map
 void fused_box(int nl, int *box_w, int *box_h);
 int configure_fused_kernels();

@@ -151,9 +151,10 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
 
     for (int level = max_level; level >= 0; --level) {
         const LevelGeom &L = P.lv[level];
-        const uint8_t *IA = L.img + (size_t)plane_a * L.plane_px;
+        const uint8_t *IA = L.img + (size_t)plane_a * L.iplane_px;
         const short2 *DA = L.dxy + (size_t)plane_a * L.plane_px;
-        const uint8_t *JB = L.img + (size_t)plane_b * L.plane_px;
+        const uint8_t *JB = L.img + (size_t)plane_b * L.iplane_px;
+        const int ipitch = L.ipitch;
         const float sc = __int_as_float((127 - level) << 23);
         float prev_x = __fmul_rn(px, sc), prev_y = __fmul_rn(py, sc);
         float nx, ny;
@@ -175,7 +176,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             int x = lx0, y = ly0;
             for (int p = tid; p < npx; p += kGenThreads) {
                 const int X = ipx + x, Y = ipy + y;
-                const int ival = sample_u8(IA, L.pitch, L.w, L.h, X, Y, w00, w01, w10, w11);
+                const int ival = sample_u8(IA, ipitch, L.w, L.h, X, Y, w00, w01, w10, w11);
                 const bool xi0 = (unsigned)X < (unsigned)L.w, xi1 = (unsigned)(X + 1) < (unsigned)L.w;
                 const bool yi0 = (unsigned)Y < (unsigned)L.h, yi1 = (unsigned)(Y + 1) < (unsigned)L.h;
                 const short2 z = make_short2(0, 0);
@@ -213,7 +214,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 // window inside the frame and <= 60 pixels per thread: no border arithmetic, 32-bit partial sums
                 int a1 = 0, a2 = 0;
                 for (int p = tid; p < npx; p += kGenThreads) {
-                    const uint8_t *r0 = JB + (iny + y) * L.pitch + (inx + x), *r1 = r0 + L.pitch;
+                    const uint8_t *r0 = JB + (iny + y) * ipitch + (inx + x), *r1 = r0 + ipitch;
                     const int diff = ((r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9) - Iw[p];
                     const short2 d = dIw[p];
                     a1 += diff * d.x; a2 += diff * d.y;
@@ -223,7 +224,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 sb1 = a1; sb2 = a2;
             } else {
                 for (int p = tid; p < npx; p += kGenThreads) {
-                    const int diff = sample_u8(JB, L.pitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
+                    const int diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
                     const short2 d = dIw[p];
                     sb1 += (long long)(diff * d.x); sb2 += (long long)(diff * d.y);
                     x += kGenThreads;
@@ -242,7 +243,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             long long se = 0;
             int x = lx0, y = ly0;
             for (int p = tid; p < npx; p += kGenThreads) {
-                const int diff = sample_u8(JB, L.pitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
+                const int diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
                 se += diff < 0 ? -diff : diff;
                 x += kGenThreads;
                 while (x >= ww) { x -= ww; y++; }
@@ -378,15 +379,16 @@ struct WarpRole {
 // (3 lanes per row, 10 rows per instruction; the caller commits and waits); patches touching the border gather bytes
 // row by row through REFLECT_101, the apron OpenCV keeps around every level (plain stores, visible after __syncwarp).
 template <int N>
-__device__ __forceinline__ int stage_u8(const uint8_t *__restrict__ img, int pitch, int w, int h, int x0, int y0,
+__device__ __forceinline__ int stage_u8(const uint8_t *__restrict__ img, int pitch, int w, int h, bool apron, int x0, int y0,
                                         uint32_t *patch, const WarpRole &R)
 {
-    const bool fast = x0 >= 0 && y0 >= 0 && x0 + N <= w && y0 + N <= h;
+    // levels >= 1 carry a physical REFLECT_101 apron (common.cuh): every admissible patch is a plain aligned copy
+    const bool fast = apron || (x0 >= 0 && y0 >= 0 && x0 + N <= w && y0 + N <= h);
     if (fast) {
         const int off = x0 & 15;
         const int ng = (off + N + 15) >> 4;               // 16-byte groups per row: 2 or 3
         if (R.lane < 30 && R.g3 < ng) {
-            const uint8_t *src = img + (size_t)(y0 + R.dr3) * pitch + (x0 - off) + 16 * R.g3;
+            const uint8_t *src = img + (ptrdiff_t)(y0 + R.dr3) * pitch + (x0 - off) + 16 * R.g3;
             const uint32_t dst = smem_u32(patch + R.dr3 * kU8Pitch + 4 * R.g3);
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -482,7 +484,7 @@ __device__ __forceinline__ void prefetch_src(const LkParams &P, int plane_a, int
         float sx, sy;
         int ix, iy;
         if (src_origin(px, py, level, L.w, L.h, sx, sy, ix, iy)) {
-            stage_u8<kPatch>(L.img + (size_t)plane_a * L.plane_px, L.pitch, L.w, L.h, ix, iy, ip, R);
+            stage_u8<kPatch>(L.img + (size_t)plane_a * L.iplane_px, L.ipitch, L.w, L.h, L.apron != 0, ix, iy, ip, R);
             stage_dxy(L.dxy + (size_t)plane_a * L.plane_px, L.pitch, L.h, ix, iy, dxp, R);
         }
     }
@@ -500,8 +502,9 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
 #pragma unroll 1
     for (int level = max_level; level >= 0; --level) {
         const LevelGeom &L = P.lv[level];
-        const int Lw = L.w, Lh = L.h, Lp = L.pitch;
-        const uint8_t *JB = L.img + (size_t)plane_b * L.plane_px;
+        const int Lw = L.w, Lh = L.h, Lp = L.ipitch;
+        const bool apron = L.apron != 0;
+        const uint8_t *JB = L.img + (size_t)plane_b * L.iplane_px;
         cp_async_wait<0>();                      // this level's I / dI patches (and every older copy) have landed
         __syncwarp();
 
@@ -519,7 +522,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
         prev_x = __fsub_rn(prev_x, half); prev_y = __fsub_rn(prev_y, half);
         int w00, w01, w10, w11;
         bilinear_weights(__fsub_rn(prev_x, (float)ipx), __fsub_rn(prev_y, (float)ipy), w00, w01, w10, w11);
-        const bool fastI = ipx >= 0 && ipy >= 0 && ipx + kPatch <= Lw && ipy + kPatch <= Lh;
+        const bool fastI = apron || (ipx >= 0 && ipy >= 0 && ipx + kPatch <= Lw && ipy + kPatch <= Lh);
         const int offI = fastI ? (ipx & 15) : 0, offD = ipx & 3;
 
         // ---- target patch around the first position: in flight while the template is computed ----
@@ -528,7 +531,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
         bool staged = !window_oob(__float2int_rd(nx), __float2int_rd(ny), Lw, Lh);
         if (staged) {
             sx0 = patch_origin(__float2int_rd(nx), Lw); sy0 = patch_origin(__float2int_rd(ny), Lh);
-            offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, jp, R);
+            offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, apron, sx0, sy0, jp, R);
         }
         cp_async_commit();
 
@@ -583,7 +586,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
                 sx0 = patch_origin(inx, Lw); sy0 = patch_origin(iny, Lh);
                 __syncwarp();
-                offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, jp, R);
+                offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, apron, sx0, sy0, jp, R);
                 cp_async_commit();
                 cp_async_wait<0>();
                 __syncwarp();
@@ -615,7 +618,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
                 sx0 = patch_origin(inx, Lw); sy0 = patch_origin(iny, Lh);
                 __syncwarp();
-                offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, sx0, sy0, jp, R);
+                offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, apron, sx0, sy0, jp, R);
                 cp_async_commit();
                 cp_async_wait<0>();
                 __syncwarp();

@@ -25,11 +25,118 @@ constexpr int kRowWords = kBoxW / 4;   // 40
 constexpr int kLaneWord0 = kHaloL / 4 - 1;   // word holding columns x-4..x-1 of lane 0
 constexpr int kRowsPerWarp = 8;
 
+// REFLECT_101 apron of the levels >= 1 (common.cuh): what copyMakeBorder builds around every pyramid level inside
+// cv::calcOpticalFlowPyrLK, written once per pushed frame so that the LK kernel stages coarse-level patches without border
+// arithmetic.  A thread writes one aligned 4-byte word of the apron: kApron rows above and below the image over the padded
+// width, and kApronCols columns left and right of every image row; sources are the level's own pixels (L2-resident).
+// The work is cut into regions of one CTA each (apron_regions): with one launch per level the regions of level l ride as
+// extra CTAs in that level's own pyr_scharr_kernel launch (level l is complete by then and nothing in the launch writes
+// it), so the apron costs neither a launch nor a serial tail; after the fused multi-level kernel one apron_kernel launch
+// covers every level >= 1 of every plane (grid.y = level - 1, grid.z = plane).
+constexpr int kApronThreads = 128;
+constexpr int kApronCols = 28;          // kApron rounded up to whole words
+
+struct ApronLevels {
+    LevelGeom lv[PSNW_MAX_LEVELS];
+    int n;
+};
+
+constexpr int kSideL = kApronCols / 4;      // words written left of every image row
+constexpr int kSideR = kSideL + 1;          // ... and right of it, starting at the word that holds column w (w & ~3)
+
+__device__ __forceinline__ int reflect101(int p, int n)
+{
+    p = p < 0 ? -p : p;
+    p = p >= n ? 2 * (n - 1) - p : p;
+    return min(max(p, 0), n - 1);          // only positions beyond a single reflection (never sampled) are clamped
+}
+
+// the word of four REFLECT_101 sources of pixels (tx .. tx+3, ty).  The source columns are contiguous (ascending inside
+// the image, descending where mirrored) unless the word straddles a fold: then two aligned word loads, a funnel shift and
+// a byte reversal replace four byte loads.
+__device__ __forceinline__ uint32_t apron_word_load(const uint8_t *plane0, int pitch, int W, int H, int tx, int ty)
+{
+    const uint8_t *srow = plane0 + (ptrdiff_t)reflect101(ty, H) * pitch;
+    const int c0 = reflect101(tx, W), c3 = reflect101(tx + 3, W);
+    uint32_t v = 0;
+    if (c3 - c0 == 3 || c0 - c3 == 3) {
+        const int lo = min(c0, c3);
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(srow + (lo & ~3));
+        const uint32_t a = __ldcg(wp), b = (lo & 3) ? __ldcg(wp + 1) : 0u;
+        v = __funnelshift_r(a, b, 8 * (lo & 3));
+        if (c0 > c3) v = __byte_perm(v, 0u, 0x0123);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v |= (uint32_t)__ldcg(srow + reflect101(tx + k, W)) << (8 * k);
+    }
+    return v;
+}
+
+// CTAs needed for the apron of a level with h rows: groups of kApronRep rows above / below the image, then bands of
+// kApronRep * nthreads / 16 image rows (kApronRep words per thread keep the CTAs few and not launch-rate bound)
+constexpr int kApronRep = 1;
+__host__ __device__ inline int apron_regions(int h, int nthreads)
+{
+    const int band = kApronRep * (nthreads / 16);
+    return (2 * kApron + kApronRep - 1) / kApronRep + (h + band - 1) / band;
+}
+
+// region < ceil(2 kApron / kApronRep): kApronRep apron rows above / below the image over the padded width (threads stride
+// over the words of a row); else a band of image rows, 16 word slots per row = kSideL words left of the row and kSideR
+// right of it (a word that straddles column w rewrites the image pixels it holds with their own values).
+__device__ __forceinline__ void apron_region(const LevelGeom &L, int plane, int region, int tid, int nthreads)
+{
+    const int W = L.w, H = L.h, pitch = L.ipitch;
+    uint8_t *plane0 = L.img + (size_t)plane * L.iplane_px;
+    constexpr int n_tb = (2 * kApron + kApronRep - 1) / kApronRep;
+    if (region < n_tb) {
+        const int row_words = (W + 3) / 4 + 2 * kSideL;
+        for (int r = region * kApronRep; r < min((region + 1) * kApronRep, 2 * kApron); ++r) {
+            const int ty = r < kApron ? r - kApron : H + (r - kApron);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(plane0 + (ptrdiff_t)ty * pitch - kApronCols);
+            for (int i = tid; i < row_words; i += nthreads) dst[i] = apron_word_load(plane0, pitch, W, H, 4 * i - kApronCols, ty);
+        }
+    } else {
+        const int c = tid & 15;
+        if (c >= kSideL + kSideR) return;
+        const int tx = c < kSideL ? 4 * c - kApronCols : (W & ~3) + 4 * (c - kSideL);
+        const int y0 = (region - n_tb) * kApronRep * (nthreads / 16) + (tid >> 4);
+        uint32_t v[kApronRep];
+#pragma unroll
+        for (int k = 0; k < kApronRep; ++k) {              // loads first: one round trip to L2
+            const int ty = y0 + k * (nthreads / 16);
+            if (ty < H) v[k] = apron_word_load(plane0, pitch, W, H, tx, ty);
+        }
+#pragma unroll
+        for (int k = 0; k < kApronRep; ++k) {
+            const int ty = y0 + k * (nthreads / 16);
+            if (ty < H) *reinterpret_cast<uint32_t *>(plane0 + (ptrdiff_t)ty * pitch + tx) = v[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kApronThreads)
+apron_kernel(const ApronLevels A, const PlaneList planes)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");     // the pyramid launch before this one has completed
+    const LevelGeom &L = A.lv[blockIdx.y];
+    if ((int)blockIdx.x < apron_regions(L.h, kApronThreads))
+        apron_region(L, planes.plane[blockIdx.z], blockIdx.x, threadIdx.x, kApronThreads);
+}
+
 template <bool kHasNext>
 __global__ void __launch_bounds__(128)
 pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, const LevelGeom nxt,
-                  const PlaneList planes)
+                  const PlaneList planes, const int tiles_y)
 {
+    if ((int)blockIdx.y >= tiles_y) {
+        // extra CTAs of a level >= 1: the REFLECT_101 apron of this (input) level, complete since the previous launch
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int region = ((int)blockIdx.y - tiles_y) * (int)gridDim.x + (int)blockIdx.x;
+        if (region < apron_regions(cur.h, 128)) apron_region(cur, planes.plane[blockIdx.z], region, threadIdx.x, 128);
+        return;
+    }
     __shared__ __align__(128) uint32_t tile[kBoxH * kRowWords];
     __shared__ __align__(8) uint64_t bar;
 
@@ -56,7 +163,7 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
         const int r = i / kBoxW, c = i - r * kBoxW;
         const int gx = x0 - kHaloL + c, gy = y0 - kHaloT + r;
         uint8_t v = 0;
-        if (gx >= 0 && gy >= 0 && gx < cur.w && gy < cur.h) v = cur.img[(size_t)plane * cur.plane_px + (size_t)gy * cur.pitch + gx];
+        if (gx >= 0 && gy >= 0 && gx < cur.w && gy < cur.h) v = cur.img[(size_t)plane * cur.iplane_px + (size_t)gy * cur.ipitch + gx];
         reinterpret_cast<uint8_t *>(tile)[i] = v;
     }
     __syncthreads();
@@ -144,9 +251,12 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
                 v[i] = (pg[(rr - 4) % 5][i] + pg[rr % 5][i]) + 4 * (pg[(rr - 3) % 5][i] + pg[(rr - 1) % 5][i]) +
                        6 * pg[(rr - 2) % 5][i];
             const int ox = (x0 >> 1) + 2 * lane;
-            if (j < nxt.h && ox < nxt.pitch) {
-                const uint16_t pk = (uint16_t)(((v[0] + 128) >> 8) | (((v[1] + 128) >> 8) << 8));
-                *reinterpret_cast<uint16_t *>(nxt.img + (size_t)plane * nxt.plane_px + (size_t)j * nxt.pitch + ox) = pk;
+            if (j < nxt.h && ox < nxt.w) {
+                const int p0 = (v[0] + 128) >> 8, p1 = (v[1] + 128) >> 8;
+                uint8_t *g = nxt.img + (size_t)plane * nxt.iplane_px + (size_t)j * nxt.ipitch + ox;
+                const bool two = ox + 1 < nxt.w;
+                if (two) *reinterpret_cast<uint16_t *>(g) = (uint16_t)(p0 | (p1 << 8));
+                else     g[0] = (uint8_t)p0;
             }
         }
     }
@@ -177,14 +287,16 @@ bgr2gray_kernel(const uint8_t *__restrict__ bgr, size_t bgr_pitch, uint8_t *__re
 
 }  // namespace
 
-int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes,
+int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron,
                      cudaStream_t stream)
 {
     const LevelGeom &cur = pyr.lv[level];
     const bool has_next = level + 1 < pyr.levels;
     const LevelGeom &nxt = pyr.lv[has_next ? level + 1 : level];
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((cur.w + kTileW - 1) / kTileW, (cur.h + kTileH - 1) / kTileH, planes.n);
+    const int tiles_x = (cur.w + kTileW - 1) / kTileW, tiles_y = (cur.h + kTileH - 1) / kTileH;
+    const int apron_y = (cur.apron && with_apron) ? (apron_regions(cur.h, 128) + tiles_x - 1) / tiles_x : 0;   // extra grid rows
+    cfg.gridDim = dim3(tiles_x, tiles_y + apron_y, planes.n);
     cfg.blockDim = dim3(128);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
@@ -193,9 +305,32 @@ int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, c
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = has_next ? cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<true>, *map_in, cur, nxt, planes)
-                                   : cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<false>, *map_in, cur, nxt, planes);
+    const cudaError_t e = has_next ? cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<true>, *map_in, cur, nxt, planes, tiles_y)
+                                   : cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<false>, *map_in, cur, nxt, planes, tiles_y);
     return e == cudaSuccess ? 1 : -1;
+}
+
+int launch_apron(const PyrDesc &pyr, int first_level, int last_level, const PlaneList &planes, cudaStream_t stream)
+{
+    first_level = max(first_level, 1);
+    if (last_level < first_level) return 0;
+    ApronLevels A;
+    A.n = last_level - first_level + 1;
+    int regions = 0;
+    for (int l = first_level; l <= last_level; ++l) {
+        A.lv[l - first_level] = pyr.lv[l];
+        regions = max(regions, apron_regions(pyr.lv[l].h, kApronThreads));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(regions, A.n, planes.n);
+    cfg.blockDim = dim3(kApronThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL: launch latency hides under the previous kernel's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, apron_kernel, A, planes) == cudaSuccess ? 1 : -1;
 }
 
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,

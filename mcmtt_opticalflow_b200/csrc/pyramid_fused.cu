@@ -171,7 +171,7 @@ __device__ __forceinline__ void fused_level(uint8_t *smem, const FusedLevels &L,
                         if (a0) d[0] = (uint8_t)v[0];
                         if (a1) d[1] = (uint8_t)v[1];
                         if (Y >= oy1 && Y < oy1 + h1 && X >= ox1 && X < ox1 + w1) {          // own part of level K+1 -> HBM
-                            uint8_t *g = nx.img + (size_t)plane * nx.plane_px + (size_t)Y * nx.pitch + X;
+                            uint8_t *g = nx.img + (size_t)plane * nx.iplane_px + (size_t)Y * nx.ipitch + X;
                             if (a0 && a1) *reinterpret_cast<uint16_t *>(g) = (uint16_t)(v[0] | (v[1] << 8));
                             else if (a0) g[0] = (uint8_t)v[0];
                         }

@@ -55,6 +55,7 @@ EXPORTS = [
     "psnw_klt_detect_batch", "psnw_join", "psnw_gridfast_detect", "psnw_read_fast_map", "psnw_points_in_boxes", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
     "psnw_push_frames_bgr", "psnw_frames_held", "psnw_klt_detect", "psnw_klt_track", "psnw_klt_track_batch",
     "psnw_box_update", "psnw_sync", "psnw_last_error", "psnw_get_stream", "psnw_level_info", "psnw_read_level",
+    "psnw_read_level_apron",
     "psnw_read_min_eig", "psnw_launch_count", "psnw_push_frame_bytes", "psnw_rebuild_pyramids", "psnw_levels_built",
 ]
 
@@ -102,6 +103,8 @@ def load():
                                         C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_level_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.psnw_read_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        if hasattr(lib, "psnw_read_level_apron"):       # absent only from older bring-up builds named by PSNW_KLT_LIB
+            lib.psnw_read_level_apron.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         lib.psnw_read_min_eig.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib = lib
     return _lib
@@ -232,6 +235,15 @@ class KLTContext:
         dxy = np.empty((h, w, 2), np.int16)
         self._ck(self.lib.psnw_read_level(self._h, cam, slot, level, img.ctypes.data, dxy.ctypes.data))
         return img, dxy
+
+    def read_level_apron(self, cam, slot, level):
+        """Image of one level including the REFLECT_101 apron kept in HBM (levels >= 1): (array, apron width)."""
+        a = C.c_int(0)
+        self._ck(self.lib.psnw_read_level_apron(self._h, cam, slot, level, None, C.byref(a)))
+        w, h, _ = self.level_info(level)
+        out = np.empty((h + 2 * a.value, w + 2 * a.value), np.uint8)
+        self._ck(self.lib.psnw_read_level_apron(self._h, cam, slot, level, out.ctypes.data, C.byref(a)))
+        return out, a.value
 
     def read_min_eig(self, cam=0, slot=0):
         out = np.empty((self.height, self.width), np.float32)

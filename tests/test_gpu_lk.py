@@ -108,6 +108,32 @@ def test_c2_shaped_batch_vs_oracle(oracle, fb):
         assert j["status"].mean() > 0.5          # the synthetic texture is trackable
 
 
+@pytest.mark.parametrize("w,h", [(200, 150), (333, 97), (768, 576)])
+def test_border_seeds_all_levels(oracle, w, h):
+    """Seeds hugging every border and corner: the windows cross the frame edge on every pyramid level (REFLECT_101 image
+    apron kept in HBM on levels >= 1, on-the-fly mirror on level 0, zero derivative apron), some leave the frame."""
+    rng = np.random.default_rng(w + h)
+    cam = synth.Camera(w, h, 3, cam=4)
+    f0, f1 = cam.frame(0), cam.frame(1)
+    n = 600
+    t = rng.uniform(0, 1, n)
+    band = rng.uniform(-3.0, 14.0, n)                       # distance from the edge, a few seeds outside the frame
+    side = rng.integers(0, 4, n)
+    x = np.where(side == 0, band, np.where(side == 1, w - 1 - band, t * (w - 1)))
+    y = np.where(side == 2, band, np.where(side == 3, h - 1 - band, t * (h - 1)))
+    corners = np.array([[0.5, 0.5], [w - 1.5, 0.5], [0.5, h - 1.5], [w - 1.5, h - 1.5], [10.0, 10.0], [w - 11.0, h - 11.0]])
+    pts = np.concatenate([np.stack([x, y], 1), corners]).astype(np.float32)
+    with klt.KLTContext(w, h, levels=4, fb_thresh=1.0) as ctx:
+        ctx.push_frame(f0); ctx.push_frame(f1)
+        o, st, er, fb = ctx.track(pts)
+        ml = ctx.levels - 1
+    pa, pb = oracle.build_pyramid(f0, ml), oracle.build_pyramid(f1, ml)
+    g_o, g_st, g_er, g_fb = oracle.track_fb(pa, pb, pts, (21, 21), ml, fb_thresh=1.0, exact_sums=True)
+    _tight(o, st, er, g_o, g_st, g_er, ("border", w, h))
+    assert np.abs(fb - g_fb).max() <= 1e-4
+    assert st.mean() > 0.05
+
+
 def test_reference_faithful_per_target_windows(oracle):
     """Reference call pattern: window (int)box.w x (int)box.h per target (Tracker2D.cpp:877), default 4 levels."""
     w, h, ntgt = 768, 576, 12

@@ -17,6 +17,22 @@ def _check_levels(ctx, oracle, img, cam=0, slot=0):
         assert g_img.shape == cur.shape
         assert np.array_equal(g_img, cur), "u8 level %d differs" % l
         assert np.array_equal(g_dxy, oracle.scharr(cur)), "Scharr level %d differs" % l
+        _check_apron(ctx, cur, cam, slot, l)
+
+
+def _check_apron(ctx, img, cam, slot, level):
+    """Levels >= 1 keep a REFLECT_101 apron in HBM (what copyMakeBorder builds around every level inside
+    calcOpticalFlowPyrLK); every apron pixel a single reflection defines must equal np.pad(mode='reflect')."""
+    pad, a = ctx.read_level_apron(cam, slot, level)
+    h, w = img.shape
+    assert a == (26 if level else 0)
+    assert np.array_equal(pad[a:a + h, a:a + w], img)
+    if not a:
+        return
+    ax, ay = min(a, w - 1), min(a, h - 1)               # reflection depth available on this level
+    want = np.pad(img, ((ay, ay), (ax, ax)), mode="reflect")
+    got = pad[a - ay:a + h + ay, a - ax:a + w + ax]
+    assert np.array_equal(got, want), "apron of level %d differs" % level
 
 
 @pytest.mark.parametrize("mode", ["level", "fused"])

@@ -9,8 +9,10 @@ PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PE
 stream = torch.cuda.Stream()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = []
-for (w, h, levels, ncam) in [(768, 576, 4, 1), (768, 576, 4, 4), (768, 576, 4, 16), (768, 576, 4, 64), (1920, 1080, 4, 1),
-                             (1920, 1080, 4, 8), (1920, 1080, 4, 32), (3840, 2160, 5, 1), (3840, 2160, 5, 4), (3840, 2160, 5, 16)]:
+ONLY = os.environ.get("PYR_SWEEP_ONLY")        # e.g. "768,576,4,64": a single configuration (profiling aid)
+CFGS = [tuple(int(v) for v in ONLY.split(","))] if ONLY else [(768, 576, 4, 1), (768, 576, 4, 4), (768, 576, 4, 16), (768, 576, 4, 64), (1920, 1080, 4, 1),
+                             (1920, 1080, 4, 8), (1920, 1080, 4, 32), (3840, 2160, 5, 1), (3840, 2160, 5, 4), (3840, 2160, 5, 16)]
+for (w, h, levels, ncam) in CFGS:
     ctx = klt.KLTContext(w, h, n_cameras=ncam, levels=levels, ring_slots=1, stream=stream.cuda_stream, max_points=1024, max_targets=64)
     rng = np.random.default_rng(0)
     frames = [rng.integers(0, 256, size=(h, w), dtype=np.uint8) for _ in range(min(ncam, 4))]
@@ -31,6 +33,6 @@ for (w, h, levels, ncam) in [(768, 576, 4, 1), (768, 576, 4, 4), (768, 576, 4, 1
     alg = ctx.push_frame_bytes * ncam
     r = {"w": w, "h": h, "levels": levels, "frames": ncam, "MB": round(alg / 1e6, 2), "ms_mean": round(float(ms.mean()), 4),
          "ms_min": round(float(ms.min()), 4), "GBs_mean": round(alg / ms.mean() / 1e6, 1), "frac": round(alg / ms.mean() / 1e6 / PEAK, 3)}
-    print(json.dumps(r)); out.append(r)
+    print(json.dumps(r), flush=True); out.append(r)
     ctx.close()
 json.dump(out, open("gpurun_out/pyr_sweep.json", "w"), indent=1)
