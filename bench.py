@@ -118,8 +118,9 @@ class ClockSampler(threading.Thread):
 class GpuRig:
     """One GPU's rig driven through the C ABI; all per-step arrays preallocated (device and pinned host)."""
 
-    def __init__(self, wl, rank, device):
+    def __init__(self, wl, rank, device, pipeline=True):
         import torch
+        self.pipeline = pipeline
         from mcmtt_opticalflow_b200 import klt
         self.torch, self.klt = torch, klt
         self.w, self.h, self.ncam, self.ntgt, self.per, self.levels = WORKLOADS[wl]
@@ -199,10 +200,10 @@ class GpuRig:
             a.out_xy, a.status, a.err, a.fb_err = out_ptr + o * 8, st_ptr + o, err_ptr + o * 4, fb_ptr + o * 4
         return arr
 
-    def _push(self, t_idx, host):
+    def _push(self, t_idx, host, overlap=False):
         src = self.h_frames if host else self.d_frames
         ptrs = (C.c_void_p * self.ncam)(*[src[c][t_idx].data_ptr() for c in range(self.ncam)])
-        mem = self.klt.MEM_PINNED if host else self.klt.MEM_DEVICE
+        mem = (self.klt.MEM_PINNED if host else self.klt.MEM_DEVICE) | (self.klt.MEM_OVERLAP if overlap else 0)
         self.ctx._ck(self.ctx.lib.psnw_push_frames(self.ctx._h, self.ncam, self.cams.ctypes.data, ptrs, self.w, t_idx, mem))
 
     def _detect(self, t_idx, seeds, counts, mem):
@@ -225,12 +226,12 @@ class GpuRig:
         if self.grid:
             g = self.torch.from_numpy(np.tile(self.grid_pts, (self.ncam, 1))).to(self.dev)
             self.d_seeds[0].copy_(g); self.d_seeds[1].copy_(g)
-            self.ctx.sync()
-            self.step_idx = 1
-            return
-        self._detect(pingpong(0), self.d_seeds[self.which], self.d_counts_det, self.klt.MEM_DEVICE)
-        boxes0 = np.concatenate([self.boxes[c][pingpong(0)] for c in range(self.ncam)])
-        self.d_boxes_in.copy_(self.torch.from_numpy(boxes0).to(self.dev))
+        else:
+            self._detect(pingpong(0), self.d_seeds[self.which], self.d_counts_det, self.klt.MEM_DEVICE)
+            boxes0 = np.concatenate([self.boxes[c][pingpong(0)] for c in range(self.ncam)])
+            self.d_boxes_in.copy_(self.torch.from_numpy(boxes0).to(self.dev))
+        if self.pipeline:                    # one frame in flight: the frame a step tracks into was pushed by the step before
+            self._push(pingpong(1), host)
         self.ctx.sync()
         self.step_idx = 1
 
@@ -241,27 +242,33 @@ class GpuRig:
         (tracked points, status, updated boxes, inlier counts and mask) are copied out to pinned host memory.
         Seeds are internal state of the path (detect output -> next step's track input) and stay on the device.
         Detection of the next step's seeds runs on the auxiliary stream and overlaps with tracking."""
+        # (grid workloads keep their seeds: self.which is not flipped)
         klt, ctx = self.klt, self.ctx
         t_idx = pingpong(self.step_idx)
         cur, nxt = self.which, self.which ^ 1
         seeds, seeds_next = self.d_seeds[cur], self.d_seeds[nxt]
-        self._push(t_idx, host)
-        if self.grid:                        # C4: dense grid, forward + backward LK + FB gate only
-            jobs = self._jobs(seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(), self.d_err.data_ptr(), self.d_fb.data_ptr())
-            ctx._ck(ctx.lib.psnw_klt_track_batch(ctx._h, jobs, self.ncam, klt.MEM_DEVICE))
-            if host:
-                self.h_blob.copy_(self.d_blob, non_blocking=True)
-            self.step_idx += 1
-            return
-        self._detect(t_idx, seeds_next, self.d_counts_det, klt.MEM_DEVICE | klt.MEM_OVERLAP)
         jobs = self._jobs(seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(), self.d_err.data_ptr(), self.d_fb.data_ptr())
-        ctx._ck(ctx.lib.psnw_klt_track_batch(ctx._h, jobs, self.ncam, klt.MEM_DEVICE))
-        ctx.box_update_raw(self.d_boxes_in.data_ptr(), self.ntargets, seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(),
-                           self.d_off.data_ptr(), self.d_boxes_out.data_ptr(), self.d_mask.data_ptr(), self.d_counts.data_ptr(), klt.MEM_DEVICE)
+        if self.pipeline:
+            # One frame in flight (SURVEY C5): frame t_idx is already on the device -- the previous step pushed it while
+            # it was tracking.  This step tracks into it and ingests the NEXT frame on the upload stream
+            # (PSNW_MEM_OVERLAP), so the H2D copy and the pyramid build run under the LK launch.  Every step still
+            # uploads one rig frame, tracks one and returns one result.
+            if not self.grid:
+                self._detect(t_idx, seeds_next, self.d_counts_det, klt.MEM_DEVICE | klt.MEM_OVERLAP)
+            ctx._ck(ctx.lib.psnw_klt_track_batch(ctx._h, jobs, self.ncam, klt.MEM_DEVICE))
+            self._push(pingpong(self.step_idx + 1), host, overlap=True)
+        else:
+            self._push(t_idx, host)
+            if not self.grid:
+                self._detect(t_idx, seeds_next, self.d_counts_det, klt.MEM_DEVICE | klt.MEM_OVERLAP)
+            ctx._ck(ctx.lib.psnw_klt_track_batch(ctx._h, jobs, self.ncam, klt.MEM_DEVICE))
+        if not self.grid:                    # C4 (dense grid) is forward + backward LK + FB gate only
+            ctx.box_update_raw(self.d_boxes_in.data_ptr(), self.ntargets, seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(),
+                               self.d_off.data_ptr(), self.d_boxes_out.data_ptr(), self.d_mask.data_ptr(), self.d_counts.data_ptr(), klt.MEM_DEVICE)
+            self.which = nxt
         ctx.join()
         if host:
             self.h_blob.copy_(self.d_blob, non_blocking=True)
-        self.which = nxt
         self.step_idx += 1
 
     def e2e_bytes(self):
@@ -319,7 +326,10 @@ class GpuRig:
         if self.grid:
             self.step(False)
         seeds = self.d_seeds[self.which]
-        jobs = self._jobs(seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(), self.d_err.data_ptr(), self.d_fb.data_ptr(), 0, 1)
+        # pipelined: slot 0 already holds the next frame, the seeds belong to slot 1 -- exactly the next step's launch;
+        # otherwise the newest frame's seeds are tracked back into the previous frame
+        sf, st_ = (1, 0) if self.pipeline else (0, 1)
+        jobs = self._jobs(seeds.data_ptr(), self.d_out.data_ptr(), self.d_status.data_ptr(), self.d_err.data_ptr(), self.d_fb.data_ptr(), sf, st_)
         with t.cuda.stream(self.stream):
             ev = [(t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)) for _ in range(reps)]
             for i in range(reps):
@@ -447,6 +457,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="push each frame inside its own step (no frame in flight)")
     args = ap.parse_args()
     warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -458,7 +469,9 @@ def main():
                           % (args.workload, ncam, w, h, ("%d targets/view x %d seeds" % (ntgt, per)) if ntgt else "dense grid stride 4 px",
                              levels, " + LocalSearchKLT box update + Shi-Tomasi re-detect" if ntgt else ""),
               "cameras_per_gpu": ncam, "points_per_step_per_gpu": npts_cfg, "lk_solves_per_step_per_gpu": 2 * npts_cfg,
-              "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "cameras sharded, %d rig(s), no collective" % world}
+              "l2": "flushed between timed steps (256 MiB memset)",
+              "frames_in_flight": "1: each step tracks the frame pushed by the step before and ingests the next one (H2D + pyramid on "
+                                  "the upload stream, PSNW_MEM_OVERLAP) under its LK launch" if not args.no_pipeline else "0: push, then track", "parallelism": "cameras sharded, %d rig(s), no collective" % world}
 
     if args.impl == "reference":
         if rank != 0:
@@ -481,7 +494,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    rig = GpuRig(args.workload, rank, local)
+    rig = GpuRig(args.workload, rank, local, pipeline=not args.no_pipeline)
 
     def barrier():
         if dist is not None:

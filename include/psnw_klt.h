@@ -53,10 +53,16 @@ enum {
 };
 
 enum { PSNW_MEM_HOST = 0, PSNW_MEM_PINNED = 1, PSNW_MEM_DEVICE = 2 };
-/* OR-ed into the mem_flags of psnw_klt_detect(_batch) (PINNED / DEVICE only): the detection runs on an auxiliary
- * stream forked from the context stream at the call, so the psnw_klt_track / psnw_box_update calls that FOLLOW
- * overlap with it (they must not consume its outputs).  The outputs are complete after psnw_join (device-side
- * join, no host block), psnw_sync, or the next push / detect call. */
+/* OR-ed into mem_flags (PINNED / DEVICE only; ignored with HOST).
+ *  psnw_klt_detect(_batch): the detection runs on an auxiliary stream forked from the context stream at the call, so the
+ *    psnw_klt_track / psnw_box_update calls that FOLLOW overlap with it (they must not consume its outputs).  The outputs
+ *    are complete after psnw_join (device-side join, no host block), psnw_sync, or the next plain push / detect call.
+ *  psnw_push_frame(s)(_bgr): the upload and the pyramid build run on an upload stream that waits only for the launches
+ *    already enqueued that read the ring slots being recycled -- not for the rest of the context stream -- so the NEXT
+ *    frame is ingested while the current one is still being tracked (one frame in flight).  The ring rotates at the call:
+ *    slot numbers in later calls refer to the new ring, and every later call that reads frames (track, detect, read_*)
+ *    first makes the context stream wait for the push (device-side, no host block).  The caller keeps the source
+ *    frames unchanged until psnw_sync or psnw_join. */
 #define PSNW_MEM_OVERLAP 0x100
 
 /* psnw_box_update estimators */

@@ -38,6 +38,16 @@ struct psnw_ctx {
     cudaStream_t aux = nullptr;           // PSNW_MEM_OVERLAP detect calls run here, forked from / joined to `stream`
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool aux_pending = false;
+    // PSNW_MEM_OVERLAP pushes (upload + pyramid of the NEXT frame while the current one is tracked) run on `up`.  They
+    // are ordered after the already enqueued readers of the planes they recycle through reader events: every launch that
+    // reads pyramid planes records an event from a small ring and stamps the planes with its sequence number.
+    cudaStream_t up = nullptr;
+    cudaEvent_t ev_up = nullptr;
+    bool up_pending = false;
+    static constexpr int kReaderRing = 8;
+    cudaEvent_t rd_ev[kReaderRing] = {};
+    uint64_t rd_seq = 0;
+    std::vector<uint64_t> plane_rd_seq;
     PyrDesc pyr;
     uint8_t *img_alloc[PSNW_MAX_LEVELS] = {};   // allocation behind pyr.lv[l].img (which points at pixel (0,0) of plane 0)
     CUtensorMap maps[PSNW_MAX_LEVELS];
@@ -54,6 +64,7 @@ struct psnw_ctx {
     DevBuf desc;                          // job / group descriptors (track)
     unsigned *lk_work = nullptr;          // [2] work counters of the persistent 21x21 LK kernel (self-resetting)
     int lk_ctas = 0;                      // resident CTAs of that kernel on this device
+    bool lk_persistent = true;            // persistent warps + work counter; PSNW_LK_PERSISTENT=0 (bring-up): one point per warp
     DevBuf det_desc;                      // target descriptors + staged outputs (detect; may run on the aux stream)
     DevBuf cand;                          // detect candidate scratch
     DevBuf bgr;                           // BGR staging for psnw_push_frames_bgr
@@ -198,9 +209,30 @@ int enter(psnw_ctx *ctx)
     return PSNW_OK;
 }
 
-// make the main stream wait for an overlapped detect (no host block)
+// make the main stream wait for an overlapped push: every consumer of ring slots calls this first (no host block)
+int join_up(psnw_ctx *ctx)
+{
+    if (ctx->up_pending) {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0));
+        ctx->up_pending = false;
+    }
+    return PSNW_OK;
+}
+
+// a launch on `st` reads the listed planes: overlapped pushes that recycle one of them wait for it
+int note_readers(psnw_ctx *ctx, cudaStream_t st, const int *planes, int n)
+{
+    if (n <= 0) return PSNW_OK;
+    const uint64_t seq = ++ctx->rd_seq;
+    CK(cudaEventRecord(ctx->rd_ev[seq % psnw_ctx::kReaderRing], st));
+    for (int i = 0; i < n; ++i) ctx->plane_rd_seq[planes[i]] = seq;
+    return PSNW_OK;
+}
+
+// make the main stream wait for an overlapped detect and an overlapped push (no host block)
 int join_aux(psnw_ctx *ctx)
 {
+    if (int rc = join_up(ctx)) return rc;
     if (ctx->aux_pending) {
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
         ctx->aux_pending = false;
@@ -222,7 +254,7 @@ int effective_max_level(const psnw_ctx *c, int win_w, int win_h)
 
 cudaMemcpyKind h2d(int mem_flags) { return mem_flags == PSNW_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
 
-int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes)
+int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t st)
 {
     for (size_t b = 0; b < planes.size(); b += 63) {
         PlaneList pl;
@@ -235,7 +267,7 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes)
         const size_t px = (size_t)ctx->pyr.lv[0].w * ctx->pyr.lv[0].h * pl.n;
         const bool fused = ctx->fused_levels && (ctx->pyr_mode == 2 || (ctx->pyr_mode == 0 && px <= ctx->fused_max_px));
         if (fused) {
-            const int r = launch_pyr_fused(ctx->pyr, ctx->fused_levels, &ctx->map_fused, pl, ctx->stream);
+            const int r = launch_pyr_fused(ctx->pyr, ctx->fused_levels, &ctx->map_fused, pl, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_fused_kernel launch", cudaGetLastError());
             ctx->launches += r;
             first = ctx->fused_levels < ctx->pyr.levels ? ctx->fused_levels - 1 : ctx->pyr.levels;   // level 3 again to feed level 4
@@ -244,16 +276,16 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes)
         // own input level with extra CTAs; the levels only the fused kernel produced get one apron launch.  When level
         // `first` is re-run only to feed the next level (5-level pyramids) it carries its apron as well.
         if (fused && first >= ctx->pyr.levels) {
-            const int r = launch_apron(ctx->pyr, 1, ctx->pyr.levels - 1, pl, ctx->stream);
+            const int r = launch_apron(ctx->pyr, 1, ctx->pyr.levels - 1, pl, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "apron_kernel launch", cudaGetLastError());
             ctx->launches += r;
         } else if (fused && first > 1) {
-            const int r = launch_apron(ctx->pyr, 1, first - 1, pl, ctx->stream);
+            const int r = launch_apron(ctx->pyr, 1, first - 1, pl, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "apron_kernel launch", cudaGetLastError());
             ctx->launches += r;
         }
         for (int l = first; l < ctx->pyr.levels; ++l) {
-            const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, 1, ctx->stream);
+            const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, 1, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_scharr_kernel launch", cudaGetLastError());
             ctx->launches += r;
         }
@@ -261,7 +293,7 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes)
     return PSNW_OK;
 }
 
-int advance_ring(psnw_ctx *ctx, int n, const int *cams, std::vector<int> &planes)
+int advance_ring(psnw_ctx *ctx, int n, const int *cams, std::vector<int> &planes, bool overlap = false)
 {
     for (int i = 0; i < n; ++i) {
         const int cam = cams[i];
@@ -269,7 +301,10 @@ int advance_ring(psnw_ctx *ctx, int n, const int *cams, std::vector<int> &planes
         for (int j = 0; j < i; ++j)
             if (cams[j] == cam) return fail(ctx, PSNW_EARG, "duplicate camera in psnw_push_frames");
     }
-    if (int rc = join_aux(ctx)) return rc;      // a push may recycle the slot an overlapped detect still reads
+    // a push may recycle the slot an overlapped detect still reads; an overlapped push orders itself after the readers
+    // of exactly the planes it recycles instead (push_stream)
+    if (!overlap)
+        if (int rc = join_aux(ctx)) return rc;
     planes.resize(n);
     for (int i = 0; i < n; ++i) {
         const int cam = cams[i];
@@ -277,6 +312,33 @@ int advance_ring(psnw_ctx *ctx, int n, const int *cams, std::vector<int> &planes
         ctx->held[cam] = std::min(ctx->held[cam] + 1, ctx->p.ring_slots);
         planes[i] = plane_of(ctx, cam, 0);
         ctx->plane_seq[planes[i]] = ++ctx->seq;
+    }
+    return PSNW_OK;
+}
+
+// Stream a push runs on.  PSNW_MEM_OVERLAP (pinned / device memory only): the upload stream, made to wait for the launches
+// already enqueued that read the recycled planes -- and for nothing else, so the push overlaps the LK launch in flight.
+int push_stream(psnw_ctx *ctx, bool overlap, const std::vector<int> &planes, cudaStream_t *st)
+{
+    *st = ctx->stream;
+    if (!overlap) return PSNW_OK;
+    *st = ctx->up;
+    uint64_t newest = 0;
+    for (int p : planes) newest = std::max(newest, ctx->plane_rd_seq[p]);
+    if (newest == 0) return PSNW_OK;
+    if (newest + psnw_ctx::kReaderRing > ctx->rd_seq) {
+        CK(cudaStreamWaitEvent(ctx->up, ctx->rd_ev[newest % psnw_ctx::kReaderRing], 0));
+    } else {                                            // its event was reused since: wait for every recent reader
+        for (int i = 0; i < psnw_ctx::kReaderRing; ++i) CK(cudaStreamWaitEvent(ctx->up, ctx->rd_ev[i], 0));
+    }
+    return PSNW_OK;
+}
+
+int push_done(psnw_ctx *ctx, bool overlap)
+{
+    if (overlap) {
+        CK(cudaEventRecord(ctx->ev_up, ctx->up));
+        ctx->up_pending = true;
     }
     return PSNW_OK;
 }
@@ -325,6 +387,7 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     ctx->head.assign(p->n_cameras, p->ring_slots - 1);
     ctx->held.assign(p->n_cameras, 0);
     ctx->plane_seq.assign(ctx->planes, 0);
+    ctx->plane_rd_seq.assign(ctx->planes, 0);
     ctx->eig.assign(p->n_cameras, nullptr);
     ctx->eig_tag.assign(p->n_cameras, 0);
     ctx->fmap.assign(p->n_cameras, nullptr);
@@ -345,11 +408,20 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     if (ctx->lk_ctas <= 0) return bail(PSNW_ECUDA);
     if (cudaMalloc(&ctx->lk_work, 2 * sizeof(unsigned)) != cudaSuccess) return bail(PSNW_ENOMEM);
     cudaMemsetAsync(ctx->lk_work, 0, 2 * sizeof(unsigned), ctx->stream);
+    if (const char *m = getenv("PSNW_LK_PERSISTENT")) ctx->lk_persistent = m[0] == '1';
     if (const char *m = getenv("PSNW_PYR_MODE")) ctx->pyr_mode = !strcmp(m, "level") ? 1 : !strcmp(m, "fused") ? 2 : 0;
-    if (cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess ||
+    // the side streams outrank the context stream: their short kernels (pyramid, detection) take the SM slots that LK
+    // warps free one by one instead of queueing behind the whole LK grid
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->up, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming) != cudaSuccess)
         return bail(PSNW_ECUDA);
+    for (cudaEvent_t &e : ctx->rd_ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(PSNW_ECUDA);
 
     // level geometry; levels smaller than 8 px are not built (no window fits them anyway)
     int w = p->width, h = p->height, levels = 0;
@@ -394,7 +466,11 @@ int psnw_destroy(psnw_ctx *ctx)
     if (!ctx) return PSNW_EARG;
     cudaSetDevice(ctx->p.device);
     if (ctx->aux) cudaStreamSynchronize(ctx->aux);
+    if (ctx->up) cudaStreamSynchronize(ctx->up);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_up) cudaEventDestroy(ctx->ev_up);
+    for (cudaEvent_t e : ctx->rd_ev) if (e) cudaEventDestroy(e);
+    if (ctx->up) cudaStreamDestroy(ctx->up);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
@@ -428,8 +504,13 @@ int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const
     if (n <= 0 || !cams || !grays || pitch < (size_t)ctx->p.width) return fail(ctx, PSNW_EARG, "psnw_push_frames arguments");
     for (int i = 0; i < n; ++i)
         if (!grays[i]) return fail(ctx, PSNW_EARG, "null frame pointer");
+    const bool overlap = (mem_flags & PSNW_MEM_OVERLAP) != 0 && (mem_flags & 0xff) != PSNW_MEM_HOST;
+    mem_flags &= 0xff;
     std::vector<int> planes;
-    int rc = advance_ring(ctx, n, cams, planes);
+    int rc = advance_ring(ctx, n, cams, planes, overlap);
+    if (rc) return rc;
+    cudaStream_t st;
+    rc = push_stream(ctx, overlap, planes, &st);
     if (rc) return rc;
     const LevelGeom &l0 = ctx->pyr.lv[0];
     // Frames that sit at a constant stride in the caller's memory and go to planes at a constant stride (the usual
@@ -445,16 +526,16 @@ int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const
     }
     if (one_copy) {
         CK(cudaMemcpy2DAsync(l0.img + (size_t)planes[0] * l0.plane_px, (size_t)dstride, grays[0], (size_t)sstride,
-                             (size_t)l0.plane_px, n, h2d(mem_flags), ctx->stream));
+                             (size_t)l0.plane_px, n, h2d(mem_flags), st));
     } else {
         for (int i = 0; i < n; ++i)
             CK(cudaMemcpy2DAsync(l0.img + (size_t)planes[i] * l0.plane_px, l0.pitch, grays[i], pitch, l0.w, l0.h,
-                                 h2d(mem_flags), ctx->stream));
+                                 h2d(mem_flags), st));
     }
-    rc = build_pyramids(ctx, planes);
+    rc = build_pyramids(ctx, planes, st);
     if (rc) return rc;
     if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
-    return PSNW_OK;
+    return push_done(ctx, overlap);
 }
 
 int psnw_push_frame(psnw_ctx *ctx, int cam, const uint8_t *gray, size_t pitch, uint32_t frame_idx, int mem_flags)
@@ -470,6 +551,8 @@ int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *c
     if (int rc_enter = enter(ctx)) return rc_enter;
     if (n <= 0 || !cams || !bgr || pitch < (size_t)ctx->p.width * 3 || (luma_bits != 14 && luma_bits != 15))
         return fail(ctx, PSNW_EARG, "psnw_push_frames_bgr arguments");
+    const bool overlap = (mem_flags & PSNW_MEM_OVERLAP) != 0 && (mem_flags & 0xff) != PSNW_MEM_HOST;
+    mem_flags &= 0xff;
     const LevelGeom &l0 = ctx->pyr.lv[0];
     const size_t row = ((size_t)l0.w * 3 + 255) & ~(size_t)255, frame = row * l0.h;
     if (mem_flags != PSNW_MEM_DEVICE) {
@@ -477,26 +560,33 @@ int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *c
         if (rc) return rc;
     }
     std::vector<int> planes;
-    int rc = advance_ring(ctx, n, cams, planes);
+    int rc = advance_ring(ctx, n, cams, planes, overlap);
     if (rc) return rc;
+    cudaStream_t st;
+    rc = push_stream(ctx, overlap, planes, &st);
+    if (rc) return rc;
+    if (overlap && mem_flags != PSNW_MEM_DEVICE) {      // the BGR staging buffer may still feed a conversion on the main stream
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+    }
     for (int i = 0; i < n; ++i) {
         const uint8_t *src = bgr[i];
         size_t src_pitch = pitch;
         if (!src) return fail(ctx, PSNW_EARG, "null frame pointer");
         if (mem_flags != PSNW_MEM_DEVICE) {
             uint8_t *dst = reinterpret_cast<uint8_t *>(ctx->bgr.p) + frame * i;
-            CK(cudaMemcpy2DAsync(dst, row, bgr[i], pitch, (size_t)l0.w * 3, l0.h, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpy2DAsync(dst, row, bgr[i], pitch, (size_t)l0.w * 3, l0.h, cudaMemcpyHostToDevice, st));
             src = dst; src_pitch = row;
         }
         const int r = launch_bgr2gray(src, src_pitch, l0.img + (size_t)planes[i] * l0.plane_px, l0.pitch, l0.w, l0.h,
-                                      luma_bits, ctx->stream);
+                                      luma_bits, st);
         if (r < 0) return fail(ctx, PSNW_ECUDA, "bgr2gray_kernel launch", cudaGetLastError());
         ctx->launches += r;
     }
-    rc = build_pyramids(ctx, planes);
+    rc = build_pyramids(ctx, planes, st);
     if (rc) return rc;
     if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
-    return PSNW_OK;
+    return push_done(ctx, overlap);
 }
 
 int psnw_rebuild_pyramids(psnw_ctx *ctx, int n, const int *cams)
@@ -508,7 +598,8 @@ int psnw_rebuild_pyramids(psnw_ctx *ctx, int n, const int *cams)
         if (!slot_ok(ctx, cams[i], 0)) return fail(ctx, PSNW_ESTATE, "psnw_rebuild_pyramids: camera holds no frame");
         planes[i] = plane_of(ctx, cams[i], 0);
     }
-    return build_pyramids(ctx, planes);
+    if (int rc = join_aux(ctx)) return rc;
+    return build_pyramids(ctx, planes, ctx->stream);
 }
 
 int psnw_frames_held(psnw_ctx *ctx, int cam)
@@ -522,6 +613,7 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     if (!ctx) return PSNW_EARG;
     if (int rc_enter = enter(ctx)) return rc_enter;
     if (!jobs || n_jobs <= 0) return fail(ctx, PSNW_EARG, "psnw_klt_track_batch: no jobs");
+    if (int rc_up = join_up(ctx)) return rc_up;          // an overlapped push may still be filling the slots tracked here
     const bool dev = mem_flags == PSNW_MEM_DEVICE;
     int total = 0, total_groups = 0;
     for (int j = 0; j < n_jobs; ++j) {
@@ -603,11 +695,19 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     P.min_eig = ctx->p.min_eig_thresh;
     P.fb_thresh = ctx->p.fb_thresh;
     P.do_fb = do_fb ? 1 : 0;
-    P.work = ctx->lk_work;
+    P.work = ctx->lk_persistent ? ctx->lk_work : nullptr;
     const int r = launch_lk(P, all21 ? 1 : 0, max_win_px, ctx->lk_ctas, ctx->stream);
     if (r == -2) return fail(ctx, PSNW_EARG, "psnw_klt_track: window too large for shared memory");
     if (r < 0) return fail(ctx, PSNW_ECUDA, "lk kernel launch", cudaGetLastError());
     ctx->launches += r;
+    {
+        std::vector<int> rd;
+        for (const TrackGroup &g : dg) {
+            if (rd.empty() || rd[rd.size() - 2] != g.plane_from || rd.back() != g.plane_to) { rd.push_back(g.plane_from); rd.push_back(g.plane_to); }
+        }
+        rc = note_readers(ctx, ctx->stream, rd.data(), (int)rd.size());
+        if (rc) return rc;
+    }
 
     if (!dev) {
         for (int j = 0; j < n_jobs; ++j) {
@@ -755,6 +855,12 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
     }
     rc = ensure_min_eig(ctx, cs, st);
     if (rc) return rc;
+    {
+        std::vector<int> rd;
+        for (const auto &c : cs) rd.push_back(plane_of(ctx, c.first, c.second));
+        rc = note_readers(ctx, st, rd.data(), (int)rd.size());
+        if (rc) return rc;
+    }
 
     // mask ROI = box.cropWithSize(cols, rows).cv()  (PSNWhere_Types.h:146-153,181; Tracker2D.cpp:735).  `boxes` is
     // always host memory: detections come from the host-side detector files (PSNWhere.cpp:261).
@@ -901,6 +1007,8 @@ int psnw_gridfast_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, 
         if (r < 0) return fail(ctx, PSNW_ECUDA, "fast_map_kernel launch", cudaGetLastError());
         ctx->launches += r;
         ctx->fmap_tag[cam] = ctx->plane_seq[plane];
+        rc = note_readers(ctx, ctx->stream, &plane, 1);
+        if (rc) return rc;
     }
     const bool dev = mem_flags == PSNW_MEM_DEVICE;
     const size_t tb = (sizeof(GridFastTarget) * n_targets + 255) & ~(size_t)255;
@@ -990,6 +1098,7 @@ int psnw_read_level(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *img_ou
     if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_read_level: camera/slot holds no frame");
     const LevelGeom &g = ctx->pyr.lv[level];
     const int plane = plane_of(ctx, cam, slot);
+    if (int rc_up = join_up(ctx)) return rc_up;
     CK(cudaStreamSynchronize(ctx->stream));
     if (img_out) CK(cudaMemcpy2D(img_out, g.w, g.img + (size_t)plane * g.iplane_px, g.ipitch, g.w, g.h, cudaMemcpyDeviceToHost));
     if (dxy_out) CK(cudaMemcpy2D(dxy_out, (size_t)g.w * 4, g.dxy + (size_t)plane * g.plane_px, (size_t)g.pitch * 4, (size_t)g.w * 4, g.h, cudaMemcpyDeviceToHost));
@@ -1005,6 +1114,7 @@ int psnw_read_level_apron(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *
     const int a = g.apron ? kApron : 0;
     if (apron) *apron = a;
     if (!out) return PSNW_OK;
+    if (int rc_up = join_up(ctx)) return rc_up;
     CK(cudaStreamSynchronize(ctx->stream));
     const uint8_t *src = g.img + (size_t)plane_of(ctx, cam, slot) * g.iplane_px - (ptrdiff_t)a * g.ipitch - a;
     CK(cudaMemcpy2D(out, g.w + 2 * a, src, g.ipitch, g.w + 2 * a, g.h + 2 * a, cudaMemcpyDeviceToHost));

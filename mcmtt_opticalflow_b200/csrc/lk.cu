@@ -667,10 +667,15 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
         R.dr7 = lane / 7; R.g7 = lane - 7 * R.dr7;
     }
 
-    for (;;) {
-        int i = 0;
-        if (lane == 0) i = (int)atomicAdd(P.work, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
+    const bool persistent = P.work != nullptr;
+    for (int it = 0;; ++it) {
+        int i = blockIdx.x * kWarpsPerCta + wib;
+        if (persistent) {
+            if (lane == 0) i = (int)atomicAdd(P.work, 1u);
+            i = __shfl_sync(0xffffffffu, i, 0);
+        } else if (it) {
+            break;                               // one point per warp: the hardware CTA scheduler balances the load
+        }
         if (i >= P.n_pts) break;
 
         const TrackJob &job = P.jobs[find_job(P.jobs, P.n_jobs, i)];
@@ -693,7 +698,7 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
         }
         finish_point(P, job, k, p0, f, b, lane);
     }
-    if (lane == 0) {
+    if (persistent && lane == 0) {
         const unsigned total = gridDim.x * kWarpsPerCta;
         if (atomicAdd(P.work + 1, 1u) + 1 == total) { P.work[0] = 0; P.work[1] = 0; }
     }
@@ -720,7 +725,8 @@ int launch_lk(const LkParams &P, int all_21x21, int max_win_px, int resident_cta
 {
     if (P.n_pts <= 0) return 0;
     if (all_21x21) {
-        const int grid = min((P.n_pts + kWarpsPerCta - 1) / kWarpsPerCta, max(resident_ctas, 1));
+        int grid = (P.n_pts + kWarpsPerCta - 1) / kWarpsPerCta;
+        if (P.work) grid = min(grid, max(resident_ctas, 1));
         lk_w21_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(P);
     } else {
         const int stride = (max_win_px + 7) & ~7;

@@ -1,0 +1,78 @@
+"""GPU tier: overlapped frame intake (PSNW_MEM_OVERLAP on psnw_push_frames) -- the next frame is uploaded and its pyramid
+built on the upload stream while the current frame is still being tracked.  Results must be bit-identical to the serial
+order, including when the ring is so short that the push recycles a slot the LK launch in flight still reads."""
+import numpy as np
+import pytest
+
+from mcmtt_opticalflow_b200 import klt, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(w, h, frames, pts, ring_slots, overlap, levels=4):
+    """Tracks pts through consecutive frame pairs (always from the original seeds); -> list of (out, status, err, fb)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n = len(pts)
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    d_pts = torch.from_numpy(pts).to(dev)
+    res = []
+    with klt.KLTContext(w, h, levels=levels, ring_slots=ring_slots, fb_thresh=1.0, max_points=max(n, 1024)) as ctx:
+        outs = [dict(out=torch.zeros((n, 2), dtype=torch.float32, device=dev), status=torch.zeros(n, dtype=torch.uint8, device=dev),
+                     err=torch.zeros(n, dtype=torch.float32, device=dev), fb=torch.zeros(n, dtype=torch.float32, device=dev))
+                for _ in range(len(frames) - 1)]
+        push = lambda k, ov: ctx.push_frames([pinned[k].data_ptr()], [0], k, klt.MEM_PINNED | (klt.MEM_OVERLAP if ov else 0), pitch=w)
+        push(0, False)
+        if overlap:
+            push(1, False)
+        for k in range(1, len(frames)):
+            o = outs[k - 1]
+            job = dict(cam=0, slot_from=1, slot_to=0, n_pts=n, pts=d_pts.data_ptr(), out=o["out"].data_ptr(),
+                       status=o["status"].data_ptr(), err=o["err"].data_ptr(), fb_err=o["fb"].data_ptr())
+            if overlap:
+                ctx.track_batch([job], mem=klt.MEM_DEVICE)            # frames k-1 -> k, both already on the device
+                if k + 1 < len(frames):
+                    push(k + 1, True)                                   # ingest k+1 under the LK launch
+            else:
+                push(k, False)
+                ctx.track_batch([job], mem=klt.MEM_DEVICE)
+        ctx.sync()
+        for o in outs:
+            res.append(tuple(o[key].cpu().numpy() for key in ("out", "status", "err", "fb")))
+    return res
+
+
+@pytest.mark.parametrize("ring_slots", [2, 3, 4])
+def test_overlapped_push_equals_serial(ring_slots):
+    w, h = 768, 576
+    cam = synth.Camera(w, h, 12, cam=2)
+    frames = [cam.frame(k) for k in range(6)]
+    pts, _ = synth.seeds_in_boxes(cam.boxes(0), 400, w, h, np.random.default_rng(9))    # a launch long enough to overlap
+    serial = _run(w, h, frames, pts, ring_slots, overlap=False)
+    piped = _run(w, h, frames, pts, ring_slots, overlap=True)
+    assert len(serial) == len(piped) == 5
+    for k, (a, b) in enumerate(zip(serial, piped)):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), ("step", k)
+    assert serial[0][1].mean() > 0.5
+
+
+def test_overlapped_push_then_readers_wait(oracle):
+    """Every reader of ring slots (read_level, detect, track) first waits for a pending overlapped push."""
+    import torch
+    w, h = 384, 288
+    cam = synth.Camera(w, h, 4, cam=1)
+    f0, f1 = cam.frame(0), cam.frame(1)
+    p1 = torch.from_numpy(f1).pin_memory()
+    with klt.KLTContext(w, h, levels=3) as ctx:
+        ctx.push_frame(f0)
+        ctx.push_frames([p1.data_ptr()], [0], 1, klt.MEM_PINNED | klt.MEM_OVERLAP, pitch=w)
+        img, dxy = ctx.read_level(0, 0, 1)
+        assert np.array_equal(img, oracle.pyr_down(f1)) and np.array_equal(dxy, oracle.scharr(oracle.pyr_down(f1)))
+        img0, _ = ctx.read_level(0, 1, 0)
+        assert np.array_equal(img0, f0)
+        seeds, counts = ctx.detect(cam.boxes(1), 30, 0.01, 3.0)
+        eig = ctx.read_min_eig()
+        assert np.array_equal(eig, oracle.min_eig_map(f1))
+        for t in range(4):
+            assert np.array_equal(seeds[t, :counts[t]], oracle.detect(f1, cam.boxes(1)[t], 30, 0.01, 3.0, eig=eig))

@@ -3,7 +3,7 @@
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-rig = bench.GpuRig("c2", 0, 0)
+rig = bench.GpuRig(os.environ.get("QT_WORKLOAD", "c2"), 0, 0, pipeline=os.environ.get("QT_PIPELINE", "1") == "1")
 rig.prime(False)
 lk, frac = rig.time_track(reps=20)
 sec, launches = rig.timed(50, 5, host=False)
