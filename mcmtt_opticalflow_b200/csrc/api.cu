@@ -404,7 +404,10 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     }
 
     if (configure_lk_kernels() || configure_box_kernels() || configure_detect_kernels() || configure_fused_kernels()) return bail(PSNW_ECUDA);
-    ctx->lk_ctas = lk_w21_resident_ctas();
+    {
+        const char *m = getenv("PSNW_LK_CTAS_PER_SM");     // bring-up: cap of the persistent grid
+        ctx->lk_ctas = lk_w21_resident_ctas(m ? atoi(m) : 0);
+    }
     if (ctx->lk_ctas <= 0) return bail(PSNW_ECUDA);
     if (cudaMalloc(&ctx->lk_work, 2 * sizeof(unsigned)) != cudaSuccess) return bail(PSNW_ENOMEM);
     cudaMemsetAsync(ctx->lk_work, 0, 2 * sizeof(unsigned), ctx->stream);
@@ -670,23 +673,31 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
         pt += J.n_pts; gb += J.n_targets;
     }
 
-    // descriptors -> device
+    // descriptors: inside the kernel parameters when they fit, else through a pinned staging slot -> device
+    const bool embed = n_jobs <= kEmbedJobs && total_groups <= kEmbedGroups;
     const size_t jb = sizeof(TrackJob) * n_jobs, gbytes = sizeof(TrackGroup) * total_groups;
     const size_t goff = (jb + 255) & ~(size_t)255;
-    int rc = ensure(ctx, ctx->desc, goff + gbytes);
-    if (rc) return rc;
-    StageSlot *s;
-    rc = stage_acquire(ctx, goff + gbytes, &s);
-    if (rc) return rc;
-    memcpy(s->h, dj.data(), jb);
-    memcpy(s->h + goff, dg.data(), gbytes);
-    rc = stage_upload(ctx, s, ctx->desc.p, goff + gbytes);
-    if (rc) return rc;
+    int rc = PSNW_OK;
+    if (!embed) {
+        rc = ensure(ctx, ctx->desc, goff + gbytes);
+        if (rc) return rc;
+        StageSlot *s;
+        rc = stage_acquire(ctx, goff + gbytes, &s);
+        if (rc) return rc;
+        memcpy(s->h, dj.data(), jb);
+        memcpy(s->h + goff, dg.data(), gbytes);
+        rc = stage_upload(ctx, s, ctx->desc.p, goff + gbytes);
+        if (rc) return rc;
+    }
 
     LkParams P;
     memcpy(P.lv, ctx->pyr.lv, sizeof P.lv);
-    P.jobs = reinterpret_cast<const TrackJob *>(ctx->desc.p);
-    P.groups = reinterpret_cast<const TrackGroup *>(ctx->desc.p + goff);
+    P.jobs = embed ? nullptr : reinterpret_cast<const TrackJob *>(ctx->desc.p);
+    P.groups = embed ? nullptr : reinterpret_cast<const TrackGroup *>(ctx->desc.p + goff);
+    if (embed) {
+        memcpy(P.ejobs, dj.data(), jb);
+        memcpy(P.egroups, dg.data(), gbytes);
+    }
     P.n_jobs = n_jobs; P.n_pts = total;
     P.max_iters = ctx->p.max_iters;
     P.eps2 = ctx->p.epsilon * ctx->p.epsilon;

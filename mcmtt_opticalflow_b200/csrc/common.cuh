@@ -58,10 +58,15 @@ struct TrackJob {
     int group_base, n_targets;
 };
 
+// small batches carry their descriptors inside the kernel parameters (no copy ahead of the launch)
+constexpr int kEmbedJobs = 8, kEmbedGroups = 16;
+
 struct LkParams {
     LevelGeom lv[PSNW_MAX_LEVELS];
-    const TrackJob *jobs;
+    const TrackJob *jobs;      // null: ejobs / egroups below
     const TrackGroup *groups;
+    TrackJob ejobs[kEmbedJobs];
+    TrackGroup egroups[kEmbedGroups];
     int n_jobs, n_pts;
     int max_iters;
     double eps2;
@@ -89,7 +94,7 @@ int configure_fused_kernels();
 int launch_pyr_fused(const PyrDesc &pyr, int nl, const CUtensorMap *map0, const PlaneList &planes, cudaStream_t stream);
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,
                     int luma_bits, cudaStream_t stream);
-int lk_w21_resident_ctas();   // CTAs of the persistent 21x21 kernel resident at once on the current device, or -1
+int lk_w21_resident_ctas(int max_per_sm);   // CTAs of the persistent 21x21 kernel resident at once on the current device (capped per SM when > 0), or -1
 int launch_lk(const LkParams &P, int all_21x21, int max_win_px, int resident_ctas, cudaStream_t stream);
 int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
                       const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,

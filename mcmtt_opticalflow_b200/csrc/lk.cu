@@ -291,10 +291,11 @@ lk_generic_kernel(const __grid_constant__ LkParams P, int max_win_px)
     short2 *dIw = reinterpret_cast<short2 *>(smem_raw);
     short *Iw = reinterpret_cast<short *>(dIw + stride);
 
-    const TrackJob &job = P.jobs[find_job(P.jobs, P.n_jobs, i)];
+    const TrackJob *jobs = P.jobs ? P.jobs : P.ejobs;
+    const TrackJob &job = jobs[find_job(jobs, P.n_jobs, i)];
     const int k = i - job.pt_begin;
     const int t = job.target_of_pt ? job.target_of_pt[k] : 0;
-    const TrackGroup g = P.groups[job.group_base + min(max(t, 0), job.n_targets - 1)];
+    const TrackGroup g = (P.jobs ? P.groups : P.egroups)[job.group_base + min(max(t, 0), job.n_targets - 1)];
     const float2 p0 = job.pts[k];
 
     Solve f, b;
@@ -678,10 +679,11 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
         }
         if (i >= P.n_pts) break;
 
-        const TrackJob &job = P.jobs[find_job(P.jobs, P.n_jobs, i)];
+        const TrackJob *jobs = P.jobs ? P.jobs : P.ejobs;
+        const TrackJob &job = jobs[find_job(jobs, P.n_jobs, i)];
         const int k = i - job.pt_begin;
         const int t = job.target_of_pt ? job.target_of_pt[k] : 0;
-        const TrackGroup g = P.groups[job.group_base + min(max(t, 0), job.n_targets - 1)];
+        const TrackGroup g = (P.jobs ? P.groups : P.egroups)[job.group_base + min(max(t, 0), job.n_targets - 1)];
         const float2 p0 = job.pts[k];
 
         // forward pass, then (fused forward-backward check) the same solver from the tracked position back into the
@@ -712,12 +714,13 @@ int configure_lk_kernels()
 }
 
 // CTAs of the persistent 21x21 kernel that are resident at once on the current device (SM count x occupancy)
-int lk_w21_resident_ctas()
+int lk_w21_resident_ctas(int max_per_sm)
 {
     int dev = 0, sms = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk_w21_kernel, kWarpsPerCta * 32, 0) != cudaSuccess)
         return -1;
+    if (max_per_sm > 0) per_sm = min(per_sm, max_per_sm);
     return sms * per_sm;
 }
 
