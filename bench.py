@@ -537,6 +537,9 @@ def main():
             pass
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         rig.prime(False)
+        n0 = rig.ctx.launch_count
+        rig.ctx.rebuild_pyramids(rig.cams)
+        pyr_launches = rig.ctx.launch_count - n0
         pyr_mean, pyr_best = rig.time_pyramid()
         alg = rig.ctx.push_frame_bytes * ncam
         ach = alg / pyr_mean / 1e9
@@ -546,7 +549,12 @@ def main():
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_pyr_traffic.json")))["traffic_bytes_per_group"]
             except Exception:
                 pass
-        roofline = {"kernel": "pyr_scharr_kernel (%d PDL-chained launches = one per level, %d frames batched in grid.z)" % (levels, ncam),
+        pyr_kernel = ("pyr_scharr_kernel (%d PDL-chained launches = one per level, each writing its level's REFLECT_101 apron with extra CTAs; "
+                      "%d frames batched in grid.z)" % (pyr_launches, ncam)) if pyr_launches >= levels else \
+                     ("pyr_fused_kernel (levels 0-%d in one launch, TMA-staged, halo recompute) + apron_kernel%s; %d launches, %d frames "
+                      "batched in grid.z" % (min(levels, 4) - 1, " + pyr_scharr_kernel for the last level" if pyr_launches > 2 else "",
+                                             pyr_launches, ncam))
+        roofline = {"kernel": pyr_kernel,
                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "algorithmic_bytes": alg, "ms": 1e3 * pyr_mean, "best_ms": 1e3 * pyr_best, "peak_source": peak_src}
         roofline["frames_in_flight_sweep"] = pyramid_sweep(rig, peak) if args.workload == "c2" else None

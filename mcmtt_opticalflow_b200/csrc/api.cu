@@ -52,6 +52,7 @@ struct psnw_ctx {
     uint8_t *img_alloc[PSNW_MAX_LEVELS] = {};   // allocation behind pyr.lv[l].img (which points at pixel (0,0) of plane 0)
     CUtensorMap maps[PSNW_MAX_LEVELS];
     CUtensorMap map_fused;                // level-0 map with the box of the fused multi-level kernel
+    CUtensorMap *lk_maps = nullptr;       // device copy of the LK kernel's patch maps: 3 per level (LkParams::tmaps)
     int fused_levels = 0;                 // 3 or 4 when the fused kernel is usable, else 0
     size_t fused_max_px = 2200000;   // auto mode: fused kernel up to this many level-0 pixels per launch
     int pyr_mode = 0;                     // 0 auto, 1 per-level kernels only, 2 fused whenever possible (PSNW_PYR_MODE, bring-up)
@@ -186,6 +187,31 @@ int make_tensor_maps(psnw_ctx *ctx)
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(ctx, PSNW_ECUDA, "cuTensorMapEncodeTiled(fused level-0 map)");
     }
+    // patch maps of the 21x21 LK kernel: u8 image with the I box (48 x 22) and the J box (48 x 30), (dx,dy) image with the
+    // 28 x 22 box.  Apron levels describe the whole padded plane -- the apron is ordinary memory to the copy -- and the
+    // kernel offsets its coordinates by (kApronL, kApron); the derivative map zero-fills outside the image.
+    std::vector<CUtensorMap> lk(3 * ctx->pyr.levels);
+    for (int l = 0; l < ctx->pyr.levels; ++l) {
+        const LevelGeom &g = ctx->pyr.lv[l];
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const cuuint64_t idims[3] = {(cuuint64_t)(g.apron ? g.ipitch : g.w), (cuuint64_t)(g.apron ? g.h + 2 * kApron : g.h), (cuuint64_t)ctx->planes};
+        const cuuint64_t istr[2] = {(cuuint64_t)g.ipitch, (cuuint64_t)g.iplane_px};
+        void *ibase = g.apron ? (void *)ctx->img_alloc[l] : (void *)g.img;
+        for (int k = 0; k < 2; ++k) {
+            const cuuint32_t box[3] = {48, (cuuint32_t)(k ? 30 : 22), 1};
+            if (encode(&lk[3 * l + k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ibase, idims, istr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return fail(ctx, PSNW_ECUDA, "cuTensorMapEncodeTiled(LK image patch map)");
+        }
+        const cuuint64_t ddims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.h, (cuuint64_t)ctx->planes};
+        const cuuint64_t dstr[2] = {(cuuint64_t)g.pitch * 4, (cuuint64_t)g.plane_px * 4};
+        const cuuint32_t dbox[3] = {28, 22, 1};
+        if (encode(&lk[3 * l + 2], CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, g.dxy, ddims, dstr, dbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return fail(ctx, PSNW_ECUDA, "cuTensorMapEncodeTiled(LK derivative patch map)");
+    }
+    if (cudaMalloc(&ctx->lk_maps, sizeof(CUtensorMap) * lk.size()) != cudaSuccess) return fail(ctx, PSNW_ENOMEM, "cudaMalloc LK tensor maps");
+    CK(cudaMemcpy(ctx->lk_maps, lk.data(), sizeof(CUtensorMap) * lk.size(), cudaMemcpyHostToDevice));
     return PSNW_OK;
 }
 
@@ -487,6 +513,7 @@ int psnw_destroy(psnw_ctx *ctx)
     if (ctx->arena.p) cudaFree(ctx->arena.p);
     if (ctx->desc.p) cudaFree(ctx->desc.p);
     if (ctx->lk_work) cudaFree(ctx->lk_work);
+    if (ctx->lk_maps) cudaFree(ctx->lk_maps);
     if (ctx->cand.p) cudaFree(ctx->cand.p);
     if (ctx->bgr.p) cudaFree(ctx->bgr.p);
     for (StageSlot &s : ctx->stage) {
@@ -707,6 +734,7 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     P.fb_thresh = ctx->p.fb_thresh;
     P.do_fb = do_fb ? 1 : 0;
     P.work = ctx->lk_persistent ? ctx->lk_work : nullptr;
+    P.tmaps = ctx->lk_maps;
     const int r = launch_lk(P, all21 ? 1 : 0, max_win_px, ctx->lk_ctas, ctx->stream);
     if (r == -2) return fail(ctx, PSNW_EARG, "psnw_klt_track: window too large for shared memory");
     if (r < 0) return fail(ctx, PSNW_ECUDA, "lk kernel launch", cudaGetLastError());

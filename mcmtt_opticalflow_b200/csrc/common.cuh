@@ -74,6 +74,7 @@ struct LkParams {
     float min_eig;
     float fb_thresh;
     int do_fb;
+    const CUtensorMap *tmaps; // [3 * level + {0: I box 48x22, 1: J box 48x30, 2: (dx,dy) box 28x22}] of the 21x21 kernel (lk.cu)
     unsigned *work;           // [2] point counter / finished-warp counter of the persistent 21x21 kernel (zero between launches)
 };
 

@@ -15,12 +15,13 @@
 //                       in shared memory, image reads through L1 with on-the-fly REFLECT_101 / zero borders.
 //   lk_w21_kernel       21x21 window (BASELINE configs): persistent warps draw points from a device counter; the
 //                       441 pixels are 63 horizontal runs of 7, two runs per lane; the template (I, Ix, Iy) lives in
-//                       registers; patches are staged with cp.async (source patches one level ahead, the target
-//                       patch once per level with a 4-px margin) and bilinearly sampled with dp2a on packed
-//                       bytes; reductions use REDUX.
+//                       registers; patches are staged by TMA boxes completing on per-warp mbarriers (source
+//                       patches one level ahead, the target patch once per level with a 4-px margin) and
+//                       bilinearly sampled with dp2a on packed bytes; reductions use REDUX.
 #include <float.h>
 
 #include "common.cuh"
+#include "pyr_common.cuh"
 
 namespace psnw {
 
@@ -312,12 +313,14 @@ constexpr int kW = 21;                            // window
 constexpr int kPatch = kW + 1;                    // 22 x 22 samples feed the 21 x 21 bilinear window
 constexpr int kMargin = 4;                        // extra samples staged around the target-image patch
 constexpr int kJPatch = kPatch + 2 * kMargin;     // 30 x 30: the window may drift 8 px inside it before a re-stage
-constexpr int kU8Pitch = 12;                      // words per staged u8 row: 48 B >= 15 + 30, rows stay 16-byte aligned (cp.async)
-constexpr int kIWords = kPatch * kU8Pitch;        // 264
-constexpr int kJWords = kJPatch * kU8Pitch;       // 360
+constexpr int kU8Pitch = 12;                      // words per staged u8 row: 48 B = three 16-byte groups >= 15 + 30
 constexpr int kDxPitch = 28;                      // words per staged derivative row = 7 groups of 4 pixels
-constexpr int kDxWords = kPatch * kDxPitch;       // 616
-constexpr int kWarpSmemWords = kIWords + kJWords + kDxWords;   // 1240 words = 4960 B per warp
+// per-warp shared memory: three TMA destinations, each 128-byte aligned
+constexpr int kDBytes = 2560;                     // 22 rows x 112 B = 2464, rounded up
+constexpr int kIBytes = 1152;                     // 22 rows x 48 B = 1056, rounded up
+constexpr int kJBytes = 1536;                     // 30 rows x 48 B = 1440, rounded up
+constexpr int kWarpSmemBytes = kDBytes + kIBytes + kJBytes;    // 5248 B per warp
+constexpr int kIBoxBytes = kPatch * kU8Pitch * 4, kJBoxBytes = kJPatch * kU8Pitch * 4, kDBoxBytes = kPatch * kDxPitch * 4;
 #ifndef PSNW_LK_WARPS
 #define PSNW_LK_WARPS 4
 #endif
@@ -339,20 +342,6 @@ __device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c)
     return d;
 }
 
-// ---- asynchronous global -> shared copies (LDGSTS): no staging registers, completion tracked per commit group ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, int src_bytes)   // src_bytes 0: zeros
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 __device__ __forceinline__ int refl_clamp(int p, int n)
 {
     p = p < 0 ? -p : p;
@@ -370,63 +359,59 @@ __device__ __forceinline__ bool window_oob(int ix, int iy, int w, int h)
 struct WarpRole {
     int lane;
     int row0, col0, row1, col1;   // the lane's two runs: run r -> (row r / 3, first column 7 * (r % 3)); lane 31 owns one
-    int dr3, g3;                  // u8 staging: 16-byte group g3 of row dr3 (+10, +20)
-    int dr7, g7;                  // derivative staging: 16-byte group g7 of row dr7 (+4, +8, ...)
     bool two;
 };
 
-// ---- staging of an N x N u8 patch with top-left sample (x0, y0) into rows of kU8Pitch words; returns the byte offset
-// of sample column 0 inside a staged row.  Patches inside the frame are copied as aligned 16-byte groups with cp.async
-// (3 lanes per row, 10 rows per instruction; the caller commits and waits); patches touching the border gather bytes
-// row by row through REFLECT_101, the apron OpenCV keeps around every level (plain stores, visible after __syncwarp).
-template <int N>
-__device__ __forceinline__ int stage_u8(const uint8_t *__restrict__ img, int pitch, int w, int h, bool apron, int x0, int y0,
-                                        uint32_t *patch, const WarpRole &R)
+// Per-warp staging state.  Patches are fetched by TMA (cp.async.bulk.tensor, one instruction issued by lane 0 per patch)
+// and complete on two mbarriers: `src` for the source-frame patches (I and its derivatives, prefetched one level ahead)
+// and `tgt` for the target-image patch.  ph* = parity of the next completion, pend* = a completion is outstanding.
+struct Stage {
+    uint32_t bar_src, bar_tgt;
+    uint32_t ph_src, ph_tgt;
+    bool pend_src, pend_tgt;
+};
+
+__device__ __forceinline__ void stage_wait_src(Stage &S)
 {
-    // levels >= 1 carry a physical REFLECT_101 apron (common.cuh): every admissible patch is a plain aligned copy
-    const bool fast = apron || (x0 >= 0 && y0 >= 0 && x0 + N <= w && y0 + N <= h);
-    if (fast) {
-        const int off = x0 & 15;
-        const int ng = (off + N + 15) >> 4;               // 16-byte groups per row: 2 or 3
-        if (R.lane < 30 && R.g3 < ng) {
-            const uint8_t *src = img + (ptrdiff_t)(y0 + R.dr3) * pitch + (x0 - off) + 16 * R.g3;
-            const uint32_t dst = smem_u32(patch + R.dr3 * kU8Pitch + 4 * R.g3);
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if (10 * i + R.dr3 < N) cp_async16(dst + i * (10 * kU8Pitch * 4), src + (size_t)i * 10 * pitch);
-        }
-        return off;
-    }
-    if (R.lane < N) {
-        const uint8_t *col = img + refl_clamp(x0 + R.lane, w);
-        uint8_t *pb = reinterpret_cast<uint8_t *>(patch) + R.lane;
-#pragma unroll 2
-        for (int row = 0; row < N; ++row) pb[row * (kU8Pitch * 4)] = col[(size_t)refl_clamp(y0 + row, h) * pitch];
-    }
-    return 0;
+    if (S.pend_src) { mbar_wait(S.bar_src, S.ph_src); S.ph_src ^= 1u; S.pend_src = false; }
+}
+__device__ __forceinline__ void stage_wait_tgt(Stage &S)
+{
+    if (S.pend_tgt) { mbar_wait(S.bar_tgt, S.ph_tgt); S.ph_tgt ^= 1u; S.pend_tgt = false; }
 }
 
-// ---- staging of the 22 x 22 (dx,dy) samples at (x0, y0) as aligned 16-byte groups (7 lanes per row, 4 rows per
-// instruction); the word offset of sample column 0 inside a staged row is x0 & 3.  Outside the frame the derivative
-// apron is zero (BORDER_CONSTANT): groups left of x = 0 or beyond the row pitch and rows outside [0, h) are zero-filled;
-// columns in [w, pitch) already hold zeros (K1 writes them).
-__device__ __forceinline__ void stage_dxy(const short2 *__restrict__ D, int pitch, int h, int x0, int y0, uint32_t *dxp,
-                                          const WarpRole &R)
+// tensor maps of level l (LkParams::tmaps): [3l] u8 image with the 48 x 22 box, [3l+1] u8 image with the 48 x 30 box,
+// [3l+2] (dx,dy) image with the 28 x 22 box.  Apron levels describe the padded plane (the apron is ordinary memory to the
+// copy), level 0 the bare image; the derivative map zero-fills outside the image = the BORDER_CONSTANT apron of OpenCV.
+enum { kMapI = 0, kMapJ = 1, kMapD = 2 };
+
+// ---- staging of an N x N u8 patch with top-left sample (x0, y0) into rows of kU8Pitch words; returns the byte offset of
+// sample column 0 inside a staged row.  A patch that lies inside the frame, or anywhere on a level with a REFLECT_101
+// apron, is one TMA box of three aligned 16-byte groups per row (*tma_bytes receives its size; the caller has armed the
+// mbarrier).  On level 0 a patch touching the border is gathered byte by byte through REFLECT_101 (plain stores).
+template <int N>
+__device__ __forceinline__ int stage_u8(const LkParams &P, int level, int plane, int x0, int y0, uint32_t *patch,
+                                        uint32_t bar, const WarpRole &R, int *tma_bytes)
 {
-    const int gx = x0 - (x0 & 3) + 4 * R.g7;
-    const bool xin = gx >= 0 && gx < pitch;
-    if (R.lane < 28) {
-        const uint32_t dst = smem_u32(dxp + R.dr7 * kDxPitch + 4 * R.g7);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int row = 4 * i + R.dr7;
-            if (row < kPatch) {
-                const bool ok = xin && (unsigned)(y0 + row) < (unsigned)h;
-                const short2 *src = ok ? D + (ptrdiff_t)(y0 + row) * pitch + gx : D;
-                cp_async16_zfill(dst + i * (4 * kDxPitch * 4), src, ok ? 16 : 0);
-            }
-        }
+    const LevelGeom &L = P.lv[level];
+    const bool fast = L.apron || (x0 >= 0 && y0 >= 0 && x0 + N <= L.w && y0 + N <= L.h);
+    if (fast) {
+        const int off = x0 & 15;
+        *tma_bytes = N * kU8Pitch * 4;
+        if (R.lane == 0)
+            tma_load_3d(smem_u32(patch), P.tmaps + 3 * level + (N == kPatch ? kMapI : kMapJ),
+                        x0 - off + (L.apron ? kApronL : 0), y0 + (L.apron ? kApron : 0), plane, bar);
+        return off;
     }
+    *tma_bytes = 0;
+    if (R.lane < N) {
+        const uint8_t *col = L.img + (size_t)plane * L.iplane_px + refl_clamp(x0 + R.lane, L.w);
+        uint8_t *pb = reinterpret_cast<uint8_t *>(patch) + R.lane;
+#pragma unroll 2
+        for (int row = 0; row < N; ++row) pb[row * (kU8Pitch * 4)] = col[(size_t)refl_clamp(y0 + row, L.h) * L.ipitch];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // these generic stores precede later TMA writes to the buffer
+    return 0;
 }
 
 // Bilinear sums of a horizontal run of 7 samples starting at byte column `bc` of patch row `row`:
@@ -474,39 +459,51 @@ __device__ __forceinline__ bool src_origin(float px, float py, int level, int Lw
     return !window_oob(ix, iy, Lw, Lh);
 }
 
-// Stages the source-frame patches (I and its derivatives) of `level` -- always one commit group, possibly empty.
-// Called one level ahead: by then the template of the current level is in registers, so the copies land while the
-// current level iterates and the next level starts without waiting for memory.
+// Stages the source-frame patches (I and its derivatives) of `level` on the `src` barrier.  Called one level ahead: by
+// then the template of the current level is in registers, so the copies land while the current level iterates and the
+// next level starts without waiting for memory.
 __device__ __forceinline__ void prefetch_src(const LkParams &P, int plane_a, int level, float px, float py,
-                                             uint32_t *ip, uint32_t *dxp, const WarpRole &R)
+                                             uint32_t *ip, uint32_t *dxp, Stage &S, const WarpRole &R)
 {
-    if (level >= 0) {
-        const LevelGeom &L = P.lv[level];
-        float sx, sy;
-        int ix, iy;
-        if (src_origin(px, py, level, L.w, L.h, sx, sy, ix, iy)) {
-            stage_u8<kPatch>(L.img + (size_t)plane_a * L.iplane_px, L.ipitch, L.w, L.h, L.apron != 0, ix, iy, ip, R);
-            stage_dxy(L.dxy + (size_t)plane_a * L.plane_px, L.pitch, L.h, ix, iy, dxp, R);
-        }
-    }
-    cp_async_commit();
+    if (level < 0) return;
+    const LevelGeom &L = P.lv[level];
+    float sx, sy;
+    int ix, iy;
+    if (!src_origin(px, py, level, L.w, L.h, sx, sy, ix, iy)) return;
+    const bool fastI = L.apron || (ix >= 0 && iy >= 0 && ix + kPatch <= L.w && iy + kPatch <= L.h);
+    if (R.lane == 0) mbar_expect_tx(S.bar_src, kDBoxBytes + (fastI ? kIBoxBytes : 0));
+    int nb;
+    stage_u8<kPatch>(P, level, plane_a, ix, iy, ip, S.bar_src, R, &nb);
+    if (R.lane == 0) tma_load_3d(smem_u32(dxp), P.tmaps + 3 * level + kMapD, ix - (ix & 3), iy, plane_a, S.bar_src);
+    S.pend_src = true;
+}
+
+// target patch at (sx0, sy0) on the `tgt` barrier; returns the byte offset of sample column 0
+__device__ __forceinline__ int stage_tgt(const LkParams &P, int level, int plane_b, int sx0, int sy0, uint32_t *jp,
+                                         Stage &S, const WarpRole &R)
+{
+    const LevelGeom &L = P.lv[level];
+    const bool fast = L.apron || (sx0 >= 0 && sy0 >= 0 && sx0 + kJPatch <= L.w && sy0 + kJPatch <= L.h);
+    if (fast && R.lane == 0) mbar_expect_tx(S.bar_tgt, kJBoxBytes);
+    int nb;
+    const int off = stage_u8<kJPatch>(P, level, plane_b, sx0, sy0, jp, S.bar_tgt, R, &nb);
+    S.pend_tgt = nb != 0;
+    return off;
 }
 
 __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_level, float px, float py,
-                                       uint32_t *ip, uint32_t *jp, uint32_t *dxp, const WarpRole &R, Solve &o)
+                                       uint32_t *ip, uint32_t *jp, uint32_t *dxp, Stage &S, const WarpRole &R, Solve &o)
 {
     constexpr float half = (kW - 1) * 0.5f;
     float next_x = 0.f, next_y = 0.f, er = 0.f;
     int st = 1;
 
-    prefetch_src(P, plane_a, max_level, px, py, ip, dxp, R);
+    prefetch_src(P, plane_a, max_level, px, py, ip, dxp, S, R);
 #pragma unroll 1
     for (int level = max_level; level >= 0; --level) {
         const LevelGeom &L = P.lv[level];
-        const int Lw = L.w, Lh = L.h, Lp = L.ipitch;
-        const bool apron = L.apron != 0;
-        const uint8_t *JB = L.img + (size_t)plane_b * L.iplane_px;
-        cp_async_wait<0>();                      // this level's I / dI patches (and every older copy) have landed
+        const int Lw = L.w, Lh = L.h;
+        stage_wait_src(S);                       // this level's I / dI patches have landed
         __syncwarp();
 
         float prev_x, prev_y, nx, ny;
@@ -517,13 +514,13 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
         next_x = nx; next_y = ny;
         if (!src_ok) {
             if (level == 0) { st = 0; er = 0.f; }
-            prefetch_src(P, plane_a, level - 1, px, py, ip, dxp, R);
+            prefetch_src(P, plane_a, level - 1, px, py, ip, dxp, S, R);
             continue;
         }
         prev_x = __fsub_rn(prev_x, half); prev_y = __fsub_rn(prev_y, half);
         int w00, w01, w10, w11;
         bilinear_weights(__fsub_rn(prev_x, (float)ipx), __fsub_rn(prev_y, (float)ipy), w00, w01, w10, w11);
-        const bool fastI = apron || (ipx >= 0 && ipy >= 0 && ipx + kPatch <= Lw && ipy + kPatch <= Lh);
+        const bool fastI = L.apron || (ipx >= 0 && ipy >= 0 && ipx + kPatch <= Lw && ipy + kPatch <= Lh);
         const int offI = fastI ? (ipx & 15) : 0, offD = ipx & 3;
 
         // ---- target patch around the first position: in flight while the template is computed ----
@@ -532,9 +529,8 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
         bool staged = !window_oob(__float2int_rd(nx), __float2int_rd(ny), Lw, Lh);
         if (staged) {
             sx0 = patch_origin(__float2int_rd(nx), Lw); sy0 = patch_origin(__float2int_rd(ny), Lh);
-            offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, apron, sx0, sy0, jp, R);
+            offJ = stage_tgt(P, level, plane_b, sx0, sy0, jp, S, R);
         }
-        cp_async_commit();
 
         // ---- template into registers ----
         int tC[14], tIx[14], tIy[14];          // tC = 256 - 512 * I: the dp2a chain then yields (J - I) << 9 directly
@@ -564,8 +560,8 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             }
         }
         __syncwarp();                            // every lane is done with the I / dI patches ...
-        prefetch_src(P, plane_a, level - 1, px, py, ip, dxp, R);   // ... so the next level's copies may overwrite them
-        cp_async_wait<1>();                      // the target patch (the older group) has landed
+        prefetch_src(P, plane_a, level - 1, px, py, ip, dxp, S, R);   // ... so the next level's copies may overwrite them
+        stage_wait_tgt(S);                       // the target patch has landed
         __syncwarp();
         const long long s11 = warp_sum_i32(a11[0] + a11[1]), s12 = warp_sum_i32(a12[0] + a12[1]), s22 = warp_sum_i32(a22[0] + a22[1]);
         float A11, A12, A22, Dinv;
@@ -587,9 +583,8 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
                 sx0 = patch_origin(inx, Lw); sy0 = patch_origin(iny, Lh);
                 __syncwarp();
-                offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, apron, sx0, sy0, jp, R);
-                cp_async_commit();
-                cp_async_wait<0>();
+                offJ = stage_tgt(P, level, plane_b, sx0, sy0, jp, S, R);
+                stage_wait_tgt(S);
                 __syncwarp();
                 staged = true;
             }
@@ -619,9 +614,8 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
                 sx0 = patch_origin(inx, Lw); sy0 = patch_origin(iny, Lh);
                 __syncwarp();
-                offJ = stage_u8<kJPatch>(JB, Lp, Lw, Lh, apron, sx0, sy0, jp, R);
-                cp_async_commit();
-                cp_async_wait<0>();
+                offJ = stage_tgt(P, level, plane_b, sx0, sy0, jp, S, R);
+                stage_wait_tgt(S);
                 __syncwarp();
             }
             const int bx = offJ + (inx - sx0), by = iny - sy0;
@@ -642,7 +636,8 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             er = __fdiv_rn(__ll2float_rn(se), (float)(32 * kW * kW));
         }
     }
-    cp_async_wait<0>();
+    stage_wait_src(S);                           // (a skipped level may leave a prefetch outstanding)
+    stage_wait_tgt(S);
     __syncwarp();                                // the patches are free for the next solve
     o.x = next_x; o.y = next_y; o.st = st; o.err = st ? er : 0.f;
 }
@@ -653,9 +648,11 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
 __global__ void __launch_bounds__(kWarpsPerCta * 32, PSNW_LK_MINB)
 lk_w21_kernel(const __grid_constant__ LkParams P)
 {
-    __shared__ __align__(16) uint32_t smem[kWarpsPerCta * kWarpSmemWords];
+    __shared__ __align__(128) uint8_t smem[kWarpsPerCta * kWarpSmemBytes];
+    __shared__ __align__(8) uint64_t bars[kWarpsPerCta][2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t *ip = smem + wib * kWarpSmemWords, *jp = ip + kIWords, *dxp = jp + kJWords;
+    uint32_t *dxp = reinterpret_cast<uint32_t *>(smem + wib * kWarpSmemBytes);
+    uint32_t *ip = dxp + kDBytes / 4, *jp = ip + kIBytes / 4;
 
     WarpRole R;
     R.lane = lane;
@@ -664,9 +661,13 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
         const int r0 = lane, r1 = R.two ? lane + 32 : 62;
         R.row0 = r0 / 3; R.col0 = 7 * (r0 - 3 * R.row0);
         R.row1 = r1 / 3; R.col1 = 7 * (r1 - 3 * R.row1);
-        R.dr3 = R.row0; R.g3 = lane - 3 * R.row0;
-        R.dr7 = lane / 7; R.g7 = lane - 7 * R.dr7;
     }
+    Stage S;
+    S.bar_src = smem_u32(&bars[wib][0]); S.bar_tgt = smem_u32(&bars[wib][1]);
+    S.ph_src = S.ph_tgt = 0u;
+    S.pend_src = S.pend_tgt = false;
+    if (lane == 0) { mbar_init(S.bar_src, 1); mbar_init(S.bar_tgt, 1); }
+    __syncwarp();
 
     const bool persistent = P.work != nullptr;
     for (int it = 0;; ++it) {
@@ -695,7 +696,7 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
 #pragma unroll 1
         for (int pass = 0; pass < npass; ++pass) {
             const float sx = pass ? f.x : p0.x, sy = pass ? f.y : p0.y;
-            solve_w21(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, R, cur);
+            solve_w21(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, S, R, cur);
             if (pass) b = cur; else f = cur;
         }
         finish_point(P, job, k, p0, f, b, lane);
