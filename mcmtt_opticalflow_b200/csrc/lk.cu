@@ -492,7 +492,8 @@ __device__ __forceinline__ int stage_tgt(const LkParams &P, int level, int plane
 }
 
 __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_level, float px, float py,
-                                       uint32_t *ip, uint32_t *jp, uint32_t *dxp, Stage &S, const WarpRole &R, Solve &o)
+                                       uint32_t *ip, uint32_t *jp, uint32_t *dxp, Stage &S, const WarpRole &R, bool want_err,
+                                       Solve &o)
 {
     constexpr float half = (kW - 1) * 0.5f;
     float next_x = 0.f, next_y = 0.f, er = 0.f;
@@ -609,6 +610,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             const float qx = __fsub_rn(next_x, half), qy = __fsub_rn(next_y, half);
             const int inx = __float2int_rd(qx), iny = __float2int_rd(qy);
             if (window_oob(inx, iny, Lw, Lh)) { st = 0; continue; }
+            if (!want_err) continue;             // the backward pass of the FB check only needs position and status
             bilinear_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
             const int jt = (w00 & 0xffff) | (w01 << 16), jb = (w10 & 0xffff) | (w11 << 16);
             if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
@@ -696,7 +698,7 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
 #pragma unroll 1
         for (int pass = 0; pass < npass; ++pass) {
             const float sx = pass ? f.x : p0.x, sy = pass ? f.y : p0.y;
-            solve_w21(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, S, R, cur);
+            solve_w21(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, S, R, pass == 0, cur);
             if (pass) b = cur; else f = cur;
         }
         finish_point(P, job, k, p0, f, b, lane);
