@@ -549,16 +549,17 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
                     const uint32_t n0 = d0[k + 1], n1 = d1[k + 1];
-                    int ix = (sext16(q0) * w00 + sext16(n0) * w01 + sext16(q1) * w10 + sext16(n1) * w11 + (1 << 13)) >> 14;
-                    int iy = (((int)q0 >> 16) * w00 + ((int)n0 >> 16) * w01 + ((int)q1 >> 16) * w10 + ((int)n1 >> 16) * w11 + (1 << 13)) >> 14;
-                    if (run && !R.two) { ix = 0; iy = 0; }
-                    tC[run * 7 + k] = 256 - ((v[k] >> 9) << 9);
+                    const int ix = (sext16(q0) * w00 + sext16(n0) * w01 + sext16(q1) * w10 + sext16(n1) * w11 + (1 << 13)) >> 14;
+                    const int iy = (((int)q0 >> 16) * w00 + ((int)n0 >> 16) * w01 + ((int)q1 >> 16) * w10 + ((int)n1 >> 16) * w11 + (1 << 13)) >> 14;
+                    tC[run * 7 + k] = 256 - (v[k] & ~511);      // 256 - 512 * I
                     tIx[run * 7 + k] = ix;
                     tIy[run * 7 + k] = iy;
                     a11[run] += ix * ix; a12[run] += ix * iy; a22[run] += iy * iy;
                     q0 = n0; q1 = n1;
                 }
             }
+            // lane 31 owns a single run: its second one re-reads run 62 and is dropped from every sum
+            if (!R.two) { a11[1] = 0; a12[1] = 0; a22[1] = 0; }
         }
         __syncwarp();                            // every lane is done with the I / dI patches ...
         prefetch_src(P, plane_a, level - 1, px, py, ip, dxp, S, R);   // ... so the next level's copies may overwrite them
@@ -602,6 +603,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                     b2[run] += diff * tIy[run * 7 + k];
                 }
             }
+            if (!R.two) { b1[1] = 0; b2[1] = 0; }
             const long long sb1 = warp_sum_i32(b1[0] + b1[1]), sb2 = warp_sum_i32(b2[0] + b2[1]);
             if (lk_step(P, sb1, sb2, A11, A12, A22, Dinv, half, half, j, nx, ny, pdx, pdy, next_x, next_y)) break;
         }
