@@ -60,6 +60,26 @@ def test_box_update_random_vs_oracle(ctx, oracle):
             assert g_counts[t] == len(inl)
 
 
+def test_box_update_maximum_target_size(ctx, oracle):
+    """PSNW_MAX_PTS_PER_TARGET = 4096 features in one target (the capacity of the shared-memory arrays), next to a
+    3000-feature and an empty one."""
+    rng = np.random.default_rng(7)
+    ns = np.array([4096, 0, 3000])
+    off = np.concatenate([[0], np.cumsum(ns)]).astype(np.int32)
+    pre = rng.uniform(0, 1900, size=(off[-1], 2)).astype(np.float32)
+    cur = (pre + rng.uniform(-3, 3, size=2) + np.round(rng.normal(0, 1.0, size=pre.shape) * 8) / 8).astype(np.float32)
+    boxes = np.array([[100.0, 80.0, 61.5, 140.0], [5.0, 5.0, 40.0, 96.0], [700.0, 300.0, 33.25, 80.0]])
+    status = (rng.random(off[-1]) < 0.9).astype(np.uint8)
+    for st in (None, status):
+        g_boxes, g_mask, g_counts = ctx.box_update(boxes, pre, cur, off, status=st)
+        for t in range(3):
+            s = slice(off[t], off[t + 1])
+            b, inl = oracle.local_search_klt(boxes[t], pre[s], cur[s], None if st is None else st[s])
+            assert np.array_equal(g_boxes[t], b), t
+            assert np.array_equal(np.flatnonzero(g_mask[s]), inl), t
+            assert g_counts[t] == len(inl)
+
+
 def test_min_eig_map_bit_exact_and_selection(golden, oracle):
     a = golden["a"]
     with klt.KLTContext(a.shape[1], a.shape[0], levels=2) as c:

@@ -134,6 +134,34 @@ def test_border_seeds_all_levels(oracle, w, h):
     assert st.mean() > 0.05
 
 
+def test_ragged_many_jobs_batch(oracle):
+    """One launch over 11 jobs -- more than fit in the kernel parameters, so the descriptors travel through the staging
+    path -- on two cameras and several slot pairs, with empty jobs in between and ragged sizes."""
+    w, h = 320, 240
+    cams = [synth.Camera(w, h, 5, cam=c) for c in range(2)]
+    rng = np.random.default_rng(3)
+    with klt.KLTContext(w, h, n_cameras=2, levels=4, fb_thresh=1.0, max_points=1 << 13) as ctx:
+        frames = [[c.frame(k) for k in range(3)] for c in cams]
+        for k in range(3):
+            ctx.push_frames([frames[0][k], frames[1][k]])
+        sizes = [0, 1, 37, 0, 256, 5, 64, 0, 100, 33, 2]
+        jobs = []
+        for j, n in enumerate(sizes):
+            cam, (sf, st_) = j % 2, [(1, 0), (2, 1), (2, 0), (0, 1)][j % 4]
+            pts = rng.uniform(-5, [w + 5, h + 5], size=(n, 2)).astype(np.float32)
+            jobs.append(dict(cam=cam, slot_from=sf, slot_to=st_, n_pts=n, pts=pts, out=np.zeros((n, 2), np.float32),
+                             status=np.zeros(n, np.uint8), err=np.zeros(n, np.float32), fb_err=np.zeros(n, np.float32)))
+        ctx.track_batch(jobs)
+    pyr = [[oracle.build_pyramid(f, 3) for f in fr] for fr in frames]
+    for j in jobs:
+        if j["n_pts"] == 0:
+            continue
+        a, b = pyr[j["cam"]][2 - j["slot_from"]], pyr[j["cam"]][2 - j["slot_to"]]      # slot k = k frames ago
+        g_o, g_st, g_er, g_fb = oracle.track_fb(a, b, j["pts"], fb_thresh=1.0, exact_sums=True)
+        _tight(j["out"], j["status"], j["err"], g_o, g_st, g_er, ("job", j["n_pts"]))
+        assert np.abs(j["fb_err"] - g_fb).max() <= 1e-4
+
+
 def test_reference_faithful_per_target_windows(oracle):
     """Reference call pattern: window (int)box.w x (int)box.h per target (Tracker2D.cpp:877), default 4 levels."""
     w, h, ntgt = 768, 576, 12
