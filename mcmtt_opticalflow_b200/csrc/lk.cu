@@ -51,13 +51,21 @@ __device__ __forceinline__ long long warp_sum_ll(long long v)
     return v;
 }
 
-// exact warp sum of per-lane int32 partials whose total may exceed 32 bits: two REDUX
-__device__ __forceinline__ long long warp_sum_i32(int v)
+// exact warp sum of per-lane int32 partials whose total may exceed 32 bits: two REDUX (high and low halves);
+// the same sum as a float, rounded once: hi * 2^16 + lo is formed exactly inside the fma (|hi| < 2^24, lo < 2^24), so the
+// result equals __ll2float_rn of the 64-bit sum without 64-bit integer arithmetic or the slow I2F.S64
+struct WarpSum {
+    int hi;
+    unsigned lo;
+};
+__device__ __forceinline__ WarpSum warp_sum_split(int v)
 {
-    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
-    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xffff));
-    return ((long long)hi << 16) + (long long)lo;
+    WarpSum r;
+    r.hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    r.lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xffff));
+    return r;
 }
+__device__ __forceinline__ float sum_to_float(WarpSum s) { return __fmaf_rn((float)s.hi, 65536.f, (float)s.lo); }
 
 struct Solve {
     float x, y;   // nextPts
@@ -66,12 +74,12 @@ struct Solve {
 };
 
 // 2x2 system shared by both kernels; returns false when the level is rejected (min-eig / determinant gate)
-__device__ __forceinline__ bool make_system(long long s11, long long s12, long long s22, int ww, int wh, float min_eig_thr,
+__device__ __forceinline__ bool make_system(float f11, float f12, float f22, int ww, int wh, float min_eig_thr,
                                             float &A11, float &A12, float &A22, float &Dinv)
 {
-    A11 = __fmul_rn(__ll2float_rn(s11), kFltScale);
-    A12 = __fmul_rn(__ll2float_rn(s12), kFltScale);
-    A22 = __fmul_rn(__ll2float_rn(s22), kFltScale);
+    A11 = __fmul_rn(f11, kFltScale);
+    A12 = __fmul_rn(f12, kFltScale);
+    A22 = __fmul_rn(f22, kFltScale);
     const float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     const float dd = __fsub_rn(A11, A22);
     const float rad = __fsqrt_rn(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12)));
@@ -85,11 +93,11 @@ __device__ __forceinline__ bool make_system(long long s11, long long s12, long l
 //   delta.ddot(delta) <= eps^2 is a double comparison in OpenCV; the float value decides it whenever it is further
 //   than 1e-5 (relative) from the threshold, the double product is only formed inside that band.
 //   fabs((double)(float)s) < 0.01 is exactly fabsf(s) <= 0.01f (0.01f is the largest float below the double 0.01).
-__device__ __forceinline__ bool lk_step(const LkParams &P, long long sb1, long long sb2, float A11, float A12, float A22,
+__device__ __forceinline__ bool lk_step(const LkParams &P, float fb1, float fb2, float A11, float A12, float A22,
                                         float Dinv, float half_x, float half_y, int j,
                                         float &nx, float &ny, float &pdx, float &pdy, float &next_x, float &next_y)
 {
-    const float b1 = __fmul_rn(__ll2float_rn(sb1), kFltScale), b2 = __fmul_rn(__ll2float_rn(sb2), kFltScale);
+    const float b1 = __fmul_rn(fb1, kFltScale), b2 = __fmul_rn(fb2, kFltScale);
     const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dinv);
     const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dinv);
     nx = __fadd_rn(nx, dx);
@@ -195,7 +203,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
         }
         block_sum3(s11, s12, s22, red, rsel, tid);
         float A11, A12, A22, Dinv;
-        if (!make_system(s11, s12, s22, ww, wh, P.min_eig, A11, A12, A22, Dinv)) {
+        if (!make_system(__ll2float_rn(s11), __ll2float_rn(s12), __ll2float_rn(s22), ww, wh, P.min_eig, A11, A12, A22, Dinv)) {
             if (level == 0) st = 0;
             continue;
         }
@@ -233,7 +241,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 }
             }
             { long long z = 0; block_sum3(sb1, sb2, z, red, rsel, tid); }
-            if (lk_step(P, sb1, sb2, A11, A12, A22, Dinv, half_x, half_y, j, nx, ny, pdx, pdy, next_x, next_y)) break;
+            if (lk_step(P, __ll2float_rn(sb1), __ll2float_rn(sb2), A11, A12, A22, Dinv, half_x, half_y, j, nx, ny, pdx, pdy, next_x, next_y)) break;
         }
 
         if (st && level == 0) {
@@ -565,7 +573,8 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
         prefetch_src(P, plane_a, level - 1, px, py, ip, dxp, S, R);   // ... so the next level's copies may overwrite them
         stage_wait_tgt(S);                       // the target patch has landed
         __syncwarp();
-        const long long s11 = warp_sum_i32(a11[0] + a11[1]), s12 = warp_sum_i32(a12[0] + a12[1]), s22 = warp_sum_i32(a22[0] + a22[1]);
+        const float s11 = sum_to_float(warp_sum_split(a11[0] + a11[1])), s12 = sum_to_float(warp_sum_split(a12[0] + a12[1])),
+                    s22 = sum_to_float(warp_sum_split(a22[0] + a22[1]));
         float A11, A12, A22, Dinv;
         if (!make_system(s11, s12, s22, kW, kW, P.min_eig, A11, A12, A22, Dinv)) {
             if (level == 0) st = 0;
@@ -604,7 +613,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                 }
             }
             if (!R.two) { b1[1] = 0; b2[1] = 0; }
-            const long long sb1 = warp_sum_i32(b1[0] + b1[1]), sb2 = warp_sum_i32(b2[0] + b2[1]);
+            const float sb1 = sum_to_float(warp_sum_split(b1[0] + b1[1])), sb2 = sum_to_float(warp_sum_split(b2[0] + b2[1]));
             if (lk_step(P, sb1, sb2, A11, A12, A22, Dinv, half, half, j, nx, ny, pdx, pdy, next_x, next_y)) break;
         }
 
@@ -636,8 +645,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                     }
                 }
             }
-            const long long se = warp_sum_i32(e);
-            er = __fdiv_rn(__ll2float_rn(se), (float)(32 * kW * kW));
+            er = __fdiv_rn(sum_to_float(warp_sum_split(e)), (float)(32 * kW * kW));
         }
     }
     stage_wait_src(S);                           // (a skipped level may leave a prefetch outstanding)
