@@ -157,6 +157,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
     int rsel = 0;                              // reduction scratch toggles between two slots
     const bool acc32 = npx <= 60 * kGenThreads;   // 60 * 8160 * 4080 < 2^31: per-thread partial sums fit 32 bits
     while (lx0 >= ww) { lx0 -= ww; ly0++; }
+    const int step_y = kGenThreads / ww, step_x = kGenThreads - step_y * ww;   // one stride of kGenThreads pixels in (x, y)
 
     for (int level = max_level; level >= 0; --level) {
         const LevelGeom &L = P.lv[level];
@@ -183,6 +184,24 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
         long long s11 = 0, s12 = 0, s22 = 0;
         {
             int x = lx0, y = ly0;
+            if (acc32 && ipx >= 0 && ipy >= 0 && ipx + ww < L.w && ipy + wh < L.h) {
+                // window (plus its bilinear ring) inside the frame: no border arithmetic, 32-bit partial sums
+                int a11 = 0, a12 = 0, a22 = 0;
+                for (int p = tid; p < npx; p += kGenThreads) {
+                    const uint8_t *r0 = IA + (ipy + y) * ipitch + (ipx + x), *r1 = r0 + ipitch;
+                    const int ival = (r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9;
+                    const short2 *d0 = DA + (ipy + y) * L.pitch + (ipx + x), *d1 = d0 + L.pitch;
+                    const short2 d00 = d0[0], d01 = d0[1], d10 = d1[0], d11 = d1[1];
+                    const int ix = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
+                    const int iy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
+                    Iw[p] = (short)ival;
+                    dIw[p] = make_short2((short)ix, (short)iy);
+                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                    x += step_x; y += step_y;
+                    if (x >= ww) { x -= ww; y++; }
+                }
+                s11 = a11; s12 = a12; s22 = a22;
+            } else
             for (int p = tid; p < npx; p += kGenThreads) {
                 const int X = ipx + x, Y = ipy + y;
                 const int ival = sample_u8(IA, ipitch, L.w, L.h, X, Y, w00, w01, w10, w11);
@@ -197,8 +216,8 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 Iw[p] = (short)ival;
                 dIw[p] = make_short2((short)ix, (short)iy);
                 s11 += (long long)(ix * ix); s12 += (long long)(ix * iy); s22 += (long long)(iy * iy);
-                x += kGenThreads;
-                while (x >= ww) { x -= ww; y++; }
+                x += step_x; y += step_y;
+                if (x >= ww) { x -= ww; y++; }
             }
         }
         block_sum3(s11, s12, s22, red, rsel, tid);
@@ -227,8 +246,8 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                     const int diff = ((r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9) - Iw[p];
                     const short2 d = dIw[p];
                     a1 += diff * d.x; a2 += diff * d.y;
-                    x += kGenThreads;
-                    while (x >= ww) { x -= ww; y++; }
+                    x += step_x; y += step_y;
+                    if (x >= ww) { x -= ww; y++; }
                 }
                 sb1 = a1; sb2 = a2;
             } else {
@@ -236,8 +255,8 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                     const int diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
                     const short2 d = dIw[p];
                     sb1 += (long long)(diff * d.x); sb2 += (long long)(diff * d.y);
-                    x += kGenThreads;
-                    while (x >= ww) { x -= ww; y++; }
+                    x += step_x; y += step_y;
+                    if (x >= ww) { x -= ww; y++; }
                 }
             }
             { long long z = 0; block_sum3(sb1, sb2, z, red, rsel, tid); }
@@ -254,8 +273,8 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             for (int p = tid; p < npx; p += kGenThreads) {
                 const int diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
                 se += diff < 0 ? -diff : diff;
-                x += kGenThreads;
-                while (x >= ww) { x -= ww; y++; }
+                x += step_x; y += step_y;
+                if (x >= ww) { x -= ww; y++; }
             }
             { long long z0 = 0, z1 = 0; block_sum3(se, z0, z1, red, rsel, tid); }
             er = __fdiv_rn(__ll2float_rn(se), (float)(32 * ww * wh));
