@@ -204,6 +204,8 @@ class GpuRig:
         src = self.h_frames if host else self.d_frames
         ptrs = (C.c_void_p * self.ncam)(*[src[c][t_idx].data_ptr() for c in range(self.ncam)])
         mem = (self.klt.MEM_PINNED if host else self.klt.MEM_DEVICE) | (self.klt.MEM_OVERLAP if overlap else 0)
+        if overlap and not self.grid:
+            mem |= self.klt.PUSH_EIG         # the next step detects on this frame: its Shi-Tomasi map is built with the pyramid
         self.ctx._ck(self.ctx.lib.psnw_push_frames(self.ctx._h, self.ncam, self.cams.ctypes.data, ptrs, self.w, t_idx, mem))
 
     def _detect(self, t_idx, seeds, counts, mem):

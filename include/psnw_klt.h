@@ -64,6 +64,10 @@ enum { PSNW_MEM_HOST = 0, PSNW_MEM_PINNED = 1, PSNW_MEM_DEVICE = 2 };
  *    first makes the context stream wait for the push (device-side, no host block).  The caller keeps the source
  *    frames unchanged until psnw_sync or psnw_join. */
 #define PSNW_MEM_OVERLAP 0x100
+/* OR-ed into the mem_flags of psnw_push_frame(s): also compute the Shi-Tomasi min-eigenvalue map of the pushed frames
+ * (a psnw_klt_detect on them will follow and then finds it ready).  Each camera keeps two maps, so the map of a frame
+ * ingested ahead (PSNW_MEM_OVERLAP) never disturbs a detection still reading the map of the frame before. */
+#define PSNW_PUSH_EIG 0x200
 
 /* psnw_box_update estimators */
 enum {

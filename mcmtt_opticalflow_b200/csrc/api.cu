@@ -44,7 +44,7 @@ struct psnw_ctx {
     cudaStream_t up = nullptr;
     cudaEvent_t ev_up = nullptr;
     bool up_pending = false;
-    static constexpr int kReaderRing = 8;
+    static constexpr int kReaderRing = 32;
     cudaEvent_t rd_ev[kReaderRing] = {};
     uint64_t rd_seq = 0;
     std::vector<uint64_t> plane_rd_seq;
@@ -69,7 +69,10 @@ struct psnw_ctx {
     DevBuf det_desc;                      // target descriptors + staged outputs (detect; may run on the aux stream)
     DevBuf cand;                          // detect candidate scratch
     DevBuf bgr;                           // BGR staging for psnw_push_frames_bgr
-    std::vector<float *> eig;             // per camera min-eig map (level-0 pitch), lazily allocated
+    // Shi-Tomasi maps (level-0 pitch), lazily allocated: TWO per camera ([2 cam], [2 cam + 1]) so that the map of the frame
+    // just pushed can be computed (PSNW_PUSH_EIG) while a detection still reads the map of the frame before; eig_tag =
+    // push counter of the frame a buffer holds; readers are tracked like ring planes (plane_rd_seq[planes + index])
+    std::vector<float *> eig;
     std::vector<uint64_t> eig_tag;
     std::vector<uint8_t *> fmap;          // per camera NMS'd FAST score map (GridFAST), lazily allocated
     std::vector<uint64_t> fmap_tag;
@@ -342,6 +345,68 @@ int advance_ring(psnw_ctx *ctx, int n, const int *cams, std::vector<int> &planes
     return PSNW_OK;
 }
 
+// make `st` wait for the launches already enqueued that read the listed resources (ring planes / min-eig buffers)
+int wait_readers(psnw_ctx *ctx, cudaStream_t st, const std::vector<int> &ids)
+{
+    uint64_t newest = 0;
+    for (int id : ids) newest = std::max(newest, ctx->plane_rd_seq[id]);
+    if (newest == 0) return PSNW_OK;
+    if (newest + psnw_ctx::kReaderRing > ctx->rd_seq) {
+        CK(cudaStreamWaitEvent(st, ctx->rd_ev[newest % psnw_ctx::kReaderRing], 0));
+    } else {                                            // its event was reused since: wait for every recent reader
+        for (int i = 0; i < psnw_ctx::kReaderRing; ++i) CK(cudaStreamWaitEvent(st, ctx->rd_ev[i], 0));
+    }
+    return PSNW_OK;
+}
+
+// Shi-Tomasi map of every (camera, slot) of `cs`, computed on `stream` unless a buffer already holds it; bufs[i] receives
+// the index of the buffer (into ctx->eig) with the map of cs[i].  A map is written over the older of the camera's two
+// buffers.  `side_stream`: the caller is not ordered after earlier detections (the eager path of an overlapped push), so
+// the stream first waits for the readers of the buffers it overwrites.
+int ensure_min_eig(psnw_ctx *ctx, const std::vector<std::pair<int, int>> &cs, cudaStream_t stream,
+                          std::vector<int> *bufs = nullptr, bool side_stream = false)
+{
+    const LevelGeom &l0 = ctx->pyr.lv[0];
+    EigList el;
+    el.n = 0;
+    std::vector<int> todo_plane, todo_buf;
+    if (bufs) bufs->assign(cs.size(), -1);
+    for (size_t i = 0; i < cs.size(); ++i) {
+        const int cam = cs[i].first, plane = plane_of(ctx, cam, cs[i].second);
+        for (int b = 0; b < 2; ++b)
+            if (!ctx->eig[2 * cam + b]) {
+                if (cudaMalloc(&ctx->eig[2 * cam + b], sizeof(float) * (size_t)l0.plane_px) != cudaSuccess)
+                    return fail(ctx, PSNW_ENOMEM, "cudaMalloc min-eig map", cudaGetLastError());
+                ctx->eig_tag[2 * cam + b] = 0;
+            }
+        const uint64_t want = ctx->plane_seq[plane];
+        int b = ctx->eig_tag[2 * cam] == want ? 2 * cam : ctx->eig_tag[2 * cam + 1] == want ? 2 * cam + 1 : -1;
+        if (b < 0) {
+            b = ctx->eig_tag[2 * cam] <= ctx->eig_tag[2 * cam + 1] ? 2 * cam : 2 * cam + 1;      // the older map goes
+            ctx->eig_tag[b] = want;
+            todo_plane.push_back(plane); todo_buf.push_back(b);
+        }
+        if (bufs) (*bufs)[i] = b;
+    }
+    if (todo_buf.empty()) return PSNW_OK;
+    if (side_stream) {
+        std::vector<int> ids;
+        for (int b : todo_buf) ids.push_back(ctx->planes + b);
+        if (int rc = wait_readers(ctx, stream, ids)) return rc;
+    }
+    for (size_t i = 0; i < todo_buf.size(); ++i) {
+        el.plane[el.n] = todo_plane[i];
+        el.eig[el.n] = ctx->eig[todo_buf[i]];
+        if (++el.n == 24 || i + 1 == todo_buf.size()) {
+            const int r = launch_min_eig(l0, el, stream);
+            if (r < 0) return fail(ctx, PSNW_ECUDA, "min_eig_kernel launch", cudaGetLastError());
+            ctx->launches += r;
+            el.n = 0;
+        }
+    }
+    return PSNW_OK;
+}
+
 // Stream a push runs on.  PSNW_MEM_OVERLAP (pinned / device memory only): the upload stream, made to wait for the launches
 // already enqueued that read the recycled planes -- and for nothing else, so the push overlaps the LK launch in flight.
 int push_stream(psnw_ctx *ctx, bool overlap, const std::vector<int> &planes, cudaStream_t *st)
@@ -349,15 +414,7 @@ int push_stream(psnw_ctx *ctx, bool overlap, const std::vector<int> &planes, cud
     *st = ctx->stream;
     if (!overlap) return PSNW_OK;
     *st = ctx->up;
-    uint64_t newest = 0;
-    for (int p : planes) newest = std::max(newest, ctx->plane_rd_seq[p]);
-    if (newest == 0) return PSNW_OK;
-    if (newest + psnw_ctx::kReaderRing > ctx->rd_seq) {
-        CK(cudaStreamWaitEvent(ctx->up, ctx->rd_ev[newest % psnw_ctx::kReaderRing], 0));
-    } else {                                            // its event was reused since: wait for every recent reader
-        for (int i = 0; i < psnw_ctx::kReaderRing; ++i) CK(cudaStreamWaitEvent(ctx->up, ctx->rd_ev[i], 0));
-    }
-    return PSNW_OK;
+    return wait_readers(ctx, ctx->up, planes);
 }
 
 int push_done(psnw_ctx *ctx, bool overlap)
@@ -413,9 +470,9 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     ctx->head.assign(p->n_cameras, p->ring_slots - 1);
     ctx->held.assign(p->n_cameras, 0);
     ctx->plane_seq.assign(ctx->planes, 0);
-    ctx->plane_rd_seq.assign(ctx->planes, 0);
-    ctx->eig.assign(p->n_cameras, nullptr);
-    ctx->eig_tag.assign(p->n_cameras, 0);
+    ctx->plane_rd_seq.assign(ctx->planes + 2 * p->n_cameras, 0);   // ring planes, then the min-eig buffers
+    ctx->eig.assign(2 * p->n_cameras, nullptr);
+    ctx->eig_tag.assign(2 * p->n_cameras, 0);
     ctx->fmap.assign(p->n_cameras, nullptr);
     ctx->fmap_tag.assign(p->n_cameras, 0);
     memset(&ctx->pyr, 0, sizeof ctx->pyr);
@@ -535,6 +592,7 @@ int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const
     for (int i = 0; i < n; ++i)
         if (!grays[i]) return fail(ctx, PSNW_EARG, "null frame pointer");
     const bool overlap = (mem_flags & PSNW_MEM_OVERLAP) != 0 && (mem_flags & 0xff) != PSNW_MEM_HOST;
+    const bool eager_eig = (mem_flags & PSNW_PUSH_EIG) != 0;
     mem_flags &= 0xff;
     std::vector<int> planes;
     int rc = advance_ring(ctx, n, cams, planes, overlap);
@@ -564,6 +622,16 @@ int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const
     }
     rc = build_pyramids(ctx, planes, st);
     if (rc) return rc;
+    if (eager_eig) {                          // PSNW_PUSH_EIG: a detection on these frames will follow
+        std::vector<std::pair<int, int>> cs;
+        for (int i = 0; i < n; ++i) cs.emplace_back(cams[i], 0);
+        rc = ensure_min_eig(ctx, cs, st, nullptr, overlap);
+        if (rc) return rc;
+        if (overlap) {                        // (on the context stream the image planes are ordered by the stream itself)
+            rc = note_readers(ctx, st, planes.data(), (int)planes.size());
+            if (rc) return rc;
+        }
+    }
     if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
     return push_done(ctx, overlap);
 }
@@ -826,36 +894,6 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
 }
 
 // min-eigenvalue maps of the (cam, slot) frames in `cs`, computed once per pushed frame (tag = push sequence)
-static int ensure_min_eig(psnw_ctx *ctx, const std::vector<std::pair<int, int>> &cs, cudaStream_t stream)
-{
-    const LevelGeom &l0 = ctx->pyr.lv[0];
-    EigList el;
-    el.n = 0;
-    for (const auto &c : cs) {
-        const int cam = c.first, plane = plane_of(ctx, cam, c.second);
-        if (!ctx->eig[cam]) {
-            if (cudaMalloc(&ctx->eig[cam], sizeof(float) * (size_t)l0.plane_px) != cudaSuccess)
-                return fail(ctx, PSNW_ENOMEM, "cudaMalloc min-eig map", cudaGetLastError());
-            ctx->eig_tag[cam] = 0;
-        }
-        if (ctx->eig_tag[cam] == ctx->plane_seq[plane]) continue;
-        ctx->eig_tag[cam] = ctx->plane_seq[plane];
-        el.plane[el.n] = plane;
-        el.eig[el.n] = ctx->eig[cam];
-        if (++el.n == 24) {
-            const int r = launch_min_eig(l0, el, stream);
-            if (r < 0) return fail(ctx, PSNW_ECUDA, "min_eig_kernel launch", cudaGetLastError());
-            ctx->launches += r;
-            el.n = 0;
-        }
-    }
-    if (el.n) {
-        const int r = launch_min_eig(l0, el, stream);
-        if (r < 0) return fail(ctx, PSNW_ECUDA, "min_eig_kernel launch", cudaGetLastError());
-        ctx->launches += r;
-    }
-    return PSNW_OK;
-}
 
 int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs, int max_per_target,
                           float quality, float min_dist, int mem_flags)
@@ -892,8 +930,11 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
         CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
         st = ctx->aux;
     }
-    rc = ensure_min_eig(ctx, cs, st);
+    std::vector<int> eig_buf;                 // per cs entry: the buffer holding its Shi-Tomasi map
+    rc = ensure_min_eig(ctx, cs, st, &eig_buf);
     if (rc) return rc;
+    std::vector<int> eig_of_cam(ctx->p.n_cameras, -1);
+    for (size_t i = 0; i < cs.size(); ++i) eig_of_cam[cs[i].first] = eig_buf[i];
     {
         std::vector<int> rd;
         for (const auto &c : cs) rd.push_back(plane_of(ctx, c.first, c.second));
@@ -931,7 +972,7 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
             cand_total += (size_t)d.cand_cap;
             max_area = std::max(max_area, d.cand_cap);
             max_tile = std::max(max_tile, (d.x1 - d.x0 + 2) * (d.y1 - d.y0 + 2));
-            d.eig = ctx->eig[J.cam];
+            d.eig = ctx->eig[eig_of_cam[J.cam]];
             d.out = dev ? reinterpret_cast<float2 *>(J.pts_xy) + (size_t)t * max_per_target : s_out + (size_t)(t0 + t) * max_per_target;
             d.count = dev ? J.counts + t : s_cnt + t0 + t;
         }
@@ -951,6 +992,12 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
                                        max_area, max_tile, st);
     if (r < 0) return fail(ctx, PSNW_ECUDA, "detect_select_kernel launch", cudaGetLastError());
     ctx->launches += r;
+    {                                         // the selection reads the min-eig buffers: an eager map of a later push waits for it
+        std::vector<int> rd;
+        for (int b : eig_buf) rd.push_back(ctx->planes + b);
+        rc = note_readers(ctx, st, rd.data(), (int)rd.size());
+        if (rc) return rc;
+    }
     if (!dev) {
         t0 = 0;
         for (int j = 0; j < n_jobs; ++j) {
@@ -1168,9 +1215,10 @@ int psnw_read_min_eig(psnw_ctx *ctx, int cam, int slot, float *eig_out)
     const LevelGeom &l0 = ctx->pyr.lv[0];
     int rc = join_aux(ctx);
     if (rc) return rc;
-    rc = ensure_min_eig(ctx, {{cam, slot}}, ctx->stream);
+    std::vector<int> buf;
+    rc = ensure_min_eig(ctx, {{cam, slot}}, ctx->stream, &buf);
     if (rc) return rc;
-    float *eig = ctx->eig[cam];
+    float *eig = ctx->eig[buf[0]];
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy2D(eig_out, (size_t)l0.w * 4, eig, (size_t)l0.pitch * 4, (size_t)l0.w * 4, l0.h, cudaMemcpyDeviceToHost));
     return PSNW_OK;

@@ -21,6 +21,7 @@ LIB_PATH = os.environ.get("PSNW_KLT_LIB") or os.path.join(_HERE, "libpsnw_klt.so
 OK, EARG, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4
 MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
 MEM_OVERLAP = 0x100
+PUSH_EIG = 0x200
 BOX_REFERENCE = 0
 _ERR = {EARG: "PSNW_EARG", ECUDA: "PSNW_ECUDA", ENOMEM: "PSNW_ENOMEM", ESTATE: "PSNW_ESTATE"}
 

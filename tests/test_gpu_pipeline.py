@@ -76,3 +76,38 @@ def test_overlapped_push_then_readers_wait(oracle):
         assert np.array_equal(eig, oracle.min_eig_map(f1))
         for t in range(4):
             assert np.array_equal(seeds[t, :counts[t]], oracle.detect(f1, cam.boxes(1)[t], 30, 0.01, 3.0, eig=eig))
+
+
+def test_eager_min_eig_under_overlapped_detect(oracle):
+    """PSNW_PUSH_EIG: the Shi-Tomasi map of the frame ingested ahead is built on the upload stream while an overlapped
+    detection may still read the map of the frame before (two maps per camera).  Corners must equal the oracle's on every
+    frame, and the cached map must be the one of the right frame."""
+    import torch
+    w, h, ntgt, per = 384, 288, 6, 40
+    cam = synth.Camera(w, h, ntgt, cam=5)
+    frames = [cam.frame(k) for k in range(5)]
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    dev = torch.device("cuda", 0)
+    seeds = [torch.zeros((ntgt, per, 2), dtype=torch.float32, device=dev) for _ in frames]
+    counts = [torch.zeros(ntgt, dtype=torch.int32, device=dev) for _ in frames]
+    with klt.KLTContext(w, h, levels=3) as ctx:
+        ctx.push_frames([pinned[0].data_ptr()], [0], 0, klt.MEM_PINNED, pitch=w)
+        for k in range(len(frames)):
+            boxes = np.ascontiguousarray(cam.boxes(k), np.float64)
+            job = (klt.DetectJob * 1)()
+            job[0].cam, job[0].slot, job[0].boxes, job[0].n_targets = 0, 0, boxes.ctypes.data, ntgt
+            job[0].pts_xy, job[0].counts = seeds[k].data_ptr(), counts[k].data_ptr()
+            ctx._ck(ctx.lib.psnw_klt_detect_batch(ctx._h, job, 1, per, 0.01, 3.0, klt.MEM_DEVICE | klt.MEM_OVERLAP))
+            if k + 1 < len(frames):           # ingest the next frame, with its map, while the detection runs
+                ctx.push_frames([pinned[k + 1].data_ptr()], [0], k + 1, klt.MEM_PINNED | klt.MEM_OVERLAP | klt.PUSH_EIG, pitch=w)
+        ctx.sync()
+        eig_last = ctx.read_min_eig(0, 0)
+        eig_prev = ctx.read_min_eig(0, 1)
+    assert np.array_equal(eig_last, oracle.min_eig_map(frames[-1]))
+    assert np.array_equal(eig_prev, oracle.min_eig_map(frames[-2]))
+    for k, f in enumerate(frames):
+        eig = oracle.min_eig_map(f)
+        s, c = seeds[k].cpu().numpy(), counts[k].cpu().numpy()
+        for t in range(ntgt):
+            want = oracle.detect(f, cam.boxes(k)[t], per, 0.01, 3.0, eig=eig)
+            assert c[t] == len(want) and np.array_equal(s[t, :c[t]], want), (k, t)
