@@ -187,18 +187,21 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             if (acc32 && ipx >= 0 && ipy >= 0 && ipx + ww < L.w && ipy + wh < L.h) {
                 // window (plus its bilinear ring) inside the frame: no border arithmetic, 32-bit partial sums
                 int a11 = 0, a12 = 0, a22 = 0;
+                // running offsets instead of a 2-D address per pixel: one stride of kGenThreads pixels, minus a row wrap
+                int oi = (ipy + y) * ipitch + (ipx + x), od = (ipy + y) * L.pitch + (ipx + x);
+                const int si = step_y * ipitch + step_x, sd = step_y * L.pitch + step_x;
                 for (int p = tid; p < npx; p += kGenThreads) {
-                    const uint8_t *r0 = IA + (ipy + y) * ipitch + (ipx + x), *r1 = r0 + ipitch;
+                    const uint8_t *r0 = IA + oi, *r1 = r0 + ipitch;
                     const int ival = (r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9;
-                    const short2 *d0 = DA + (ipy + y) * L.pitch + (ipx + x), *d1 = d0 + L.pitch;
+                    const short2 *d0 = DA + od, *d1 = d0 + L.pitch;
                     const short2 d00 = d0[0], d01 = d0[1], d10 = d1[0], d11 = d1[1];
                     const int ix = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
                     const int iy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
                     Iw[p] = (short)ival;
                     dIw[p] = make_short2((short)ix, (short)iy);
                     a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
-                    x += step_x; y += step_y;
-                    if (x >= ww) { x -= ww; y++; }
+                    x += step_x; oi += si; od += sd;
+                    if (x >= ww) { x -= ww; oi += ipitch - ww; od += L.pitch - ww; }
                 }
                 s11 = a11; s12 = a12; s22 = a22;
             } else
@@ -241,13 +244,15 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             if (acc32 && inx >= 0 && iny >= 0 && inx + ww < L.w && iny + wh < L.h) {
                 // window inside the frame and <= 60 pixels per thread: no border arithmetic, 32-bit partial sums
                 int a1 = 0, a2 = 0;
+                int oj = (iny + y) * ipitch + (inx + x);
+                const int sj = step_y * ipitch + step_x;
                 for (int p = tid; p < npx; p += kGenThreads) {
-                    const uint8_t *r0 = JB + (iny + y) * ipitch + (inx + x), *r1 = r0 + ipitch;
+                    const uint8_t *r0 = JB + oj, *r1 = r0 + ipitch;
                     const int diff = ((r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9) - Iw[p];
                     const short2 d = dIw[p];
                     a1 += diff * d.x; a2 += diff * d.y;
-                    x += step_x; y += step_y;
-                    if (x >= ww) { x -= ww; y++; }
+                    x += step_x; oj += sj;
+                    if (x >= ww) { x -= ww; oj += ipitch - ww; }
                 }
                 sb1 = a1; sb2 = a2;
             } else {
