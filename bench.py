@@ -39,7 +39,7 @@ WORKLOADS = {
     "c1": (768, 576, 1, 20, 100, 3),
     "c2": (768, 576, 4, 40, 100, 4),
     "c3": (1920, 1080, 1, 200, 256, 4),
-    "c4": (3840, 2160, 1, 0, 0, 5),     # dense grid KLT, stride 4 px: 959 x 539 = 516 901 seeds, track + FB only
+    "c4": (3840, 2160, 2, 0, 0, 5),     # 16-camera rig over 8 GPUs = 2 cameras per GPU; dense grid KLT, stride 4 px, track + FB only
 }
 CYCLE = 6                       # distinct time steps rendered per camera (played ping-pong)
 QUALITY, MIN_DIST = 0.01, 3.0   # psnw_klt_detect / goodFeaturesToTrack parameters
