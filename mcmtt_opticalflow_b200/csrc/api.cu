@@ -487,10 +487,7 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     }
 
     if (configure_lk_kernels() || configure_box_kernels() || configure_detect_kernels() || configure_fused_kernels()) return bail(PSNW_ECUDA);
-    {
-        const char *m = getenv("PSNW_LK_CTAS_PER_SM");     // bring-up: cap of the persistent grid
-        ctx->lk_ctas = lk_w21_resident_ctas(m ? atoi(m) : 0);
-    }
+    ctx->lk_ctas = lk_w21_resident_ctas(0);
     if (ctx->lk_ctas <= 0) return bail(PSNW_ECUDA);
     if (cudaMalloc(&ctx->lk_work, 2 * sizeof(unsigned)) != cudaSuccess) return bail(PSNW_ENOMEM);
     cudaMemsetAsync(ctx->lk_work, 0, 2 * sizeof(unsigned), ctx->stream);
