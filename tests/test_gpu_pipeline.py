@@ -111,3 +111,27 @@ def test_eager_min_eig_under_overlapped_detect(oracle):
         for t in range(ntgt):
             want = oracle.detect(f, cam.boxes(k)[t], per, 0.01, 3.0, eig=eig)
             assert c[t] == len(want) and np.array_equal(s[t, :c[t]], want), (k, t)
+
+
+def test_pipelined_bench_steps_are_periodic():
+    """Race hunt on the full pipelined step of bench.py (frame in flight, overlapped detection, eager Shi-Tomasi map,
+    persistent LK): the rig plays its frames ping-pong, so 50 free-running steps (no host sync in between) must repeat
+    bit for bit with the period of the frame sequence.  tools/soak.py runs the same check for thousands of steps."""
+    import hashlib
+    import torch
+    import bench
+    rig = bench.GpuRig("c1", 0, 0)
+    rig.prime(False)
+    period = 2 * bench.CYCLE - 2
+    snaps = []
+    with torch.cuda.stream(rig.stream):
+        for _ in range(5 * period):
+            rig.step(False)
+            snaps.append((rig.d_blob.clone(), rig.d_seeds[rig.which].clone()))
+        rig.ctx.sync()
+        rig.stream.synchronize()
+    sums = [hashlib.sha1(b.cpu().numpy().tobytes() + s.cpu().numpy().tobytes()).hexdigest() for b, s in snaps]
+    for k in range(2 * period, len(sums)):
+        assert sums[k] == sums[k - period], k
+    assert len(set(sums[2 * period:])) == period
+    rig.ctx.close()
