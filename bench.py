@@ -561,8 +561,14 @@ def main():
                     "algorithmic_bytes": alg, "ms": 1e3 * pyr_mean, "best_ms": 1e3 * pyr_best, "peak_source": peak_src}
         roofline["frames_in_flight_sweep"] = pyramid_sweep(rig, peak) if args.workload == "c2" else None
         lk_sec, st_frac = rig.time_track()
-        lk = {"kernel": "lk_w21_kernel (fwd+bwd fused)", "ms": 1e3 * lk_sec, "lk_solves_per_s": 2 * rig.npts / lk_sec,
-              "status_ok_frac": st_frac, "bound": "SM issue / shared memory (not HBM, not tensor) -- see DESIGN.md"}
+        lk = {"kernel": "lk_w21_kernel (fwd+bwd fused, persistent warps, TMA-staged patches)", "ms": 1e3 * lk_sec,
+              "lk_solves_per_s": 2 * rig.npts / lk_sec, "status_ok_frac": st_frac,
+              "bound": "SM issue slots (not HBM, not tensor) -- see DESIGN.md"}
+        if args.workload == "c2":
+            try:      # issue-slot utilisation and instruction count of the same launch from the committed ncu --set full capture
+                lk["ncu"] = json.load(open(os.path.join(ROOT, "profiles", "r01_lk_issue.json")))
+            except Exception:
+                pass
         line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8/int16 fixed point, f32 solve, f64 box", "data": "synthetic", "config": config,
