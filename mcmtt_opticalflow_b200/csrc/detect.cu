@@ -86,7 +86,7 @@ min_eig_kernel(const uint8_t *__restrict__ img_base, int w, int h, int pitch, in
     }
 }
 
-constexpr int kSelThreads = 256;
+constexpr int kSelThreads = 512;
 constexpr float kUnusedSlot = -1.0e6f;
 constexpr int kMaxAccepted = 1024;        // accepted-corner list kept in shared memory by the sorted path
 
@@ -195,7 +195,7 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
         while (n2 < nc) n2 <<= 1;
         for (int i = nc + tid; i < n2; i += kSelThreads) s_list[i] = 0ull;
         __syncthreads();
-        // each warp owns a contiguous segment of n2 / 8 keys: compare distances inside a segment only need
+        // each warp owns a contiguous segment of n2 / nwarps keys: compare distances inside a segment only need
         // __syncwarp; the few stages that cross segments take a block barrier (6 instead of ~60)
         const int seg = n2 / nwarps, sbase = warp * seg;
         for (int k = 2; k <= n2; k <<= 1)
