@@ -204,10 +204,19 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                     if (x >= ww) { x -= ww; oi += ipitch - ww; od += L.pitch - ww; }
                 }
                 s11 = a11; s12 = a12; s22 = a22;
-            } else
+            } else {
+            // the image taps of a window that stays inside the padded frame (apron levels) need no mirror arithmetic
+            const int ap = L.apron ? kApron : 0;
+            const bool img_direct = ipx >= -ap && ipy >= -ap && ipx + ww < L.w + ap && ipy + wh < L.h + ap;
             for (int p = tid; p < npx; p += kGenThreads) {
                 const int X = ipx + x, Y = ipy + y;
-                const int ival = sample_u8(IA, ipitch, L.w, L.h, X, Y, w00, w01, w10, w11);
+                int ival;
+                if (img_direct) {
+                    const uint8_t *r0 = IA + Y * ipitch + X, *r1 = r0 + ipitch;
+                    ival = (r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9;
+                } else {
+                    ival = sample_u8(IA, ipitch, L.w, L.h, X, Y, w00, w01, w10, w11);
+                }
                 const bool xi0 = (unsigned)X < (unsigned)L.w, xi1 = (unsigned)(X + 1) < (unsigned)L.w;
                 const bool yi0 = (unsigned)Y < (unsigned)L.h, yi1 = (unsigned)(Y + 1) < (unsigned)L.h;
                 const short2 z = make_short2(0, 0);
@@ -221,6 +230,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 s11 += (long long)(ix * ix); s12 += (long long)(ix * iy); s22 += (long long)(iy * iy);
                 x += step_x; y += step_y;
                 if (x >= ww) { x -= ww; y++; }
+            }
             }
         }
         block_sum3(s11, s12, s22, red, rsel, tid);
@@ -241,8 +251,11 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             long long sb1 = 0, sb2 = 0;
             int x = lx0, y = ly0;
-            if (acc32 && inx >= 0 && iny >= 0 && inx + ww < L.w && iny + wh < L.h) {
-                // window inside the frame and <= 60 pixels per thread: no border arithmetic, 32-bit partial sums
+            // levels >= 1 carry kApron mirrored pixels around the image in HBM (common.cuh): a window that leaves the frame
+            // by no more than that reads them like ordinary pixels
+            const int ap = L.apron ? kApron : 0;
+            if (acc32 && inx >= -ap && iny >= -ap && inx + ww < L.w + ap && iny + wh < L.h + ap) {
+                // window inside the (padded) frame and <= 60 pixels per thread: no border arithmetic, 32-bit partial sums
                 int a1 = 0, a2 = 0;
                 int oj = (iny + y) * ipitch + (inx + x);
                 const int sj = step_y * ipitch + step_x;
@@ -275,8 +288,16 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             bilinear_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
             long long se = 0;
             int x = lx0, y = ly0;
+            const int ap = L.apron ? kApron : 0;
+            const bool img_direct = inx >= -ap && iny >= -ap && inx + ww < L.w + ap && iny + wh < L.h + ap;
             for (int p = tid; p < npx; p += kGenThreads) {
-                const int diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
+                int diff;
+                if (img_direct) {
+                    const uint8_t *r0 = JB + (iny + y) * ipitch + (inx + x), *r1 = r0 + ipitch;
+                    diff = ((r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9) - Iw[p];
+                } else {
+                    diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
+                }
                 se += diff < 0 ? -diff : diff;
                 x += step_x; y += step_y;
                 if (x >= ww) { x -= ww; y++; }
