@@ -150,6 +150,16 @@ int stage_upload(psnw_ctx *ctx, StageSlot *s, void *dst, size_t bytes, cudaStrea
     return PSNW_OK;
 }
 
+// PSNW_MEM_HOST calls move their arguments as ONE pinned blob each way instead of one pageable copy per array: the stage
+// slot mirrors the scratch arena byte for byte, the caller's inputs are written at the offsets of their device copies,
+// [0, arena_off) goes up in one copy and comes back in one copy after the kernels, and the outputs are read from the slot.
+constexpr int kBlobMaxPts = 100000;       // larger batches keep one copy per array (no multi-megabyte pinned slots)
+template <typename T>
+T *mirror(const psnw_ctx *ctx, const StageSlot *s, const T *dev_ptr)
+{
+    return reinterpret_cast<T *>(s->h + (reinterpret_cast<const char *>(dev_ptr) - reinterpret_cast<const char *>(ctx->arena.p)));
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -723,6 +733,7 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     if (total > ctx->p.max_points || total_groups > ctx->p.max_targets)
         return fail(ctx, PSNW_ENOMEM, "psnw_klt_track: max_points / max_targets given at create time exceeded");
     if (total == 0) return PSNW_OK;
+    const bool host = mem_flags == PSNW_MEM_HOST && total <= kBlobMaxPts;    // one-blob transfers (see mirror())
 
     const bool do_fb = ctx->p.fb_thresh >= 0.f;
     std::vector<TrackJob> dj(n_jobs);
@@ -757,12 +768,25 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
             D.out = take<float2>(ctx, J.n_pts); D.status = take<uint8_t>(ctx, J.n_pts); D.err = take<float>(ctx, J.n_pts);
             D.fb_err = (do_fb && J.fb_err) ? take<float>(ctx, J.n_pts) : nullptr;
             if (ctx->arena_off > ctx->arena.cap) return fail(ctx, PSNW_ENOMEM, "psnw_klt_track: scratch arena exhausted");
-            if (J.n_pts > 0) {
+            if (J.n_pts > 0 && !host) {
                 CK(cudaMemcpyAsync(d_pts, J.pts_xy, sizeof(float2) * J.n_pts, cudaMemcpyHostToDevice, ctx->stream));
                 if (d_tgt) CK(cudaMemcpyAsync(d_tgt, J.target_of_pt, sizeof(int) * J.n_pts, cudaMemcpyHostToDevice, ctx->stream));
             }
         }
         pt += J.n_pts; gb += J.n_targets;
+    }
+
+    StageSlot *blob = nullptr;                // PSNW_MEM_HOST: all inputs up as one pinned blob (see mirror())
+    if (host) {
+        int rcb = stage_acquire(ctx, ctx->arena_off, &blob);
+        if (rcb) return rcb;
+        for (int j = 0; j < n_jobs; ++j) {
+            const psnw_track_job &J = jobs[j];
+            if (J.n_pts == 0) continue;
+            memcpy(mirror(ctx, blob, dj[j].pts), J.pts_xy, sizeof(float2) * J.n_pts);
+            if (dj[j].target_of_pt) memcpy(mirror(ctx, blob, dj[j].target_of_pt), J.target_of_pt, sizeof(int) * J.n_pts);
+        }
+        CK(cudaMemcpyAsync(ctx->arena.p, blob->h, ctx->arena_off, cudaMemcpyHostToDevice, ctx->stream));
     }
 
     // descriptors: inside the kernel parameters when they fit, else through a pinned staging slot -> device
@@ -813,6 +837,20 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
         if (rc) return rc;
     }
 
+    if (host) {                               // ... and all outputs back as one
+        CK(cudaMemcpyAsync(blob->h, ctx->arena.p, ctx->arena_off, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < n_jobs; ++j) {
+            const psnw_track_job &J = jobs[j];
+            const TrackJob &D = dj[j];
+            if (J.n_pts == 0) continue;
+            memcpy(J.out_xy, mirror(ctx, blob, D.out), sizeof(float2) * J.n_pts);
+            memcpy(J.status, mirror(ctx, blob, D.status), J.n_pts);
+            memcpy(J.err, mirror(ctx, blob, D.err), sizeof(float) * J.n_pts);
+            if (D.fb_err) memcpy(J.fb_err, mirror(ctx, blob, D.fb_err), sizeof(float) * J.n_pts);
+        }
+        return PSNW_OK;
+    }
     if (!dev) {
         for (int j = 0; j < n_jobs; ++j) {
             const psnw_track_job &J = jobs[j];
@@ -873,6 +911,28 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
     float2 *d_pre = take<float2>(ctx, n_pts), *d_cur = take<float2>(ctx, n_pts);
     uint8_t *d_st = status ? take<uint8_t>(ctx, n_pts) : nullptr, *d_mask = take<uint8_t>(ctx, n_pts);
     if (ctx->arena_off > ctx->arena.cap) return fail(ctx, PSNW_ENOMEM, "psnw_box_update: scratch arena exhausted");
+    if (mem_flags == PSNW_MEM_HOST && n_pts <= kBlobMaxPts) {
+        StageSlot *s;
+        int rc = stage_acquire(ctx, ctx->arena_off, &s);
+        if (rc) return rc;
+        memcpy(mirror(ctx, s, d_in), boxes_in, sizeof(double) * 4 * n_targets);
+        memcpy(mirror(ctx, s, d_off), target_offsets, sizeof(int) * (n_targets + 1));
+        if (n_pts > 0) {
+            memcpy(mirror(ctx, s, d_pre), pre_xy, sizeof(float2) * n_pts);
+            memcpy(mirror(ctx, s, d_cur), cur_xy, sizeof(float2) * n_pts);
+            if (d_st) memcpy(mirror(ctx, s, d_st), status, n_pts);
+        }
+        CK(cudaMemcpyAsync(ctx->arena.p, s->h, ctx->arena_off, cudaMemcpyHostToDevice, ctx->stream));
+        r = launch_box_update(d_in, n_targets, d_pre, d_cur, d_st, d_off, d_out, d_mask, d_cnt, max_per, ctx->stream);
+        if (r < 0) return fail(ctx, PSNW_ECUDA, "box_update_kernel launch", cudaGetLastError());
+        ctx->launches += r;
+        CK(cudaMemcpyAsync(s->h, ctx->arena.p, ctx->arena_off, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(boxes_out, mirror(ctx, s, d_out), sizeof(double) * 4 * n_targets);
+        memcpy(inlier_counts, mirror(ctx, s, d_cnt), sizeof(int) * n_targets);
+        if (n_pts > 0) memcpy(inlier_mask, mirror(ctx, s, d_mask), n_pts);
+        return PSNW_OK;
+    }
     CK(cudaMemcpyAsync(d_in, boxes_in, sizeof(double) * 4 * n_targets, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_off, target_offsets, sizeof(int) * (n_targets + 1), cudaMemcpyHostToDevice, ctx->stream));
     if (n_pts > 0) {
