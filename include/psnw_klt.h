@@ -211,6 +211,18 @@ PSNW_API int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_target
                              double *boxes_out, uint8_t *inlier_mask, int *inlier_counts, int mem_flags);
 
 /*
+ * psnw_klt_track immediately followed by psnw_box_update on its result -- the pair the reference always runs together
+ * (.cpp:776-787 backward, :871-893 forward) -- as one call: one upload, two launches, one download, one wait.  The
+ * points of target t are pts_xy[target_offsets[t] .. target_offsets[t+1]) (so target_of_pt is implied), the window of
+ * target t is win_wh[t] (NULL: context default); use_status = 0 lets every point vote for the box (backward caller,
+ * :787), 1 only those the tracker kept (forward caller, :883-888).  Outputs as in the two separate calls.
+ */
+PSNW_API int psnw_klt_track_update(psnw_ctx *ctx, int cam, int slot_from, int slot_to, const float *pts_xy,
+                                   const int *target_offsets, int n_targets, const int *win_wh, const double *boxes_in,
+                                   int use_status, float *out_xy, uint8_t *status, float *err, double *boxes_out,
+                                   uint8_t *inlier_mask, int *inlier_counts, int mem_flags);
+
+/*
  * "Next" row: counts[d][t] = number of tracker t's tracked points inside detection box d
  * (PSN_Rect::contain) -- the per-pair counts behind the reference's optical-flow majority check
  * (Tracker2D.cpp:939-944, :981-1022) -- computed next to the LK output so the points need not leave the device.

@@ -1083,6 +1083,83 @@ int psnw_klt_detect(psnw_ctx *ctx, int cam, int slot, const double *boxes, int n
 }
 
 // "next" row f-3: per (detection, tracker) count of tracked points inside the detection box (Tracker2D.cpp:939-944)
+int psnw_klt_track_update(psnw_ctx *ctx, int cam, int slot_from, int slot_to, const float *pts_xy, const int *target_offsets,
+                          int n_targets, const int *win_wh, const double *boxes_in, int use_status, float *out_xy,
+                          uint8_t *status, float *err, double *boxes_out, uint8_t *inlier_mask, int *inlier_counts, int mem_flags)
+{
+    if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
+    if (n_targets == 0) return PSNW_OK;
+    if (n_targets < 0 || !target_offsets || !boxes_in || !boxes_out || !inlier_mask || !inlier_counts)
+        return fail(ctx, PSNW_EARG, "psnw_klt_track_update arguments");
+    if (mem_flags != PSNW_MEM_HOST) {
+        // pinned / device memory: nothing to merge, the two calls already queue back to back on the context stream
+        if (mem_flags == PSNW_MEM_DEVICE) return fail(ctx, PSNW_EARG, "psnw_klt_track_update: with device memory call psnw_klt_track_batch and psnw_box_update (target_offsets must be readable on the host)");
+        const int n = target_offsets[n_targets];
+        std::vector<int> tgt(std::max(n, 1));
+        for (int t = 0; t < n_targets; ++t)
+            for (int i = target_offsets[t]; i < target_offsets[t + 1]; ++i) tgt[i] = t;
+        int rc = psnw_klt_track(ctx, cam, slot_from, slot_to, pts_xy, tgt.data(), n, win_wh, n_targets, out_xy, status, err, nullptr, PSNW_MEM_HOST);
+        if (rc) return rc;
+        return psnw_box_update(ctx, boxes_in, n_targets, pts_xy, out_xy, use_status ? status : nullptr, target_offsets, PSNW_BOX_REFERENCE,
+                               boxes_out, inlier_mask, inlier_counts, PSNW_MEM_HOST);
+    }
+    const int n_pts = target_offsets[n_targets];
+    int max_per = 1;
+    for (int t = 0; t < n_targets; ++t) {
+        const int k = target_offsets[t + 1] - target_offsets[t];
+        if (k < 0 || k > PSNW_MAX_PTS_PER_TARGET) return fail(ctx, PSNW_EARG, "psnw_klt_track_update: offsets not ascending or > PSNW_MAX_PTS_PER_TARGET points in a target");
+        max_per = std::max(max_per, k);
+    }
+    if (n_pts <= 0)                               // nothing to track: the boxes come back as LocalSearchKLT returns them for no features
+        return psnw_box_update(ctx, boxes_in, n_targets, pts_xy, out_xy, nullptr, target_offsets, PSNW_BOX_REFERENCE, boxes_out,
+                               inlier_mask, inlier_counts, PSNW_MEM_HOST);
+    if (!pts_xy || !out_xy || !status || !err) return fail(ctx, PSNW_EARG, "psnw_klt_track_update: null point arrays");
+    if (n_pts > ctx->p.max_points || n_targets > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_klt_track_update: max_points / max_targets exceeded");
+    if (!slot_ok(ctx, cam, slot_from) || !slot_ok(ctx, cam, slot_to)) return fail(ctx, PSNW_ESTATE, "psnw_klt_track_update: camera/slot holds no frame");
+
+    // scratch layout (one blob up, one blob down -- see mirror()); the track call below runs on these device arrays
+    ctx->arena_off = 0;
+    float2 *d_pts = take<float2>(ctx, n_pts), *d_out = take<float2>(ctx, n_pts);
+    int *d_tgt = take<int>(ctx, n_pts), *d_off = take<int>(ctx, n_targets + 1), *d_cnt = take<int>(ctx, n_targets);
+    uint8_t *d_st = take<uint8_t>(ctx, n_pts), *d_mask = take<uint8_t>(ctx, n_pts);
+    float *d_err = take<float>(ctx, n_pts);
+    float *d_fb = ctx->p.fb_thresh >= 0.f ? take<float>(ctx, n_pts) : nullptr;
+    double *d_in = take<double>(ctx, (size_t)n_targets * 4), *d_bout = take<double>(ctx, (size_t)n_targets * 4);
+    const size_t blob_bytes = ctx->arena_off;
+    if (blob_bytes > ctx->arena.cap) return fail(ctx, PSNW_ENOMEM, "psnw_klt_track_update: scratch arena exhausted");
+    StageSlot *s;
+    int rc = stage_acquire(ctx, blob_bytes, &s);
+    if (rc) return rc;
+    memcpy(mirror(ctx, s, d_pts), pts_xy, sizeof(float2) * n_pts);
+    memcpy(mirror(ctx, s, d_off), target_offsets, sizeof(int) * (n_targets + 1));
+    memcpy(mirror(ctx, s, d_in), boxes_in, sizeof(double) * 4 * n_targets);
+    int *h_tgt = mirror(ctx, s, d_tgt);
+    for (int t = 0; t < n_targets; ++t)
+        for (int i = target_offsets[t]; i < target_offsets[t + 1]; ++i) h_tgt[i] = t;
+    CK(cudaMemcpyAsync(ctx->arena.p, s->h, blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
+
+    psnw_track_job j;
+    j.cam = cam; j.slot_from = slot_from; j.slot_to = slot_to;
+    j.n_pts = n_pts; j.pts_xy = reinterpret_cast<const float *>(d_pts); j.target_of_pt = d_tgt;
+    j.n_targets = n_targets; j.win_wh = win_wh;
+    j.out_xy = reinterpret_cast<float *>(d_out); j.status = d_st; j.err = d_err; j.fb_err = d_fb;
+    rc = psnw_klt_track_batch(ctx, &j, 1, PSNW_MEM_DEVICE);         // (takes nothing from the arena with device pointers)
+    if (rc) return rc;
+    const int r = launch_box_update(d_in, n_targets, d_pts, d_out, use_status ? d_st : nullptr, d_off, d_bout, d_mask, d_cnt, max_per, ctx->stream);
+    if (r < 0) return fail(ctx, PSNW_ECUDA, "box_update_kernel launch", cudaGetLastError());
+    ctx->launches += r;
+    CK(cudaMemcpyAsync(s->h, ctx->arena.p, blob_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_xy, mirror(ctx, s, d_out), sizeof(float2) * n_pts);
+    memcpy(status, mirror(ctx, s, d_st), n_pts);
+    memcpy(err, mirror(ctx, s, d_err), sizeof(float) * n_pts);
+    memcpy(boxes_out, mirror(ctx, s, d_bout), sizeof(double) * 4 * n_targets);
+    memcpy(inlier_mask, mirror(ctx, s, d_mask), n_pts);
+    memcpy(inlier_counts, mirror(ctx, s, d_cnt), sizeof(int) * n_targets);
+    return PSNW_OK;
+}
+
 int psnw_points_in_boxes(psnw_ctx *ctx, const float *pts_xy, const int *tracker_offsets, int n_trackers,
                          const double *det_boxes, int n_detections, int *counts, int mem_flags)
 {

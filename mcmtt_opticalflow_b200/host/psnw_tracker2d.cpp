@@ -216,11 +216,11 @@ size_t CPSNWhere_Tracker2D::Track2D_BackwardFeatureTracking(std::vector<stDetect
         std::vector<float> err(n);
         std::vector<double> bout(4 * idx.size());
         std::vector<int> ninl(idx.size());
-        if (!Check(psnw_klt_track(m_klt, m_nKltCam, k - 1, k, &pts[0].x, tgt.data(), n, win.data(), (int)idx.size(),
-                                  &out[0].x, st.data(), err.data(), nullptr, PSNW_MEM_HOST), "psnw_klt_track(backward)")) break;
-        // position estimation: status is ignored in the backward pass (:787)
-        if (!Check(psnw_box_update(m_klt, bin.data(), (int)idx.size(), &pts[0].x, &out[0].x, nullptr, off.data(), PSNW_BOX_REFERENCE,
-                                   bout.data(), inl.data(), ninl.data(), PSNW_MEM_HOST), "psnw_box_update(backward)")) break;
+        // calcOpticalFlowPyrLK (:776-782) + LocalSearchKLT (:787) of every live detection as one call; position estimation
+        // ignores the LK status in the backward pass (:787)
+        if (!Check(psnw_klt_track_update(m_klt, m_nKltCam, k - 1, k, &pts[0].x, off.data(), (int)idx.size(), win.data(), bin.data(),
+                                         /*use_status=*/0, &out[0].x, st.data(), err.data(), bout.data(), inl.data(), ninl.data(),
+                                         PSNW_MEM_HOST), "psnw_klt_track_update(backward)")) break;
         for (size_t i = 0; i < idx.size(); ++i) {
             stDetectedObject &det = m_vecDetection2D[idx[i]];
             if ((size_t)ninl[i] < PSN_2D_FEATURE_MIN_NUM_TRACK) { alive[idx[i]] = 0; continue; }   // :788
@@ -273,11 +273,10 @@ std::vector<float> CPSNWhere_Tracker2D::Track2D_ForwardTrackingAndGetMatchingSco
     std::vector<double> bout(4 * T);
     std::vector<int> ninl(T);
     if (n > 0) {
-        if (!Check(psnw_klt_track(m_klt, m_nKltCam, 1, 0, &pts[0].x, tgt.data(), n, win.data(), (int)T, &out[0].x, st.data(),
-                                  err.data(), nullptr, PSNW_MEM_HOST), "psnw_klt_track(forward)")) return matchingCostArray;
-        // motion estimation on the status-filtered pairs (:883-893)
-        if (!Check(psnw_box_update(m_klt, bin.data(), (int)T, &pts[0].x, &out[0].x, st.data(), off.data(), PSNW_BOX_REFERENCE,
-                                   bout.data(), inl.data(), ninl.data(), PSNW_MEM_HOST), "psnw_box_update(forward)")) return matchingCostArray;
+        // calcOpticalFlowPyrLK (:871-877) + motion estimation on the status-filtered pairs (:883-893) as one call
+        if (!Check(psnw_klt_track_update(m_klt, m_nKltCam, 1, 0, &pts[0].x, off.data(), (int)T, win.data(), bin.data(),
+                                         /*use_status=*/1, &out[0].x, st.data(), err.data(), bout.data(), inl.data(), ninl.data(),
+                                         PSNW_MEM_HOST), "psnw_klt_track_update(forward)")) return matchingCostArray;
     }
 
     for (size_t t = 0; t < T; ++t) {

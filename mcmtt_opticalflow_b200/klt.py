@@ -56,7 +56,7 @@ EXPORTS = [
     "psnw_klt_detect_batch", "psnw_join", "psnw_gridfast_detect", "psnw_read_fast_map", "psnw_points_in_boxes", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
     "psnw_push_frames_bgr", "psnw_frames_held", "psnw_klt_detect", "psnw_klt_track", "psnw_klt_track_batch",
     "psnw_box_update", "psnw_sync", "psnw_last_error", "psnw_get_stream", "psnw_level_info", "psnw_read_level",
-    "psnw_read_level_apron",
+    "psnw_read_level_apron", "psnw_klt_track_update",
     "psnw_read_min_eig", "psnw_launch_count", "psnw_push_frame_bytes", "psnw_rebuild_pyramids", "psnw_levels_built",
 ]
 
@@ -100,6 +100,10 @@ def load():
         lib.psnw_klt_track.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_klt_track_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        if hasattr(lib, "psnw_klt_track_update"):
+            lib.psnw_klt_track_update.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                  C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_int]
         lib.psnw_box_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_level_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -291,6 +295,20 @@ class KLTContext:
         self._ck(self.lib.psnw_klt_track(self._h, cam, slot_from, slot_to, _ptr(pts), _ptr(tgt), n, _ptr(win), n_targets,
                                          _ptr(out), _ptr(status), _ptr(err), _ptr(fb), MEM_HOST))
         return out, status, err, fb
+
+    def track_update(self, pts, offsets, boxes, win_wh=None, cam=0, slot_from=1, slot_to=0, use_status=True):
+        """psnw_klt_track + psnw_box_update as one call -> (out, status, err, boxes_out, inlier_mask, inlier_counts)."""
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
+        win = None if win_wh is None else np.ascontiguousarray(win_wh, np.int32).reshape(-1, 2)
+        n, nt = pts.shape[0], boxes.shape[0]
+        out, status, err = np.zeros((n, 2), np.float32), np.zeros(n, np.uint8), np.zeros(n, np.float32)
+        bout, mask, cnt = np.zeros((nt, 4), np.float64), np.zeros(n, np.uint8), np.zeros(nt, np.int32)
+        self._ck(self.lib.psnw_klt_track_update(self._h, cam, slot_from, slot_to, _ptr(pts), _ptr(offsets), nt, _ptr(win), _ptr(boxes),
+                                                1 if use_status else 0, _ptr(out), _ptr(status), _ptr(err), _ptr(bout), _ptr(mask),
+                                                _ptr(cnt), MEM_HOST))
+        return out, status, err, bout, mask, cnt
 
     def track_batch(self, jobs, mem=MEM_HOST):
         """jobs: list of dicts with cam, slot_from, slot_to, pts, [target_of_pt], [win_wh], out, status, err, [fb_err]

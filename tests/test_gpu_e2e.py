@@ -87,3 +87,24 @@ def test_backward_chain_and_forward_iou(oracle):
             assert iou(ob, nb[t]) >= MIN_IOU, t
             moved += int(np.abs(ob[:2] - prev_boxes[t][:2]).max() > 0.5)
         assert moved >= ntgt // 2                                      # the estimator really moved the boxes
+
+
+@pytest.mark.parametrize("use_status", [False, True])
+def test_track_update_equals_the_two_calls(use_status):
+    """psnw_klt_track_update (one upload, two launches, one download) == psnw_klt_track followed by psnw_box_update,
+    bit for bit, with the reference's per-target windows (generic kernel) and with the default 21x21 window."""
+    w, h, ntgt = 768, 576, 14
+    cam = synth.Camera(w, h, ntgt, cam=6)
+    f0, f1 = cam.frame(0), cam.frame(1)
+    boxes = cam.boxes(0)
+    pts, tid = synth.seeds_in_boxes(boxes, 60, w, h, np.random.default_rng(11))
+    off = (np.arange(ntgt + 1) * 60).astype(np.int32)
+    wins = np.stack([boxes[:, 2].astype(np.int32), boxes[:, 3].astype(np.int32)], 1)
+    with klt.KLTContext(w, h, levels=4, fb_thresh=-1.0) as ctx:
+        ctx.push_frame(f0); ctx.push_frame(f1)
+        for win in (wins, None):
+            o1, s1, e1, _ = ctx.track(pts, target_of_pt=tid, win_wh=win if win is not None else [[21, 21]] * ntgt)
+            b1, m1, c1 = ctx.box_update(boxes, pts, o1, off, status=s1 if use_status else None)
+            o2, s2, e2, b2, m2, c2 = ctx.track_update(pts, off, boxes, win_wh=win, use_status=use_status)
+            assert np.array_equal(o1, o2) and np.array_equal(s1, s2) and np.array_equal(e1, e2)
+            assert np.array_equal(b1, b2) and np.array_equal(m1, m2) and np.array_equal(c1, c2)
