@@ -754,7 +754,7 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
             g.max_level = effective_max_level(ctx, ww, wh);
             g.pad = 0;
             all21 = all21 && ww == 21 && wh == 21;
-            max_win_px = std::max(max_win_px, ww * wh);
+            max_win_px = std::max(max_win_px, ((ww + 3) & ~3) * wh);      // template rows are padded to 4 pixels (lk.cu)
         }
         TrackJob &D = dj[j];
         D.pt_begin = pt; D.n_pts = J.n_pts; D.group_base = gb; D.n_targets = J.n_targets;

@@ -119,6 +119,22 @@ __device__ __forceinline__ bool lk_step(const LkParams &P, float fb1, float fb2,
     return false;
 }
 
+// packed-byte helpers of both kernels
+__device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ int sext16(uint32_t w) { return (int)(short)(w & 0xffffu); }
+
 // ------------------------------------------------------------------------------------------------
 // generic window
 // ------------------------------------------------------------------------------------------------
@@ -158,6 +174,11 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
     const bool acc32 = npx <= 60 * kGenThreads;   // 60 * 8160 * 4080 < 2^31: per-thread partial sums fit 32 bits
     while (lx0 >= ww) { lx0 -= ww; ly0++; }
     const int step_y = kGenThreads / ww, step_x = kGenThreads - step_y * ww;   // one stride of kGenThreads pixels in (x, y)
+    // template rows are padded to a multiple of 4 pixels (index q = y * wp + x): the 4-pixel inner loop reads them as vectors
+    const int wp = (ww + 3) & ~3, sq = step_y * wp + step_x, q0 = ly0 * wp + lx0;
+    // the 4-pixel inner loop walks groups of 4 adjacent pixels: G groups per row, this thread's first group (gx0, gy0)
+    const int G = wp >> 2, gy0 = tid / G, gx0 = tid - gy0 * G, sgy = kGenThreads / G, sgx = kGenThreads - sgy * G;
+    const bool acc32_4 = wp * wh <= 60 * kGenThreads;
 
     for (int level = max_level; level >= 0; --level) {
         const LevelGeom &L = P.lv[level];
@@ -183,7 +204,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
 
         long long s11 = 0, s12 = 0, s22 = 0;
         {
-            int x = lx0, y = ly0;
+            int x = lx0, y = ly0, q = q0;
             if (acc32 && ipx >= 0 && ipy >= 0 && ipx + ww < L.w && ipy + wh < L.h) {
                 // window (plus its bilinear ring) inside the frame: no border arithmetic, 32-bit partial sums
                 int a11 = 0, a12 = 0, a22 = 0;
@@ -197,11 +218,11 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                     const short2 d00 = d0[0], d01 = d0[1], d10 = d1[0], d11 = d1[1];
                     const int ix = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
                     const int iy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
-                    Iw[p] = (short)ival;
-                    dIw[p] = make_short2((short)ix, (short)iy);
+                    Iw[q] = (short)ival;
+                    dIw[q] = make_short2((short)ix, (short)iy);
                     a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
-                    x += step_x; oi += si; od += sd;
-                    if (x >= ww) { x -= ww; oi += ipitch - ww; od += L.pitch - ww; }
+                    x += step_x; q += sq; oi += si; od += sd;
+                    if (x >= ww) { x -= ww; q += wp - ww; oi += ipitch - ww; od += L.pitch - ww; }
                 }
                 s11 = a11; s12 = a12; s22 = a22;
             } else {
@@ -225,11 +246,11 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 const short2 d10 = (xi0 && yi1) ? d1[0] : z, d11 = (xi1 && yi1) ? d1[1] : z;
                 const int ix = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
                 const int iy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
-                Iw[p] = (short)ival;
-                dIw[p] = make_short2((short)ix, (short)iy);
+                Iw[q] = (short)ival;
+                dIw[q] = make_short2((short)ix, (short)iy);
                 s11 += (long long)(ix * ix); s12 += (long long)(ix * iy); s22 += (long long)(iy * iy);
-                x += step_x; y += step_y;
-                if (x >= ww) { x -= ww; y++; }
+                x += step_x; y += step_y; q += sq;
+                if (x >= ww) { x -= ww; y++; q += wp - ww; }
             }
             }
         }
@@ -250,31 +271,63 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             long long sb1 = 0, sb2 = 0;
-            int x = lx0, y = ly0;
+            int x = lx0, y = ly0, q = q0;
             // levels >= 1 carry kApron mirrored pixels around the image in HBM (common.cuh): a window that leaves the frame
             // by no more than that reads them like ordinary pixels
             const int ap = L.apron ? kApron : 0;
-            if (acc32 && inx >= -ap && iny >= -ap && inx + ww < L.w + ap && iny + wh < L.h + ap) {
+            if (acc32_4 && inx >= -ap && iny >= -ap && inx + ww < L.w + ap && iny + wh < L.h + ap &&
+                inx + wp + 4 <= ipitch - (L.apron ? kApronL : 0)) {
+                // Four adjacent pixels per step, the inner loop of the 21x21 kernel: two aligned words per image row, funnel
+                // shifts to the window's byte phase (inx & 3, the same for every row: pitches are multiples of 4), dp2a on the
+                // packed bytes, template read as vectors.  The bytes past the window in the last group of a row (and the
+                // few the aligned words over-read, inside the row pitch) never reach the sums.
+                const int sh8 = (inx & 3) * 8;
+                const int wt = (w00 & 0xffff) | (w01 << 16), wb = (w10 & 0xffff) | (w11 << 16);
+                const uint8_t *base = JB + (ptrdiff_t)iny * ipitch + (inx - (inx & 3));
+                int a1 = 0, a2 = 0, gx = gx0, gy = gy0;
+                for (int it = tid; it < G * wh; it += kGenThreads) {
+                    const uint32_t *r0 = reinterpret_cast<const uint32_t *>(base + (ptrdiff_t)gy * ipitch + 4 * gx);
+                    const uint32_t *r1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(r0) + ipitch);
+                    const uint32_t w0 = __ldg(r0), w1 = __ldg(r0 + 1), z0 = __ldg(r1), z1 = __ldg(r1 + 1);
+                    const uint32_t t0 = __funnelshift_r(w0, w1, sh8), t4 = w1 >> sh8;          // bytes 0..3, byte 4
+                    const uint32_t u0 = __funnelshift_r(z0, z1, sh8), u4 = z1 >> sh8;
+                    const uint32_t ts = __funnelshift_r(t0, t4, 8), us = __funnelshift_r(u0, u4, 8);   // bytes 1..4
+                    const int v0 = dp2a_lo_su(wb, u0, dp2a_lo_su(wt, t0, 256)), v1 = dp2a_lo_su(wb, us, dp2a_lo_su(wt, ts, 256));
+                    const int v2 = dp2a_hi_su(wb, u0, dp2a_hi_su(wt, t0, 256)), v3 = dp2a_hi_su(wb, us, dp2a_hi_su(wt, ts, 256));
+                    const int q4 = gy * wp + 4 * gx;
+                    const uint2 iw = *reinterpret_cast<const uint2 *>(Iw + q4);
+                    const uint4 dw = *reinterpret_cast<const uint4 *>(dIw + q4);
+                    int d0 = (v0 >> 9) - sext16(iw.x), d1 = (v1 >> 9) - ((int)iw.x >> 16);
+                    int d2 = (v2 >> 9) - sext16(iw.y), d3 = (v3 >> 9) - ((int)iw.y >> 16);
+                    const int valid = ww - 4 * gx;           // >= 4 except in the last group of a row
+                    if (valid < 4) { d3 = 0; if (valid < 3) d2 = 0; if (valid < 2) d1 = 0; }
+                    a1 += d0 * sext16(dw.x) + d1 * sext16(dw.y) + d2 * sext16(dw.z) + d3 * sext16(dw.w);
+                    a2 += d0 * ((int)dw.x >> 16) + d1 * ((int)dw.y >> 16) + d2 * ((int)dw.z >> 16) + d3 * ((int)dw.w >> 16);
+                    gx += sgx; gy += sgy;
+                    if (gx >= G) { gx -= G; gy++; }
+                }
+                sb1 = a1; sb2 = a2;
+            } else if (acc32 && inx >= -ap && iny >= -ap && inx + ww < L.w + ap && iny + wh < L.h + ap) {
                 // window inside the (padded) frame and <= 60 pixels per thread: no border arithmetic, 32-bit partial sums
                 int a1 = 0, a2 = 0;
                 int oj = (iny + y) * ipitch + (inx + x);
                 const int sj = step_y * ipitch + step_x;
                 for (int p = tid; p < npx; p += kGenThreads) {
                     const uint8_t *r0 = JB + oj, *r1 = r0 + ipitch;
-                    const int diff = ((r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9) - Iw[p];
-                    const short2 d = dIw[p];
+                    const int diff = ((r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9) - Iw[q];
+                    const short2 d = dIw[q];
                     a1 += diff * d.x; a2 += diff * d.y;
-                    x += step_x; oj += sj;
-                    if (x >= ww) { x -= ww; oj += ipitch - ww; }
+                    x += step_x; q += sq; oj += sj;
+                    if (x >= ww) { x -= ww; q += wp - ww; oj += ipitch - ww; }
                 }
                 sb1 = a1; sb2 = a2;
             } else {
                 for (int p = tid; p < npx; p += kGenThreads) {
-                    const int diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
-                    const short2 d = dIw[p];
+                    const int diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[q];
+                    const short2 d = dIw[q];
                     sb1 += (long long)(diff * d.x); sb2 += (long long)(diff * d.y);
-                    x += step_x; y += step_y;
-                    if (x >= ww) { x -= ww; y++; }
+                    x += step_x; y += step_y; q += sq;
+                    if (x >= ww) { x -= ww; y++; q += wp - ww; }
                 }
             }
             { long long z = 0; block_sum3(sb1, sb2, z, red, rsel, tid); }
@@ -287,20 +340,20 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             if (inx < -ww || inx >= L.w || iny < -wh || iny >= L.h) { st = 0; continue; }
             bilinear_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
             long long se = 0;
-            int x = lx0, y = ly0;
+            int x = lx0, y = ly0, q = q0;
             const int ap = L.apron ? kApron : 0;
             const bool img_direct = inx >= -ap && iny >= -ap && inx + ww < L.w + ap && iny + wh < L.h + ap;
             for (int p = tid; p < npx; p += kGenThreads) {
                 int diff;
                 if (img_direct) {
                     const uint8_t *r0 = JB + (iny + y) * ipitch + (inx + x), *r1 = r0 + ipitch;
-                    diff = ((r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9) - Iw[p];
+                    diff = ((r0[0] * w00 + r0[1] * w01 + r1[0] * w10 + r1[1] * w11 + (1 << 8)) >> 9) - Iw[q];
                 } else {
-                    diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[p];
+                    diff = sample_u8(JB, ipitch, L.w, L.h, inx + x, iny + y, w00, w01, w10, w11) - Iw[q];
                 }
                 se += diff < 0 ? -diff : diff;
-                x += step_x; y += step_y;
-                if (x >= ww) { x -= ww; y++; }
+                x += step_x; y += step_y; q += sq;
+                if (x >= ww) { x -= ww; y++; q += wp - ww; }
             }
             { long long z0 = 0, z1 = 0; block_sum3(se, z0, z1, red, rsel, tid); }
             er = __fdiv_rn(__ll2float_rn(se), (float)(32 * ww * wh));
@@ -381,19 +434,6 @@ constexpr int kIBoxBytes = kPatch * kU8Pitch * 4, kJBoxBytes = kJPatch * kU8Pitc
 #define PSNW_LK_MINB 4
 #endif
 constexpr int kWarpsPerCta = PSNW_LK_WARPS;
-
-__device__ __forceinline__ int dp2a_lo_su(int a, uint32_t b, int c)
-{
-    int d;
-    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ int dp2a_hi_su(int a, uint32_t b, int c)
-{
-    int d;
-    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
 
 __device__ __forceinline__ int refl_clamp(int p, int n)
 {
@@ -487,8 +527,6 @@ __device__ __forceinline__ void bilinear_run7(const uint32_t *patch, int row, in
     v[5] = dp2a_lo_su(wb, u5, dp2a_lo_su(wt, t5, c[5]));
     v[6] = dp2a_hi_su(wb, u1, dp2a_hi_su(wt, t1, c[6]));
 }
-
-__device__ __forceinline__ int sext16(uint32_t w) { return (int)(short)(w & 0xffffu); }
 
 // Origin of the staged 30 x 30 target patch for a window at (inx, iny): centred (margin 4 on every side), but slid
 // back inside the frame when the window itself is inside, so that the aligned fast path serves it.
