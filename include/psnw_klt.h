@@ -93,6 +93,11 @@ typedef struct psnw_params {
     int max_points;       /* capacity of one klt_track(_batch) call, all jobs together */
     int max_targets;      /* capacity of one klt_track(_batch) / box_update / detect call */
     void *stream;         /* cudaStream_t to enqueue on; NULL: the context creates its own */
+    int apron;            /* mirrored pixels kept around the pyramid levels >= 1 in device memory (the REFLECT_101 border
+                             calcOpticalFlowPyrLK builds around every level); 0 = 26, what the 21 x 21 window needs.  A
+                             context that tracks the reference's per-target windows (up to ~55 x 130) sets about half the
+                             largest window side (64): such windows then run without border arithmetic on the coarse
+                             levels.  Results do not depend on it. */
 } psnw_params;
 
 /* Fills *p with the reference-faithful defaults (4 levels, 21x21, 30 it, 0.01, 1e-4, fb 1.0, 4 slots). */

@@ -202,12 +202,12 @@ int make_tensor_maps(psnw_ctx *ctx)
     }
     // patch maps of the 21x21 LK kernel: u8 image with the I box (48 x 22) and the J box (48 x 30), (dx,dy) image with the
     // 28 x 22 box.  Apron levels describe the whole padded plane -- the apron is ordinary memory to the copy -- and the
-    // kernel offsets its coordinates by (kApronL, kApron); the derivative map zero-fills outside the image.
+    // kernel offsets its coordinates by (apron_l, apron); the derivative map zero-fills outside the image.
     std::vector<CUtensorMap> lk(3 * ctx->pyr.levels);
     for (int l = 0; l < ctx->pyr.levels; ++l) {
         const LevelGeom &g = ctx->pyr.lv[l];
         const cuuint32_t estr[3] = {1, 1, 1};
-        const cuuint64_t idims[3] = {(cuuint64_t)(g.apron ? g.ipitch : g.w), (cuuint64_t)(g.apron ? g.h + 2 * kApron : g.h), (cuuint64_t)ctx->planes};
+        const cuuint64_t idims[3] = {(cuuint64_t)(g.apron ? g.ipitch : g.w), (cuuint64_t)(g.h + 2 * g.apron), (cuuint64_t)ctx->planes};
         const cuuint64_t istr[2] = {(cuuint64_t)g.ipitch, (cuuint64_t)g.iplane_px};
         void *ibase = g.apron ? (void *)ctx->img_alloc[l] : (void *)g.img;
         for (int k = 0; k < 2; ++k) {
@@ -458,6 +458,7 @@ int psnw_default_params(psnw_params *p)
     p->max_points = 1 << 16;
     p->max_targets = 1 << 12;
     p->stream = nullptr;
+    p->apron = 0;
     return PSNW_OK;
 }
 
@@ -476,6 +477,7 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     ctx->p = *p;
     ctx->p.max_iters = std::min(std::max(p->max_iters, 0), 100);                 // calcOpticalFlowPyrLK clamps
     ctx->p.epsilon = std::min(std::max(p->epsilon, 0.0), 10.0);
+    ctx->p.apron = std::min(std::max(p->apron, kApronMin), kApronMax);           // 0 = default
     ctx->planes = p->n_cameras * p->ring_slots;
     ctx->head.assign(p->n_cameras, p->ring_slots - 1);
     ctx->held.assign(p->n_cameras, 0);
@@ -526,10 +528,11 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
         g.pitch = (w + 127) & ~127;
         g.plane_px = g.pitch * h;
         // level 0 is stored bare (one linear upload per frame); levels >= 1 with a REFLECT_101 apron (common.cuh)
-        g.apron = l > 0 ? 1 : 0;
-        g.ipitch = g.apron ? (kApronL + w + kApronR + 63) & ~63 : g.pitch;
-        g.iplane_px = g.apron ? g.ipitch * (h + 2 * kApron) : g.plane_px;
-        const size_t front = g.apron ? (size_t)kApron * g.ipitch + kApronL : 0;
+        g.apron = l > 0 ? ctx->p.apron : 0;
+        g.apron_l = g.apron ? apron_left(g.apron) : 0;
+        g.ipitch = g.apron ? (g.apron_l + w + apron_right(g.apron) + 63) & ~63 : g.pitch;
+        g.iplane_px = g.apron ? g.ipitch * (h + 2 * g.apron) : g.plane_px;
+        const size_t front = g.apron ? (size_t)g.apron * g.ipitch + g.apron_l : 0;
         const size_t px = (size_t)g.plane_px * ctx->planes, ipx = (size_t)g.iplane_px * ctx->planes;
         if (cudaMalloc(&ctx->img_alloc[l], ipx) != cudaSuccess || cudaMalloc(&g.dxy, px * sizeof(short2)) != cudaSuccess) {
             *out = nullptr;
@@ -1331,7 +1334,7 @@ int psnw_read_level_apron(psnw_ctx *ctx, int cam, int slot, int level, uint8_t *
     if (int rc_enter = enter(ctx)) return rc_enter;
     if (!slot_ok(ctx, cam, slot)) return fail(ctx, PSNW_ESTATE, "psnw_read_level_apron: camera/slot holds no frame");
     const LevelGeom &g = ctx->pyr.lv[level];
-    const int a = g.apron ? kApron : 0;
+    const int a = g.apron;
     if (apron) *apron = a;
     if (!out) return PSNW_OK;
     if (int rc_up = join_up(ctx)) return rc_up;

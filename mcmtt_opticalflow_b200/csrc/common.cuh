@@ -17,16 +17,19 @@ struct LevelGeom {
     int plane_px;      // h * pitch
     int ipitch;        // image row pitch in bytes
     int iplane_px;     // image plane stride in bytes
-    int apron;         // 1: a REFLECT_101 apron of kApron pixels surrounds every image plane in HBM (levels >= 1)
-    int pad_;
+    int apron;         // > 0: a REFLECT_101 apron of that many pixels surrounds every image plane in HBM (levels >= 1)
+    int apron_l;       // physical left margin of an image row in bytes (0 without apron); pixel (0,0) stays 16-byte aligned
 };
 
-// Levels >= 1 are stored with a physical REFLECT_101 apron (written by the pyramid kernels together with the pixels they
-// mirror), so the 21x21 LK kernel stages every coarse-level patch with aligned 16-byte copies and no border arithmetic.
-// kApron pixels are mirrored on each side; kApronL / kApronR are the physical left / right margins of a row (the left one
-// keeps pixel (0,0) 16-byte aligned, the right one covers the round-up of a staged row to 16 bytes).  Level 0 is stored
-// bare: frames are uploaded into it with one linear copy.
-constexpr int kApron = 26, kApronL = 32, kApronR = 48;
+// Levels >= 1 are stored with a physical REFLECT_101 apron (written by the pyramid kernels), so the LK kernels stage or
+// read coarse-level patches with aligned copies and no border arithmetic.  LevelGeom::apron pixels are mirrored on each
+// side (psnw_params::apron; at least kApronMin = 26, what the 21x21 window with its 4-pixel staging margin needs; a context
+// that tracks the reference's large per-target windows asks for more); apron_l = apron_left(a) bytes of left margin keep
+// pixel (0,0) 16-byte aligned under the round-down of a staged row to 16 bytes, apron_right(a) covers its round-up.
+// Level 0 is stored bare: frames are uploaded into it with one linear copy.
+constexpr int kApronMin = 26, kApronMax = 160;
+__host__ __device__ constexpr int apron_left(int a) { return (a + 6 + 15) & ~15; }
+__host__ __device__ constexpr int apron_right(int a) { return a + 22; }
 
 struct PyrDesc {
     LevelGeom lv[PSNW_MAX_LEVELS];

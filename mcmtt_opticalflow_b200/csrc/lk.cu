@@ -227,7 +227,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 s11 = a11; s12 = a12; s22 = a22;
             } else {
             // the image taps of a window that stays inside the padded frame (apron levels) need no mirror arithmetic
-            const int ap = L.apron ? kApron : 0;
+            const int ap = L.apron;
             const bool img_direct = ipx >= -ap && ipy >= -ap && ipx + ww < L.w + ap && ipy + wh < L.h + ap;
             for (int p = tid; p < npx; p += kGenThreads) {
                 const int X = ipx + x, Y = ipy + y;
@@ -272,11 +272,11 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             long long sb1 = 0, sb2 = 0;
             int x = lx0, y = ly0, q = q0;
-            // levels >= 1 carry kApron mirrored pixels around the image in HBM (common.cuh): a window that leaves the frame
+            // levels >= 1 carry L.apron mirrored pixels around the image in HBM (common.cuh): a window that leaves the frame
             // by no more than that reads them like ordinary pixels
-            const int ap = L.apron ? kApron : 0;
+            const int ap = L.apron;
             if (acc32_4 && inx >= -ap && iny >= -ap && inx + ww < L.w + ap && iny + wh < L.h + ap &&
-                inx + wp + 4 <= ipitch - (L.apron ? kApronL : 0)) {
+                inx + wp + 4 <= ipitch - L.apron_l) {
                 // Four adjacent pixels per step, the inner loop of the 21x21 kernel: two aligned words per image row, funnel
                 // shifts to the window's byte phase (inx & 3, the same for every row: pitches are multiples of 4), dp2a on the
                 // packed bytes, template read as vectors.  The bytes past the window in the last group of a row (and the
@@ -341,7 +341,7 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
             bilinear_weights(__fsub_rn(qx, (float)inx), __fsub_rn(qy, (float)iny), w00, w01, w10, w11);
             long long se = 0;
             int x = lx0, y = ly0, q = q0;
-            const int ap = L.apron ? kApron : 0;
+            const int ap = L.apron;
             const bool img_direct = inx >= -ap && iny >= -ap && inx + ww < L.w + ap && iny + wh < L.h + ap;
             for (int p = tid; p < npx; p += kGenThreads) {
                 int diff;
@@ -493,7 +493,7 @@ __device__ __forceinline__ int stage_u8(const LkParams &P, int level, int plane,
         *tma_bytes = N * kU8Pitch * 4;
         if (R.lane == 0)
             tma_load_3d(smem_u32(patch), P.tmaps + 3 * level + (N == kPatch ? kMapI : kMapJ),
-                        x0 - off + (L.apron ? kApronL : 0), y0 + (L.apron ? kApron : 0), plane, bar);
+                        x0 - off + L.apron_l, y0 + L.apron, plane, bar);
         return off;
     }
     *tma_bytes = 0;

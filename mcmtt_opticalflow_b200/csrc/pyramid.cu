@@ -27,22 +27,30 @@ constexpr int kRowsPerWarp = 8;
 
 // REFLECT_101 apron of the levels >= 1 (common.cuh): what copyMakeBorder builds around every pyramid level inside
 // cv::calcOpticalFlowPyrLK, written once per pushed frame so that the LK kernel stages coarse-level patches without border
-// arithmetic.  A thread writes one aligned 4-byte word of the apron: kApron rows above and below the image over the padded
-// width, and kApronCols columns left and right of every image row; sources are the level's own pixels (L2-resident).
+// arithmetic.  A thread writes one aligned 4-byte word of the apron: LevelGeom::apron rows above and below the image over the
+// padded width, and that many columns (rounded up to words) left and right of every image row; sources are the level's own
+// pixels (L2-resident).
 // The work is cut into regions of one CTA each (apron_regions): with one launch per level the regions of level l ride as
 // extra CTAs in that level's own pyr_scharr_kernel launch (level l is complete by then and nothing in the launch writes
 // it), so the apron costs neither a launch nor a serial tail; after the fused multi-level kernel one apron_kernel launch
 // covers every level >= 1 of every plane (grid.y = level - 1, grid.z = plane).
 constexpr int kApronThreads = 128;
-constexpr int kApronCols = 28;          // kApron rounded up to whole words
-
 struct ApronLevels {
     LevelGeom lv[PSNW_MAX_LEVELS];
     int n;
 };
 
-constexpr int kSideL = kApronCols / 4;      // words written left of every image row
-constexpr int kSideR = kSideL + 1;          // ... and right of it, starting at the word that holds column w (w & ~3)
+// a mirrored row is written as whole words: cols = apron rounded up to 4 pixels left of the image; right of it the words
+// start at the one that holds column w (w & ~3), one more than on the left
+__host__ __device__ inline int apron_cols(int apron) { return (apron + 3) & ~3; }
+// word slots per image row in the side bands: 16 while left + right words fit, else 32, 64, ...
+__host__ __device__ inline int apron_slot_shift(int apron)
+{
+    const int words = 2 * (apron_cols(apron) / 4) + 1;
+    int sh = 4;
+    while ((1 << sh) < words) ++sh;
+    return sh;
+}
 
 __device__ __forceinline__ int reflect101(int p, int n)
 {
@@ -72,46 +80,32 @@ __device__ __forceinline__ uint32_t apron_word_load(const uint8_t *plane0, int p
     return v;
 }
 
-// CTAs needed for the apron of a level with h rows: groups of kApronRep rows above / below the image, then bands of
-// kApronRep * nthreads / 16 image rows (kApronRep words per thread keep the CTAs few and not launch-rate bound)
-constexpr int kApronRep = 1;
-__host__ __device__ inline int apron_regions(int h, int nthreads)
+// CTAs needed for the apron of a level with h rows: one per apron row above / below the image, then bands of
+// nthreads >> slot_shift image rows
+__host__ __device__ inline int apron_regions(int h, int apron, int nthreads)
 {
-    const int band = kApronRep * (nthreads / 16);
-    return (2 * kApron + kApronRep - 1) / kApronRep + (h + band - 1) / band;
+    const int band = nthreads >> apron_slot_shift(apron);
+    return 2 * apron + (h + band - 1) / band;
 }
 
-// region < ceil(2 kApron / kApronRep): kApronRep apron rows above / below the image over the padded width (threads stride
-// over the words of a row); else a band of image rows, 16 word slots per row = kSideL words left of the row and kSideR
-// right of it (a word that straddles column w rewrites the image pixels it holds with their own values).
+// region < 2 * apron: one apron row above / below the image over the padded width (threads stride over the words of the
+// row); else a band of image rows, 2^slot_shift word slots per row = the words left of the row and those right of it (a
+// word that straddles column w rewrites the image pixels it holds with their own values).
 __device__ __forceinline__ void apron_region(const LevelGeom &L, int plane, int region, int tid, int nthreads)
 {
-    const int W = L.w, H = L.h, pitch = L.ipitch;
+    const int W = L.w, H = L.h, pitch = L.ipitch, A = L.apron, cols = apron_cols(A), side_l = cols / 4, side_r = side_l + 1;
     uint8_t *plane0 = L.img + (size_t)plane * L.iplane_px;
-    constexpr int n_tb = (2 * kApron + kApronRep - 1) / kApronRep;
-    if (region < n_tb) {
-        const int row_words = (W + 3) / 4 + 2 * kSideL;
-        for (int r = region * kApronRep; r < min((region + 1) * kApronRep, 2 * kApron); ++r) {
-            const int ty = r < kApron ? r - kApron : H + (r - kApron);
-            uint32_t *dst = reinterpret_cast<uint32_t *>(plane0 + (ptrdiff_t)ty * pitch - kApronCols);
-            for (int i = tid; i < row_words; i += nthreads) dst[i] = apron_word_load(plane0, pitch, W, H, 4 * i - kApronCols, ty);
-        }
+    if (region < 2 * A) {
+        const int row_words = (W + 3) / 4 + 2 * side_l;
+        const int ty = region < A ? region - A : H + (region - A);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(plane0 + (ptrdiff_t)ty * pitch - cols);
+        for (int i = tid; i < row_words; i += nthreads) dst[i] = apron_word_load(plane0, pitch, W, H, 4 * i - cols, ty);
     } else {
-        const int c = tid & 15;
-        if (c >= kSideL + kSideR) return;
-        const int tx = c < kSideL ? 4 * c - kApronCols : (W & ~3) + 4 * (c - kSideL);
-        const int y0 = (region - n_tb) * kApronRep * (nthreads / 16) + (tid >> 4);
-        uint32_t v[kApronRep];
-#pragma unroll
-        for (int k = 0; k < kApronRep; ++k) {              // loads first: one round trip to L2
-            const int ty = y0 + k * (nthreads / 16);
-            if (ty < H) v[k] = apron_word_load(plane0, pitch, W, H, tx, ty);
-        }
-#pragma unroll
-        for (int k = 0; k < kApronRep; ++k) {
-            const int ty = y0 + k * (nthreads / 16);
-            if (ty < H) *reinterpret_cast<uint32_t *>(plane0 + (ptrdiff_t)ty * pitch + tx) = v[k];
-        }
+        const int sh = apron_slot_shift(A), c = tid & ((1 << sh) - 1);
+        if (c >= side_l + side_r) return;
+        const int tx = c < side_l ? 4 * c - cols : (W & ~3) + 4 * (c - side_l);
+        const int ty = (region - 2 * A) * (nthreads >> sh) + (tid >> sh);
+        if (ty < H) *reinterpret_cast<uint32_t *>(plane0 + (ptrdiff_t)ty * pitch + tx) = apron_word_load(plane0, pitch, W, H, tx, ty);
     }
 }
 
@@ -120,7 +114,7 @@ apron_kernel(const ApronLevels A, const PlaneList planes)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");     // the pyramid launch before this one has completed
     const LevelGeom &L = A.lv[blockIdx.y];
-    if ((int)blockIdx.x < apron_regions(L.h, kApronThreads))
+    if ((int)blockIdx.x < apron_regions(L.h, L.apron, kApronThreads))
         apron_region(L, planes.plane[blockIdx.z], blockIdx.x, threadIdx.x, kApronThreads);
 }
 
@@ -134,7 +128,7 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         asm volatile("griddepcontrol.wait;" ::: "memory");
         const int region = ((int)blockIdx.y - tiles_y) * (int)gridDim.x + (int)blockIdx.x;
-        if (region < apron_regions(cur.h, 128)) apron_region(cur, planes.plane[blockIdx.z], region, threadIdx.x, 128);
+        if (region < apron_regions(cur.h, cur.apron, 128)) apron_region(cur, planes.plane[blockIdx.z], region, threadIdx.x, 128);
         return;
     }
     __shared__ __align__(128) uint32_t tile[kBoxH * kRowWords];
@@ -295,7 +289,7 @@ int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, c
     const LevelGeom &nxt = pyr.lv[has_next ? level + 1 : level];
     cudaLaunchConfig_t cfg = {};
     const int tiles_x = (cur.w + kTileW - 1) / kTileW, tiles_y = (cur.h + kTileH - 1) / kTileH;
-    const int apron_y = (cur.apron && with_apron) ? (apron_regions(cur.h, 128) + tiles_x - 1) / tiles_x : 0;   // extra grid rows
+    const int apron_y = (cur.apron && with_apron) ? (apron_regions(cur.h, cur.apron, 128) + tiles_x - 1) / tiles_x : 0;   // extra grid rows
     cfg.gridDim = dim3(tiles_x, tiles_y + apron_y, planes.n);
     cfg.blockDim = dim3(128);
     cfg.dynamicSmemBytes = 0;
@@ -319,7 +313,7 @@ int launch_apron(const PyrDesc &pyr, int first_level, int last_level, const Plan
     int regions = 0;
     for (int l = first_level; l <= last_level; ++l) {
         A.lv[l - first_level] = pyr.lv[l];
-        regions = max(regions, apron_regions(pyr.lv[l].h, kApronThreads));
+        regions = max(regions, apron_regions(pyr.lv[l].h, pyr.lv[l].apron, kApronThreads));
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(regions, A.n, planes.n);

@@ -37,7 +37,7 @@ class Params(C.Structure):
                 ("levels", C.c_int), ("ring_slots", C.c_int), ("win_w", C.c_int), ("win_h", C.c_int),
                 ("max_iters", C.c_int), ("epsilon", C.c_double), ("min_eig_thresh", C.c_float),
                 ("fb_thresh", C.c_float), ("max_points", C.c_int), ("max_targets", C.c_int),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("apron", C.c_int)]
 
 
 class TrackJob(C.Structure):
@@ -135,7 +135,7 @@ class KLTContext:
 
     def __init__(self, width, height, n_cameras=1, levels=4, win=(21, 21), ring_slots=4, max_iters=30,
                  epsilon=0.01, min_eig_thresh=1e-4, fb_thresh=1.0, max_points=1 << 16, max_targets=1 << 12,
-                 device=0, stream=None):
+                 device=0, stream=None, apron=0):
         self.lib = load()
         p = default_params()
         p.device, p.n_cameras, p.width, p.height = device, n_cameras, width, height
@@ -143,6 +143,7 @@ class KLTContext:
         p.max_iters, p.epsilon, p.min_eig_thresh, p.fb_thresh = max_iters, epsilon, min_eig_thresh, fb_thresh
         p.max_points, p.max_targets = max_points, max_targets
         p.stream = stream
+        p.apron = apron
         self.params = p
         self.width, self.height, self.n_cameras = width, height, n_cameras
         self.do_fb = fb_thresh >= 0

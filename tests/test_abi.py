@@ -38,9 +38,10 @@ def test_no_undeclared_exports():
 
 
 def test_params_layout_matches_header():
-    # int x9, double, float x2, int x2, pointer  (natural alignment)
-    assert C.sizeof(klt.Params) == 72
+    # int x9, double, float x2, int x2, pointer, int  (natural alignment)
+    assert C.sizeof(klt.Params) == 80
     p = klt.default_params()
+    assert p.apron == 0
     assert (p.levels, p.ring_slots, p.win_w, p.win_h, p.max_iters) == (4, 4, 21, 21, 30)
     assert p.epsilon == 0.01 and abs(p.min_eig_thresh - 1e-4) < 1e-10 and p.fb_thresh == 1.0
     assert C.sizeof(klt.TrackJob) == 80

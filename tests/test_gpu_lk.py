@@ -108,8 +108,9 @@ def test_c2_shaped_batch_vs_oracle(oracle, fb):
         assert j["status"].mean() > 0.5          # the synthetic texture is trackable
 
 
+@pytest.mark.parametrize("apron", [0, 64])
 @pytest.mark.parametrize("w,h", [(200, 150), (333, 97), (768, 576)])
-def test_border_seeds_all_levels(oracle, w, h):
+def test_border_seeds_all_levels(oracle, w, h, apron):
     """Seeds hugging every border and corner: the windows cross the frame edge on every pyramid level (REFLECT_101 image
     apron kept in HBM on levels >= 1, on-the-fly mirror on level 0, zero derivative apron), some leave the frame."""
     rng = np.random.default_rng(w + h)
@@ -123,7 +124,7 @@ def test_border_seeds_all_levels(oracle, w, h):
     y = np.where(side == 2, band, np.where(side == 3, h - 1 - band, t * (h - 1)))
     corners = np.array([[0.5, 0.5], [w - 1.5, 0.5], [0.5, h - 1.5], [w - 1.5, h - 1.5], [10.0, 10.0], [w - 11.0, h - 11.0]])
     pts = np.concatenate([np.stack([x, y], 1), corners]).astype(np.float32)
-    with klt.KLTContext(w, h, levels=4, fb_thresh=1.0) as ctx:
+    with klt.KLTContext(w, h, levels=4, fb_thresh=1.0, apron=apron) as ctx:
         ctx.push_frame(f0); ctx.push_frame(f1)
         o, st, er, fb = ctx.track(pts)
         ml = ctx.levels - 1
@@ -162,7 +163,8 @@ def test_ragged_many_jobs_batch(oracle):
         assert np.abs(j["fb_err"] - g_fb).max() <= 1e-4
 
 
-def test_reference_faithful_per_target_windows(oracle):
+@pytest.mark.parametrize("apron", [0, 64])
+def test_reference_faithful_per_target_windows(oracle, apron):
     """Reference call pattern: window (int)box.w x (int)box.h per target (Tracker2D.cpp:877), default 4 levels."""
     w, h, ntgt = 768, 576, 12
     cam = synth.Camera(w, h, ntgt, cam=9)
@@ -170,7 +172,7 @@ def test_reference_faithful_per_target_windows(oracle):
     boxes = cam.boxes(0)
     pts, tid = synth.seeds_in_boxes(boxes, 50, w, h, np.random.default_rng(5))
     win = np.stack([boxes[:, 2].astype(np.int32), boxes[:, 3].astype(np.int32)], 1)
-    with klt.KLTContext(w, h, levels=4, fb_thresh=-1.0) as ctx:
+    with klt.KLTContext(w, h, levels=4, fb_thresh=-1.0, apron=apron) as ctx:
         ctx.push_frame(f0); ctx.push_frame(f1)
         o, st, er, _ = ctx.track(pts, target_of_pt=tid, win_wh=win)
     pa, pb = oracle.build_pyramid(f0, 3), oracle.build_pyramid(f1, 3)

@@ -8,7 +8,7 @@ from mcmtt_opticalflow_b200 import klt, synth
 pytestmark = pytest.mark.gpu
 
 
-def _check_levels(ctx, oracle, img, cam=0, slot=0):
+def _check_levels(ctx, oracle, img, cam=0, slot=0, apron=26):
     cur = img
     for l in range(ctx.levels):
         if l:
@@ -17,15 +17,15 @@ def _check_levels(ctx, oracle, img, cam=0, slot=0):
         assert g_img.shape == cur.shape
         assert np.array_equal(g_img, cur), "u8 level %d differs" % l
         assert np.array_equal(g_dxy, oracle.scharr(cur)), "Scharr level %d differs" % l
-        _check_apron(ctx, cur, cam, slot, l)
+        _check_apron(ctx, cur, cam, slot, l, apron)
 
 
-def _check_apron(ctx, img, cam, slot, level):
+def _check_apron(ctx, img, cam, slot, level, apron=26):
     """Levels >= 1 keep a REFLECT_101 apron in HBM (what copyMakeBorder builds around every level inside
     calcOpticalFlowPyrLK); every apron pixel a single reflection defines must equal np.pad(mode='reflect')."""
     pad, a = ctx.read_level_apron(cam, slot, level)
     h, w = img.shape
-    assert a == (26 if level else 0)
+    assert a == (apron if level else 0)
     assert np.array_equal(pad[a:a + h, a:a + w], img)
     if not a:
         return
@@ -47,6 +47,18 @@ def test_bit_exact_vs_oracle(oracle, monkeypatch, w, h, levels, mode):
     with klt.KLTContext(w, h, n_cameras=1, levels=levels) as ctx:
         ctx.push_frame(img)
         _check_levels(ctx, oracle, img)
+
+
+@pytest.mark.parametrize("mode", ["level", "fused"])
+@pytest.mark.parametrize("apron,w,h,levels", [(64, 768, 576, 4), (40, 333, 97, 4), (160, 640, 480, 5), (5, 130, 70, 3)])
+def test_apron_width_is_a_context_parameter(oracle, monkeypatch, apron, w, h, levels, mode):
+    """psnw_params.apron: wider aprons for contexts that track large windows (clamped to [26, 160])."""
+    monkeypatch.setenv("PSNW_PYR_MODE", mode)
+    rng = np.random.default_rng(apron * 7 + w)
+    img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    with klt.KLTContext(w, h, n_cameras=1, levels=levels, apron=apron) as ctx:
+        ctx.push_frame(img)
+        _check_levels(ctx, oracle, img, apron=min(max(apron, 26), 160))
 
 
 def test_golden_fixture(golden):

@@ -11,7 +11,8 @@ w, h, ntgt, T = 768, 576, 40, 24
 cam = synth.Camera(w, h, ntgt, cam=0)
 frames = [cam.frame(t) for t in range(T)]
 boxes = [cam.boxes(t) for t in range(T)]
-with klt.KLTContext(w, h, levels=4, fb_thresh=-1.0, max_points=1 << 16, max_targets=1 << 10) as ctx:
+with klt.KLTContext(w, h, levels=4, fb_thresh=-1.0, max_points=1 << 16, max_targets=1 << 10,
+                    apron=int(os.environ.get("PSNW_APRON", "64"))) as ctx:        # per-target windows up to ~55 x 130: see psnw_params.apron
     trk = tracker2d.Tracker2D(ctx)
     ts, nobj = [], []
     for t in range(T):
