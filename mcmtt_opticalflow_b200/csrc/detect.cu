@@ -198,6 +198,27 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
         // each warp owns a contiguous segment of n2 / nwarps keys: compare distances inside a segment only need
         // __syncwarp; the few stages that cross segments take a block barrier (6 instead of ~60)
         const int seg = n2 / nwarps, sbase = warp * seg;
+        if (n2 == kSelThreads) {
+            // the usual case, one key per thread: the key stays in a register, partners inside the warp are exchanged with
+            // shuffles (35 of the 45 stages), partners in other warps through shared memory
+            unsigned long long key = s_list[tid];
+            for (int k = 2; k <= n2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    unsigned long long other;
+                    if (j >= 32) {
+                        s_list[tid] = key;
+                        __syncthreads();
+                        other = s_list[tid ^ j];
+                        __syncthreads();
+                    } else {
+                        other = __shfl_xor_sync(0xffffffffu, key, j);
+                    }
+                    // descending blocks keep the larger key at the lower index of a pair, ascending ones the smaller
+                    const bool keep_max = ((tid & j) == 0) == ((tid & k) == 0);
+                    key = keep_max ? (key > other ? key : other) : (key < other ? key : other);
+                }
+            s_list[tid] = key;
+        } else
         for (int k = 2; k <= n2; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
                 if (j >= seg) {
