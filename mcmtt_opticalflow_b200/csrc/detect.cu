@@ -133,22 +133,27 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     const int tx0 = max(T.x0 - 1, 0), ty0 = max(T.y0 - 1, 0), tx1 = min(T.x1 + 1, w), ty1 = min(T.y1 + 1, h);
     const int tw = tx1 - tx0, th = ty1 - ty0;
     const bool tiled = tw * th <= tile_cap;
+    float m = -FLT_MAX;                                          // 1. max of the map under the mask ...
     if (tiled) {
+        // ... taken while the tile is loaded: the threads walk the tile linearly (every lane busy whatever its width)
+        int y = tid / tw, x = tid - y * tw;
+        const int sy = kSelThreads / tw, sx = kSelThreads - sy * tw;
 #pragma unroll 4
-        for (int y = warp; y < th; y += nwarps) {
-            const float *src = eig + (size_t)(ty0 + y) * pitch + tx0;
-            for (int x = lane; x < tw; x += 32) tile[y * tw + x] = src[x];
+        for (int i = tid; i < tw * th; i += kSelThreads) {
+            const float v = eig[(size_t)(ty0 + y) * pitch + tx0 + x];
+            tile[i] = v;
+            if (tx0 + x >= T.x0 && tx0 + x < T.x1 && ty0 + y >= T.y0 && ty0 + y < T.y1) m = fmaxf(m, v);
+            x += sx; y += sy;
+            if (x >= tw) { x -= tw; y++; }
         }
     }
-    __syncthreads();
     const float *mp = tiled ? tile - (ty0 * tw + tx0) : eig;     // map pointer such that mp[y * ms + x] is pixel (x, y)
     const int ms = tiled ? tw : pitch;
-
-    // 1. max of the map under the mask
-    float m = -FLT_MAX;
+    if (!tiled) {
 #pragma unroll 2
-    for (int y = T.y0 + warp; y < T.y1; y += nwarps)
-        for (int x = T.x0 + lane; x < T.x1; x += 32) m = fmaxf(m, mp[y * ms + x]);
+        for (int y = T.y0 + warp; y < T.y1; y += nwarps)
+            for (int x = T.x0 + lane; x < T.x1; x += 32) m = fmaxf(m, mp[y * ms + x]);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) s_maxw[warp] = m;
@@ -161,8 +166,13 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     // 2. candidates: above threshold, 3x3 local maximum of the thresholded map, not on the frame border
     unsigned long long *glist = cand_all + T.cand_begin;
     const int cx0 = max(T.x0, 1), cx1 = min(T.x1, w - 1), cy0 = max(T.y0, 1), cy1 = min(T.y1, h - 1);
-    for (int y = cy0 + warp; y < cy1; y += nwarps)
-        for (int x = cx0 + lane; x < cx1; x += 32) {
+    const int cw = max(cx1 - cx0, 1), n_cand_px = (cx1 > cx0 && cy1 > cy0) ? cw * (cy1 - cy0) : 0;
+    int cyy = cy0 + tid / cw, cxx = cx0 + (tid - (tid / cw) * cw);
+    const int csy = kSelThreads / cw, csx = kSelThreads - csy * cw;
+    for (int i = tid; i < n_cand_px; i += kSelThreads, cxx += csx, cyy += csy) {
+        {
+            if (cxx >= cx1) { cxx -= cw; cyy++; }
+            const int x = cxx, y = cyy;
             const float *p = mp + y * ms + x;
             const float v = p[0];
             if (!(v > thr)) continue;
@@ -182,6 +192,7 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
                 if (pos < T.cand_cap) glist[pos] = key;
             }
         }
+    }
     __syncthreads();
     const int nc = min(s_nc, T.cand_cap);
     const float md2 = __fmul_rn(min_dist, min_dist);
