@@ -466,7 +466,7 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
 {
     if (!out || !p) return PSNW_EARG;
     *out = nullptr;
-    if (p->n_cameras < 1 || p->width < 16 || p->height < 16 || p->levels < 1 || p->levels > PSNW_MAX_LEVELS ||
+    if (p->n_cameras < 1 || p->width < 16 || p->height < 16 || p->width > 32768 || p->height > 32768 || p->levels < 1 || p->levels > PSNW_MAX_LEVELS ||
         p->ring_slots < 1 || p->win_w < 1 || p->win_h < 1 || p->max_iters < 0 || p->max_points < 1 || p->max_targets < 1)
         return PSNW_EARG;
     int ndev = 0;

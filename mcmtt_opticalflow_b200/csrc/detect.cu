@@ -112,6 +112,7 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     __shared__ float s_maxw[kSelThreads / 32];
     __shared__ __align__(16) unsigned s_acc[kMaxAccepted + 4];   // accepted corners (x | y << 16), padded with far-away sentinels
     __shared__ int s_nc, s_nout;
+    __shared__ __align__(16) unsigned s_near[32];                // chunk-local "too close to an earlier lane" masks of the walk
 
     const DetectTarget T = targets[blockIdx.x];
     const float *__restrict__ eig = T.eig;
@@ -169,24 +170,33 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     const int cw = max(cx1 - cx0, 1), n_cand_px = (cx1 > cx0 && cy1 > cy0) ? cw * (cy1 - cy0) : 0;
     int cyy = cy0 + tid / cw, cxx = cx0 + (tid - (tid / cw) * cw);
     const int csy = kSelThreads / cw, csx = kSelThreads - csy * cw;
-    for (int i = tid; i < n_cand_px; i += kSelThreads, cxx += csx, cyy += csy) {
-        {
-            if (cxx >= cx1) { cxx -= cw; cyy++; }
-            const int x = cxx, y = cyy;
+    // uniform trip count: the list slots of a warp's candidates are reserved with one atomic per warp and step
+    for (int i0 = 0; i0 < n_cand_px; i0 += kSelThreads, cxx += csx, cyy += csy) {
+        if (cxx >= cx1) { cxx -= cw; cyy++; }
+        const int x = cxx, y = cyy;
+        bool is_max = false;
+        float v = 0.f;
+        if (i0 + tid < n_cand_px) {
             const float *p = mp + y * ms + x;
-            const float v = p[0];
-            if (!(v > thr)) continue;
-            bool is_max = true;
+            v = p[0];
+            if (v > thr) {
+                is_max = true;
 #pragma unroll
-            for (int j = -1; j <= 1; ++j)
+                for (int j = -1; j <= 1; ++j)
 #pragma unroll
-                for (int i = -1; i <= 1; ++i) {
-                    float u = p[j * ms + i];
-                    u = (u > thr) ? u : 0.f;
-                    is_max = is_max && !(u > v);
-                }
+                    for (int i = -1; i <= 1; ++i) {
+                        float u = p[j * ms + i];
+                        u = (u > thr) ? u : 0.f;
+                        is_max = is_max && !(u > v);
+                    }
+            }
+        }
+        const unsigned found = __ballot_sync(0xffffffffu, is_max);
+        if (found) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&s_nc, __popc(found));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(found & ((1u << lane) - 1u));
             if (is_max) {
-                const int pos = atomicAdd(&s_nc, 1);
                 const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
                 if (pos < smem_cap) s_list[pos] = key;
                 if (pos < T.cand_cap) glist[pos] = key;
@@ -260,10 +270,13 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
             // the bit mask of EARLIER lanes of the chunk that are too close; (c) the in-order greedy rule becomes a
             // 32-step bit recurrence that all lanes evaluate identically: lane j is accepted iff it survived (a) and
             // none of its close predecessors was accepted.
+            // Coordinates are integers: distances are exact in int32 and d2 < min_dist^2 <=> d2 < ceil(min_dist^2).
+            const int md2i = (int)fminf(ceilf(md2), 2.0e9f);
             for (int base = 0; base < nc && n_out < max_per_target; base += 32) {
                 const unsigned long long key = (base + lane < nc) ? s_list[base + lane] : 0ull;
                 const unsigned idx = (unsigned)key;
-                const float x = (float)(int)(idx % (unsigned)w), y = (float)(int)(idx / (unsigned)w);
+                const int xi = (int)(idx % (unsigned)w), yi = (int)(idx / (unsigned)w);
+                const unsigned xy = (unsigned)xi | ((unsigned)yi << 16);
                 bool alive = key != 0ull;
                 unsigned near = 0u;
                 if (suppress) {
@@ -272,28 +285,36 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
                         const unsigned qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const float dx = x - (float)(int)(qq[u] & 0xffffu), dy = y - (float)(int)(qq[u] >> 16);
-                            if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2) alive = false;
+                            const int dx = xi - (int)(qq[u] & 0xffffu), dy = yi - (int)(qq[u] >> 16);   // |d| < 32768: no overflow
+                            if (a + u < n_out && dx * dx + dy * dy < md2i) alive = false;
                         }
                     }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const float dx = x - __shfl_sync(0xffffffffu, x, i), dy = y - __shfl_sync(0xffffffffu, y, i);
-                        if (i < lane && __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < md2) near |= 1u << i;
+                        const unsigned q = __shfl_sync(0xffffffffu, xy, i);
+                        const int dx = xi - (int)(q & 0xffffu), dy = yi - (int)(q >> 16);
+                        if (i < lane && dx * dx + dy * dy < md2i) near |= 1u << i;
                     }
                 }
                 const unsigned pre = __ballot_sync(0xffffffffu, alive);
+                s_near[lane] = near;
+                __syncwarp();
                 unsigned acc = 0u;
                 int room = max_per_target - n_out;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const unsigned nj = __shfl_sync(0xffffffffu, near, j);
-                    if (room > 0 && ((pre >> j) & 1u) && (nj & acc) == 0u) { acc |= 1u << j; --room; }
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const uint4 nq = *reinterpret_cast<const uint4 *>(&s_near[4 * j4]);     // broadcast reads
+                    const unsigned nj4[4] = {nq.x, nq.y, nq.z, nq.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int j = 4 * j4 + u;
+                        if (room > 0 && ((pre >> j) & 1u) && (nj4[u] & acc) == 0u) { acc |= 1u << j; --room; }
+                    }
                 }
                 if ((acc >> lane) & 1u) {
                     const int slot = n_out + __popc(acc & ((1u << lane) - 1u));
-                    s_acc[slot] = (unsigned)(int)x | ((unsigned)(int)y << 16);
-                    my_out[slot] = make_float2(x, y);
+                    s_acc[slot] = xy;
+                    my_out[slot] = make_float2((float)xi, (float)yi);
                 }
                 n_out += __popc(acc);
                 __syncwarp();
