@@ -168,43 +168,52 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     unsigned long long *glist = cand_all + T.cand_begin;
     const int cx0 = max(T.x0, 1), cx1 = min(T.x1, w - 1), cy0 = max(T.y0, 1), cy1 = min(T.y1, h - 1);
     const int cw = max(cx1 - cx0, 1), n_cand_px = (cx1 > cx0 && cy1 > cy0) ? cw * (cy1 - cy0) : 0;
-    int cyy = cy0 + tid / cw, cxx = cx0 + (tid - (tid / cw) * cw);
     const int csy = kSelThreads / cw, csx = kSelThreads - csy * cw;
-    // uniform trip count: the list slots of a warp's candidates are reserved with one atomic per warp and step
-    for (int i0 = 0; i0 < n_cand_px; i0 += kSelThreads, cxx += csx, cyy += csy) {
-        if (cxx >= cx1) { cxx -= cw; cyy++; }
-        const int x = cxx, y = cyy;
-        bool is_max = false;
-        float v = 0.f;
-        if (i0 + tid < n_cand_px) {
-            const float *p = mp + y * ms + x;
-            v = p[0];
-            if (v > thr) {
-                is_max = true;
+    // Pass 0 keeps the keys in shared memory only; the global list (for the rounds of 3b) is written by a second pass in
+    // the rare case that they do not fit -- the usual target sends nothing to HBM here.
+    int nc = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int cyy = cy0 + tid / cw, cxx = cx0 + (tid - (tid / cw) * cw);
+        // uniform trip count: the list slots of a warp's candidates are reserved with one atomic per warp and step
+        for (int i0 = 0; i0 < n_cand_px; i0 += kSelThreads, cxx += csx, cyy += csy) {
+            if (cxx >= cx1) { cxx -= cw; cyy++; }
+            const int x = cxx, y = cyy;
+            bool is_max = false;
+            float v = 0.f;
+            if (i0 + tid < n_cand_px) {
+                const float *p = mp + y * ms + x;
+                v = p[0];
+                if (v > thr) {
+                    is_max = true;
 #pragma unroll
-                for (int j = -1; j <= 1; ++j)
+                    for (int j = -1; j <= 1; ++j)
 #pragma unroll
-                    for (int i = -1; i <= 1; ++i) {
-                        float u = p[j * ms + i];
-                        u = (u > thr) ? u : 0.f;
-                        is_max = is_max && !(u > v);
-                    }
+                        for (int i = -1; i <= 1; ++i) {
+                            float u = p[j * ms + i];
+                            u = (u > thr) ? u : 0.f;
+                            is_max = is_max && !(u > v);
+                        }
+                }
+            }
+            const unsigned found = __ballot_sync(0xffffffffu, is_max);
+            if (found) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&s_nc, __popc(found));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(found & ((1u << lane) - 1u));
+                if (is_max) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+                    if (pass == 0) { if (pos < smem_cap) s_list[pos] = key; }
+                    else if (pos < T.cand_cap) glist[pos] = key;
+                }
             }
         }
-        const unsigned found = __ballot_sync(0xffffffffu, is_max);
-        if (found) {
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(&s_nc, __popc(found));
-            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(found & ((1u << lane) - 1u));
-            if (is_max) {
-                const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
-                if (pos < smem_cap) s_list[pos] = key;
-                if (pos < T.cand_cap) glist[pos] = key;
-            }
-        }
+        __syncthreads();
+        nc = min(s_nc, T.cand_cap);
+        if (pass == 1 || (nc <= smem_cap && max_per_target <= kMaxAccepted)) break;      // uniform: the sorted path serves it
+        __syncthreads();
+        if (tid == 0) s_nc = 0;
+        __syncthreads();
     }
-    __syncthreads();
-    const int nc = min(s_nc, T.cand_cap);
     const float md2 = __fmul_rn(min_dist, min_dist);
     const bool suppress = min_dist >= 1.f;
     int n_out = 0;

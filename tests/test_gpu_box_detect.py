@@ -103,6 +103,22 @@ def test_min_eig_map_bit_exact_and_selection(golden, oracle):
         assert np.array_equal(pts[0, :counts[0]], golden["tie_out"])               # exact ties: higher address first
 
 
+@pytest.mark.parametrize("box,max_per,min_dist", [([0, 0, 768, 576], 300, 4.0),      # candidates exceed the shared list
+                                                  ([100, 80, 400, 300], 1500, 2.0),   # more corners than the shared accepted list
+                                                  ([10, 10, 60, 140], 100, 0.0)])     # no suppression
+def test_detect_global_list_path(oracle, box, max_per, min_dist):
+    """Targets whose candidates do not fit shared memory (or that ask for > 1024 corners) take the second candidate pass
+    into the global list and the block-wide arg-max rounds; results as goodFeaturesToTrack's restatement."""
+    w, h = 768, 576
+    f = synth.Camera(w, h, 10, cam=8).frame(0)
+    with klt.KLTContext(w, h, levels=2, max_targets=64) as c:
+        c.push_frame(f)
+        pts, counts = c.detect([box], max_per, 0.01, min_dist)
+        eig = c.read_min_eig()
+    want = oracle.detect(f, np.array(box, np.float64), max_per, 0.01, min_dist, eig=eig)
+    assert counts[0] == len(want) and np.array_equal(pts[0, :counts[0]], want)
+
+
 def test_detect_full_rig_vs_oracle(oracle):
     w, h, ntgt = 768, 576, 40
     cam = synth.Camera(w, h, ntgt, cam=4)
