@@ -567,6 +567,14 @@ def main():
         if args.workload == "c2":
             try:      # issue-slot utilisation and instruction count of the same launch from the committed ncu --set full capture
                 lk["ncu"] = json.load(open(os.path.join(ROOT, "profiles", "r01_lk_issue.json")))
+                # instruction roofline of the launch: executed warp-instructions (ncu count per solve x solves of this launch)
+                # over the live launch time, against SMs x 4 schedulers x 1 instruction per clock at the clock sampled above
+                props = torch.cuda.get_device_properties(torch.cuda.current_device())
+                mhz = ((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+                peak_issue = props.multi_processor_count * 4 * mhz * 1e6
+                ach_issue = lk["ncu"]["warp_instructions_per_solve"] * 2 * rig.npts / lk_sec
+                lk["issue_roofline"] = {"bound": "sm issue", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9,
+                                        "unit": "G warp-instructions/s", "frac": ach_issue / peak_issue}
             except Exception:
                 pass
         line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
