@@ -119,6 +119,27 @@ def test_detect_global_list_path(oracle, box, max_per, min_dist):
     assert counts[0] == len(want) and np.array_equal(pts[0, :counts[0]], want)
 
 
+def test_detect_mixed_roi_sizes(oracle):
+    """C3-shaped targets (1080p, 256 corners per target): ROIs smaller and larger than the shared-memory tile, clipped by
+    every frame border, and one outside the frame, in one launch."""
+    w, h = 1920, 1080
+    f = synth.Camera(w, h, 12, cam=4).frame(0)
+    boxes = np.array([[300.0, 200.0, 60.0, 150.0],        # 9 000 px
+                      [700.0, 100.0, 137.0, 330.0],       # 45 000 px
+                      [-20.0, 700.0, 260.0, 400.0],       # clipped left / bottom
+                      [1700.0, -30.0, 400.0, 123.0],      # clipped right / top
+                      [1000.0, 500.0, 128.0, 128.0],      # 16 900 px with the ring: just over the 64 KB tile
+                      [2500.0, 300.0, 50.0, 50.0]])       # outside the frame
+    with klt.KLTContext(w, h, levels=2, max_targets=64) as c:
+        c.push_frame(f)
+        pts, counts = c.detect(boxes, 256, 0.01, 3.0)
+        eig = c.read_min_eig()
+    for t, b in enumerate(boxes):
+        want = oracle.detect(f, b, 256, 0.01, 3.0, eig=eig)
+        assert counts[t] == len(want) and np.array_equal(pts[t, :counts[t]], want), t
+    assert counts[5] == 0 and counts[1] == 256
+
+
 def test_detect_full_rig_vs_oracle(oracle):
     w, h, ntgt = 768, 576, 40
     cam = synth.Camera(w, h, ntgt, cam=4)

@@ -44,6 +44,7 @@ def jn():
 ctx.join = jn
 
 acc = {}
+all_evs = []
 with t.cuda.stream(rig.stream):
     for i in range(60):
         rig.flush.zero_()
@@ -52,8 +53,11 @@ with t.cuda.stream(rig.stream):
         rig.step(host)
         mark("end", evs)
         if host: ctx.sync()
-        rig.stream.synchronize()
-        if i >= 10:
-            for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
-                acc.setdefault(n1, []).append(e0.elapsed_time(e1) * 1e3)
+        if os.environ.get('QT_SYNC', '1') == '1': rig.stream.synchronize()
+        all_evs.append(evs)
+
+rig.stream.synchronize()
+for evs in all_evs[10:]:
+    for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+        acc.setdefault(n1, []).append(e0.elapsed_time(e1) * 1e3)
 print(json.dumps({k: round(float(np.mean(v)), 1) for k, v in acc.items()}), "total_us", round(sum(float(np.mean(v)) for v in acc.values()), 1))
