@@ -208,15 +208,15 @@ class GpuRig:
             mem |= self.klt.PUSH_EIG         # the next step detects on this frame: its Shi-Tomasi map is built with the pyramid
         self.ctx._ck(self.ctx.lib.psnw_push_frames(self.ctx._h, self.ncam, self.cams.ctypes.data, ptrs, self.w, t_idx, mem))
 
-    def _detect(self, t_idx, seeds, counts, mem):
-        """Shi-Tomasi seeds inside the detection boxes of frame t_idx, all cameras in one batched call."""
-        key = (t_idx, seeds.data_ptr())
+    def _detect(self, t_idx, seeds, counts, mem, slot=0):
+        """Shi-Tomasi seeds inside the detection boxes of frame t_idx (ring slot `slot`), all cameras in one batched call."""
+        key = (t_idx, seeds.data_ptr(), slot)
         jobs = self._det_cache.get(key)
         if jobs is None:
             jobs = (self.klt.DetectJob * self.ncam)()
             for c in range(self.ncam):
                 j = jobs[c]
-                j.cam, j.slot, j.boxes, j.n_targets = c, 0, self.boxes[c][t_idx].ctypes.data, self.ntgt
+                j.cam, j.slot, j.boxes, j.n_targets = c, slot, self.boxes[c][t_idx].ctypes.data, self.ntgt
                 j.pts_xy = seeds.data_ptr() + c * self.npts_cam * 8
                 j.counts = counts.data_ptr() + c * self.ntgt * 4
             self._det_cache[key] = jobs

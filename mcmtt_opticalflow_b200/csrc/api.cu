@@ -65,6 +65,7 @@ struct psnw_ctx {
     DevBuf desc;                          // job / group descriptors (track)
     unsigned *lk_work = nullptr;          // [2] work counters of the persistent 21x21 LK kernel (self-resetting)
     int lk_ctas = 0;                      // resident CTAs of that kernel on this device
+    int lk_tail = 0;                      // points at the end of a large batch whose two passes are separate work items
     bool lk_persistent = true;            // persistent warps + work counter; PSNW_LK_PERSISTENT=0 (bring-up): one point per warp
     DevBuf det_desc;                      // target descriptors + staged outputs (detect; may run on the aux stream)
     DevBuf cand;                          // detect candidate scratch
@@ -501,8 +502,11 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     if (configure_lk_kernels() || configure_box_kernels() || configure_detect_kernels() || configure_fused_kernels()) return bail(PSNW_ECUDA);
     ctx->lk_ctas = lk_w21_resident_ctas(0);
     if (ctx->lk_ctas <= 0) return bail(PSNW_ECUDA);
-    if (cudaMalloc(&ctx->lk_work, 2 * sizeof(unsigned)) != cudaSuccess) return bail(PSNW_ENOMEM);
-    cudaMemsetAsync(ctx->lk_work, 0, 2 * sizeof(unsigned), ctx->stream);
+    if (cudaMalloc(&ctx->lk_work, (2 + kLkTailMax) * sizeof(unsigned)) != cudaSuccess) return bail(PSNW_ENOMEM);
+    cudaMemsetAsync(ctx->lk_work, 0, (2 + kLkTailMax) * sizeof(unsigned), ctx->stream);
+    ctx->lk_tail = 2 * ctx->lk_ctas * 4;  // two waves of warps
+    if (const char *m = getenv("PSNW_LK_TAIL")) ctx->lk_tail = atoi(m);
+    ctx->lk_tail = std::min(std::max(ctx->lk_tail, 0), kLkTailMax);
     if (const char *m = getenv("PSNW_LK_PERSISTENT")) ctx->lk_persistent = m[0] == '1';
     if (const char *m = getenv("PSNW_PYR_MODE")) ctx->pyr_mode = !strcmp(m, "level") ? 1 : !strcmp(m, "fused") ? 2 : 0;
     // the side streams outrank the context stream: their short kernels (pyramid, detection) take the SM slots that LK
@@ -826,6 +830,8 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     P.fb_thresh = ctx->p.fb_thresh;
     P.do_fb = do_fb ? 1 : 0;
     P.work = ctx->lk_persistent ? ctx->lk_work : nullptr;
+    // (a batch that is all tail would only add the hand-over: small batches keep one item per point)
+    P.split_from = (P.work && P.do_fb && all21 && P.n_pts >= 2 * ctx->lk_tail) ? P.n_pts - ctx->lk_tail : P.n_pts;
     P.tmaps = ctx->lk_maps;
     const int r = launch_lk(P, all21 ? 1 : 0, max_win_px, ctx->lk_ctas, ctx->stream);
     if (r == -2) return fail(ctx, PSNW_EARG, "psnw_klt_track: window too large for shared memory");

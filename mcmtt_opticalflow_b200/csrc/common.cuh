@@ -78,8 +78,11 @@ struct LkParams {
     float fb_thresh;
     int do_fb;
     const CUtensorMap *tmaps; // [3 * level + {0: I box 48x22, 1: J box 48x30, 2: (dx,dy) box 28x22}] of the 21x21 kernel (lk.cu)
-    unsigned *work;           // [2] point counter / finished-warp counter of the persistent 21x21 kernel (zero between launches)
+    unsigned *work;           // [2 + kLkTailMax] item counter / finished-warp counter of the persistent 21x21 kernel, then the
+                              // hand-over flags of the split tail (all zero between launches)
+    int split_from;           // points >= split_from are tracked as two work items (forward, then backward); = n_pts: none
 };
+constexpr int kLkTailMax = 16384;   // capacity of the split tail (points)
 
 // per-device kernel attributes (opt-in dynamic shared memory); called by psnw_create on the context's device
 int configure_lk_kernels();

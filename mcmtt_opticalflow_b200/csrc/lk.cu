@@ -362,6 +362,17 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
     o.x = next_x; o.y = next_y; o.st = st; o.err = st ? er : 0.f;
 }
 
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // point index -> job (n_jobs is small; linear scan is uniform across the warp)
 __device__ __forceinline__ int find_job(const TrackJob *jobs, int n_jobs, int i)
 {
@@ -764,7 +775,13 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
     if (lane == 0) { mbar_init(S.bar_src, 1); mbar_init(S.bar_tgt, 1); }
     __syncwarp();
 
+    // Work items: point i < split_from is one item (forward + backward pass); the points of the tail are two items each --
+    // forward passes first, [split_from, n_pts), then their backward passes, [n_pts, n_pts + n_tail) -- so that the last
+    // items of the launch are half as long and the grid drains sooner.  A forward item hands its result over through the
+    // point's output slots and a flag (1 + status); items are drawn in order and a forward item never waits, so the
+    // backward item that spins on the flag always makes progress.
     const bool persistent = P.work != nullptr;
+    const int n_items = P.n_pts + (P.n_pts - P.split_from);
     for (int it = 0;; ++it) {
         int i = blockIdx.x * kWarpsPerCta + wib;
         if (persistent) {
@@ -773,7 +790,10 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
         } else if (it) {
             break;                               // one point per warp: the hardware CTA scheduler balances the load
         }
-        if (i >= P.n_pts) break;
+        if (i >= n_items) break;
+        const bool bwd_only = i >= P.n_pts;
+        if (bwd_only) i = P.split_from + (i - P.n_pts);
+        const bool fwd_only = !bwd_only && i >= P.split_from;
 
         const TrackJob *jobs = P.jobs ? P.jobs : P.ejobs;
         const TrackJob &job = jobs[find_job(jobs, P.n_jobs, i)];
@@ -787,14 +807,35 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
         Solve f, b, cur;
         f.x = f.y = f.err = 0.f; f.st = 1;
         b = f;
-        const int npass = P.do_fb ? 2 : 1;
+        unsigned *flag = P.work + 2 + (i - P.split_from);
+        if (bwd_only) {
+            unsigned v = 0;
+            if (lane == 0) {
+                while ((v = ld_acquire(flag)) == 0u) __nanosleep(100);
+                *flag = 0u;                      // self-cleaning: the next launch finds zeros
+                const float2 q = __ldcg(&job.out[k]);
+                f.x = q.x; f.y = q.y; f.err = __ldcg(&job.err[k]);
+            }
+            f.st = (int)__shfl_sync(0xffffffffu, v, 0) - 1;
+            f.x = __shfl_sync(0xffffffffu, f.x, 0); f.y = __shfl_sync(0xffffffffu, f.y, 0);
+        }
+        const int first = bwd_only ? 1 : 0, last = (P.do_fb && !fwd_only) ? 2 : 1;
 #pragma unroll 1
-        for (int pass = 0; pass < npass; ++pass) {
+        for (int pass = first; pass < last; ++pass) {
             const float sx = pass ? f.x : p0.x, sy = pass ? f.y : p0.y;
             solve_w21(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, S, R, pass == 0, cur);
             if (pass) b = cur; else f = cur;
         }
-        finish_point(P, job, k, p0, f, b, lane);
+        if (fwd_only) {
+            if (lane == 0) {
+                job.out[k] = make_float2(f.x, f.y);
+                job.err[k] = f.err;
+                __threadfence();
+                st_release(flag, 1u + (unsigned)f.st);
+            }
+        } else {
+            finish_point(P, job, k, p0, f, b, lane);
+        }
     }
     if (persistent && lane == 0) {
         const unsigned total = gridDim.x * kWarpsPerCta;

@@ -300,3 +300,30 @@ def test_north_star_gates_against_cv2_live(oracle):
     assert agree / total >= MIN_STATUS_AGREE, agree / total
     assert within / max(n_ok, 1) >= MIN_WITHIN_TOL, within / max(n_ok, 1)
     assert np.min(ious) >= 0.99, np.min(ious)                # measured: 1.0 / 1.0 (max 0.006 px) / min IoU 0.999998
+
+
+def test_split_tail_items_equal_fused_items(monkeypatch):
+    """The persistent 21x21 kernel tracks the last points of a large batch as two work items (forward pass, then backward
+    pass, handed over through a flag) so that the grid drains sooner.  Whatever the length of that tail -- none, a few
+    points, half the batch -- and however often the launch repeats (the flags clean themselves), all outputs are
+    bit-identical."""
+    w, h = 768, 576
+    cam = synth.Camera(w, h, 30, cam=3)
+    a, b = cam.frame(0), cam.frame(1)
+    rng = np.random.default_rng(23)
+    pts = np.concatenate([synth.seeds_in_boxes(cam.boxes(0), 200, w, h, rng)[0],
+                          rng.uniform(-5, [w + 5, h + 5], size=(300, 2)).astype(np.float32)])     # some seeds leave the frame
+    res = {}
+    for tail in ("0", "7", "1000", str(len(pts) // 2)):
+        monkeypatch.setenv("PSNW_LK_TAIL", tail)
+        with klt.KLTContext(w, h, levels=4, fb_thresh=1.0, max_points=len(pts)) as ctx:
+            ctx.push_frame(a); ctx.push_frame(b)
+            runs = [ctx.track(pts) for _ in range(3)]
+        for r in runs[1:]:
+            for x, y in zip(runs[0], r):
+                assert np.array_equal(x, y), tail
+        res[tail] = runs[0]
+    for tail, r in res.items():
+        for x, y in zip(res["0"], r):
+            assert np.array_equal(x, y), tail
+    assert 0.5 < res["0"][1].mean() < 1.0
