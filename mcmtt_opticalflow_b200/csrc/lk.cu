@@ -462,7 +462,9 @@ __device__ __forceinline__ bool window_oob(int ix, int iy, int w, int h)
 // per-lane roles, fixed for the whole kernel
 struct WarpRole {
     int lane;
-    int row0, col0, row1, col1;   // the lane's two runs: run r -> (row r / 3, first column 7 * (r % 3)); lane 31 owns one
+    // the lane's two runs: run r -> (row r / 3, first column 7 * (r % 3)); lane 31 owns one
+    int off0, off1;               // byte offset of the runs' first sample in a staged u8 patch: row * 48 + column
+    int doff0, doff1;             // word offset of the runs' first pixel in the staged derivative patch: row * 28 + column
     bool two;
 };
 
@@ -521,10 +523,12 @@ __device__ __forceinline__ int stage_u8(const LkParams &P, int level, int plane,
 // Bilinear sums of a horizontal run of 7 samples starting at byte column `bc` of patch row `row`:
 //   v[k] = c[k] + w_tl*p(k) + w_tr*p(k+1) + w_bl*q(k) + w_br*q(k+1),  wt/wb = (w_left | w_right << 16) of the top /
 // bottom row.  The 8+8 bytes are aligned with funnel shifts and fed to dp2a without unpacking.
-__device__ __forceinline__ void bilinear_run7(const uint32_t *patch, int row, int bc, int wt, int wb, const int c[7], int v[7])
+__device__ __forceinline__ void bilinear_run7(const uint32_t *patch, int t, int wt, int wb, const int c[7], int v[7])
 {
-    const uint32_t *p = patch + row * kU8Pitch + (bc >> 2);
-    const int sh = (bc & 3) * 8;
+    // t = byte offset of the first sample inside the patch (row * 48 + byte column); the funnel shift only looks at the low
+    // five bits of its count, so (t << 3) is the bit offset inside the aligned word
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(patch) + (t & ~3));
+    const int sh = t << 3;
     const uint32_t t0 = __funnelshift_r(p[0], p[1], sh), t1 = __funnelshift_r(p[1], p[2], sh);
     const uint32_t u0 = __funnelshift_r(p[kU8Pitch], p[kU8Pitch + 1], sh);
     const uint32_t u1 = __funnelshift_r(p[kU8Pitch + 1], p[kU8Pitch + 2], sh);
@@ -643,10 +647,9 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             const int c256[7] = {256, 256, 256, 256, 256, 256, 256};
 #pragma unroll
             for (int run = 0; run < 2; ++run) {
-                const int row = run ? R.row1 : R.row0, col = run ? R.col1 : R.col0;
                 int v[7];
-                bilinear_run7(ip, row, offI + col, wt, wb, c256, v);
-                const uint32_t *d0 = dxp + row * kDxPitch + offD + col, *d1 = d0 + kDxPitch;
+                bilinear_run7(ip, (run ? R.off1 : R.off0) + offI, wt, wb, c256, v);
+                const uint32_t *d0 = dxp + (run ? R.doff1 : R.doff0) + offD, *d1 = d0 + kDxPitch;
                 uint32_t q0 = d0[0], q1 = d1[0];
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
@@ -693,12 +696,12 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                 __syncwarp();
                 staged = true;
             }
-            const int bx = offJ + (inx - sx0), by = iny - sy0;
+            const int tj = (iny - sy0) * (kU8Pitch * 4) + offJ + (inx - sx0);
             int b1[2] = {0, 0}, b2[2] = {0, 0};
 #pragma unroll
             for (int run = 0; run < 2; ++run) {
                 int v[7];
-                bilinear_run7(jp, by + (run ? R.row1 : R.row0), bx + (run ? R.col1 : R.col0), jt, jb, &tC[run * 7], v);
+                bilinear_run7(jp, tj + (run ? R.off1 : R.off0), jt, jb, &tC[run * 7], v);
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
                     const int diff = v[k] >> 9;
@@ -725,12 +728,12 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                 stage_wait_tgt(S);
                 __syncwarp();
             }
-            const int bx = offJ + (inx - sx0), by = iny - sy0;
+            const int tj = (iny - sy0) * (kU8Pitch * 4) + offJ + (inx - sx0);
             int e = 0;
 #pragma unroll
             for (int run = 0; run < 2; ++run) {
                 int v[7];
-                bilinear_run7(jp, by + (run ? R.row1 : R.row0), bx + (run ? R.col1 : R.col0), jt, jb, &tC[run * 7], v);
+                bilinear_run7(jp, tj + (run ? R.off1 : R.off0), jt, jb, &tC[run * 7], v);
                 if (run == 0 || R.two) {
 #pragma unroll
                     for (int k = 0; k < 7; ++k) {
@@ -765,8 +768,9 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
     R.two = lane < 31;
     {
         const int r0 = lane, r1 = R.two ? lane + 32 : 62;
-        R.row0 = r0 / 3; R.col0 = 7 * (r0 - 3 * R.row0);
-        R.row1 = r1 / 3; R.col1 = 7 * (r1 - 3 * R.row1);
+        const int row0 = r0 / 3, col0 = 7 * (r0 - 3 * row0), row1 = r1 / 3, col1 = 7 * (r1 - 3 * row1);
+        R.off0 = row0 * (kU8Pitch * 4) + col0; R.off1 = row1 * (kU8Pitch * 4) + col1;
+        R.doff0 = row0 * kDxPitch + col0; R.doff1 = row1 * kDxPitch + col1;
     }
     Stage S;
     S.bar_src = smem_u32(&bars[wib][0]); S.bar_tgt = smem_u32(&bars[wib][1]);
