@@ -47,6 +47,24 @@ def test_params_layout_matches_header():
     assert C.sizeof(klt.TrackJob) == 80
 
 
+def test_python_constants_match_header():
+    """The ctypes stub restates the header's flags and error codes: compile a tiny C program that prints the header's values."""
+    import tempfile
+    names = ["PSNW_MEM_HOST", "PSNW_MEM_PINNED", "PSNW_MEM_DEVICE", "PSNW_MEM_OVERLAP", "PSNW_PUSH_EIG",
+             "PSNW_OK", "PSNW_EARG", "PSNW_ECUDA", "PSNW_ENOMEM", "PSNW_ESTATE", "(int)sizeof(psnw_params)",
+             "(int)sizeof(psnw_track_job)", "(int)sizeof(psnw_detect_job)"]
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "c.c")
+        open(src, "w").write('#include <stdio.h>\n#include "psnw_klt.h"\nint main(void){%s return 0;}\n'
+                             % "".join('printf("%%d\\n", (int)(%s));' % n for n in names))
+        exe = os.path.join(d, "c")
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.dirname(HEADER), src, "-o", exe])
+        vals = [int(v) for v in subprocess.check_output([exe]).decode().split()]
+    want = [klt.MEM_HOST, klt.MEM_PINNED, klt.MEM_DEVICE, klt.MEM_OVERLAP, klt.PUSH_EIG, 0, klt.EARG, klt.ECUDA, klt.ENOMEM,
+            klt.ESTATE, C.sizeof(klt.Params), C.sizeof(klt.TrackJob), C.sizeof(klt.DetectJob)]
+    assert vals == want
+
+
 def test_header_compiles_as_c():
     subprocess.check_call(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", HEADER])
 
