@@ -558,7 +558,9 @@ def main():
                                              pyr_launches, ncam))
         roofline = {"kernel": pyr_kernel,
                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "algorithmic_bytes": alg, "ms": 1e3 * pyr_mean, "best_ms": 1e3 * pyr_best, "peak_source": peak_src}
+                    "algorithmic_bytes": alg, "ms": 1e3 * pyr_mean, "best_ms": 1e3 * pyr_best, "peak_source": peak_src,
+                    "note": "the HBM-bound kernel group of the path (SURVEY 8d); the kernel that dominates the step, lk_w21_kernel, is "
+                            "neither HBM- nor tensor-bound: its SM-issue roofline is in lk.issue_roofline"}
         roofline["frames_in_flight_sweep"] = pyramid_sweep(rig, peak) if args.workload == "c2" else None
         lk_sec, st_frac = rig.time_track()
         lk = {"kernel": "lk_w21_kernel (fwd+bwd fused, persistent warps, TMA-staged patches)", "ms": 1e3 * lk_sec,
