@@ -56,13 +56,14 @@ enum { PSNW_MEM_HOST = 0, PSNW_MEM_PINNED = 1, PSNW_MEM_DEVICE = 2 };
 /* OR-ed into mem_flags (PINNED / DEVICE only; ignored with HOST).
  *  psnw_klt_detect(_batch): the detection runs on an auxiliary stream forked from the context stream at the call, so the
  *    psnw_klt_track / psnw_box_update calls that FOLLOW overlap with it (they must not consume its outputs).  The outputs
- *    are complete after psnw_join (device-side join, no host block), psnw_sync, or the next plain push / detect call.
+ *    are complete, for work enqueued afterwards on the context stream, after psnw_join (device-side join, no host block) or the
+ *    next plain push / detect call; the HOST may read them only after psnw_sync.
  *  psnw_push_frame(s)(_bgr): the upload and the pyramid build run on an upload stream that waits only for the launches
  *    already enqueued that read the ring slots being recycled -- not for the rest of the context stream -- so the NEXT
  *    frame is ingested while the current one is still being tracked (one frame in flight).  The ring rotates at the call:
  *    slot numbers in later calls refer to the new ring, and every later call that reads frames (track, detect, read_*)
  *    first makes the context stream wait for the push (device-side, no host block).  The caller keeps the source
- *    frames unchanged until psnw_sync or psnw_join. */
+ *    frames unchanged until psnw_sync (psnw_join only orders device work, it does not wait on the host). */
 #define PSNW_MEM_OVERLAP 0x100
 /* OR-ed into the mem_flags of psnw_push_frame(s): also compute the Shi-Tomasi min-eigenvalue map of the pushed frames
  * (a psnw_klt_detect on them will follow and then finds it ready).  Each camera keeps two maps, so the map of a frame
@@ -100,10 +101,15 @@ typedef struct psnw_params {
                              levels.  Results do not depend on it. */
 } psnw_params;
 
-/* Fills *p with the reference-faithful defaults (4 levels, 21x21, 30 it, 0.01, 1e-4, fb 1.0, 4 slots). */
+/* Fills *p with the defaults: OpenCV's calcOpticalFlowPyrLK defaults as the reference uses them (4 levels, 21x21, 30
+ * iterations, 0.01, 1e-4), 4 ring slots, and north_star's forward-backward gate fb_thresh = 1.0 px.  The reference itself
+ * has NO per-point forward-backward gate: a caller that mirrors Tracker2D.cpp:776 / :871
+ * literally sets fb_thresh < 0 (mcmtt_opticalflow_b200's Tracker2D mirror refuses a context that does not). */
 PSNW_API int psnw_default_params(psnw_params *p);
 
 PSNW_API int psnw_create(psnw_ctx **out, const psnw_params *p);   /* Tracker2D::Initialize, .cpp:99-163 */
+/* The parameters the context runs with (after psnw_create's clamping of max_iters / epsilon / apron). */
+PSNW_API int psnw_get_params(psnw_ctx *ctx, psnw_params *out);
 PSNW_API int psnw_destroy(psnw_ctx *ctx);                         /* Tracker2D::Finalize,   .cpp:176-237 */
 
 /*
@@ -177,7 +183,9 @@ PSNW_API int psnw_read_fast_map(psnw_ctx *ctx, int cam, uint8_t *map_out);
  *                         pass out_xy -> p'' and sets status = st_f & st_b & (|p - p''| <= fb_thresh),
  *                         fb_err = |p - p''| (may be NULL to drop it).  With fb_thresh < 0 it is ignored.
  * Pyramid levels are truncated per window exactly like buildOpticalFlowPyramid (level kept while both
- * dimensions stay > window).
+ * dimensions stay > window).  A target whose window cannot be tracked here (side < 1, not smaller than the frame, or more
+ * than ~34 000 pixels) is skipped, not an error: its points come back unmoved with status 0, the other targets of the
+ * batch are tracked as usual.
  */
 PSNW_API int psnw_klt_track(psnw_ctx *ctx, int cam, int slot_from, int slot_to,
                             const float *pts_xy, const int *target_of_pt, int n_pts,
@@ -238,7 +246,10 @@ PSNW_API int psnw_points_in_boxes(psnw_ctx *ctx, const float *pts_xy, const int 
                                   const double *det_boxes, int n_detections, int *counts, int mem_flags);
 
 PSNW_API int psnw_sync(psnw_ctx *ctx);
-/* Device-side join of an overlapped detect into the context stream (see PSNW_MEM_OVERLAP). */
+/* Device-side join of an overlapped detect / push into the context stream (see PSNW_MEM_OVERLAP): work enqueued on the
+ * context stream AFTER this call is ordered after them.  It does NOT block the host: host-visible buffers (pinned
+ * source frames, pinned or pageable outputs) may be reused or read only after psnw_sync -- or after the caller has
+ * synchronised the context stream (psnw_get_stream) itself once psnw_join has returned. */
 PSNW_API int psnw_join(psnw_ctx *ctx);
 PSNW_API const char *psnw_last_error(psnw_ctx *ctx);
 PSNW_API void *psnw_get_stream(psnw_ctx *ctx);

@@ -106,6 +106,14 @@ void CPSNWhere_Tracker2D::Initialize(unsigned int nCamID, psnw_ctx *ctx, int cam
     m_stTrack2DResult.camID = nCamID; m_stTrack2DResult.frameIdx = 0;
     m_stTrack2DResult.object2DInfos.clear(); m_stTrack2DResult.matMatchingCost.clear();
     m_stTrack2DResult.costRows = m_stTrack2DResult.costCols = 0;
+    // The reference has no per-point forward-backward gate (its status is calcOpticalFlowPyrLK's alone, :883-888): this
+    // mirror reproduces the reference only on a context created with fb_thresh < 0, and refuses any other.
+    psnw_params kp;
+    if (!ctx || psnw_get_params(ctx, &kp) != PSNW_OK || kp.fb_thresh >= 0.f) {
+        m_strError = "CPSNWhere_Tracker2D::Initialize: the context must be created with fb_thresh < 0 (the reference has no forward-backward gate)";
+        m_bInit = false;
+        return;
+    }
     m_bInit = true;
 }
 

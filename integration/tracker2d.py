@@ -1,4 +1,4 @@
-"""ctypes front-end of the C++ host mirror of CPSNWhere_Tracker2D (mcmtt_opticalflow_b200/host/psnw_tracker2d.*).
+"""ctypes front-end of the C++ host mirror of CPSNWhere_Tracker2D (integration/psnw_tracker2d.*).
 
 The class itself is C++ (the reference is compiled code); this module only lets the Python tests and examples drive
 it: Tracker2D(ctx, cam).run(boxes, gray, frame_idx) == CPSNWhere_Tracker2D::Run (psn_where/PSNWhere_Tracker2D.cpp:251).
@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from . import klt
+from mcmtt_opticalflow_b200 import klt
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpsnw_tracker2d.so")
 _lib = None
@@ -19,7 +19,7 @@ def load():
     if _lib is None:
         klt.load()
         if not os.path.exists(LIB_PATH):
-            raise ImportError("%s is missing: build it with `make -C mcmtt_opticalflow_b200/csrc all`" % LIB_PATH)
+            raise ImportError("%s is missing: build it with `make -C integration`" % LIB_PATH)
         lib = C.CDLL(LIB_PATH)
         lib.psnt_create.restype = C.c_void_p
         lib.psnt_create.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int]

@@ -28,6 +28,7 @@ struct StageSlot {
 };
 
 constexpr int kStageSlots = 4;
+constexpr size_t kGenericSmemMax = 200 * 1024;   // template memory of lk_generic_kernel (6 B per pixel, rows padded to 4)
 
 }  // namespace
 
@@ -356,6 +357,35 @@ int advance_ring(psnw_ctx *ctx, int n, const int *cams, std::vector<int> &planes
     return PSNW_OK;
 }
 
+// A push that fails after advance_ring must not leave slot 0 pointing at a recycled plane with stale pixels: the
+// transaction restores head / held / plane_seq / seq of the cameras it rotated unless commit() is reached.
+struct RingTxn {
+    psnw_ctx *ctx;
+    std::vector<int> cams, head, held, planes;
+    std::vector<uint64_t> pseq;
+    uint64_t seq;
+    bool done = false;
+    RingTxn(psnw_ctx *c, int n, const int *cs) : ctx(c), seq(c->seq)
+    {
+        for (int i = 0; i < n; ++i) {
+            const int cam = cs[i];
+            if (cam < 0 || cam >= c->p.n_cameras) continue;       // advance_ring rejects the call before touching anything
+            cams.push_back(cam); head.push_back(c->head[cam]); held.push_back(c->held[cam]);
+            const int S = c->p.ring_slots, next = cam * S + (c->head[cam] + 1) % S;
+            planes.push_back(next); pseq.push_back(c->plane_seq[next]);
+        }
+    }
+    void commit() { done = true; }
+    ~RingTxn()
+    {
+        if (done) return;
+        for (size_t i = 0; i < cams.size(); ++i) {
+            ctx->head[cams[i]] = head[i]; ctx->held[cams[i]] = held[i]; ctx->plane_seq[planes[i]] = pseq[i];
+        }
+        ctx->seq = seq;
+    }
+};
+
 // make `st` wait for the launches already enqueued that read the listed resources (ring planes / min-eig buffers)
 int wait_readers(psnw_ctx *ctx, cudaStream_t st, const std::vector<int> &ids)
 {
@@ -561,6 +591,14 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     return PSNW_OK;
 }
 
+int psnw_get_params(psnw_ctx *ctx, psnw_params *out)
+{
+    if (!ctx || !out) return PSNW_EARG;
+    *out = ctx->p;
+    out->stream = (void *)ctx->stream;
+    return PSNW_OK;
+}
+
 int psnw_destroy(psnw_ctx *ctx)
 {
     if (!ctx) return PSNW_EARG;
@@ -609,8 +647,9 @@ int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const
     const bool eager_eig = (mem_flags & PSNW_PUSH_EIG) != 0;
     mem_flags &= 0xff;
     std::vector<int> planes;
+    RingTxn txn(ctx, n, cams);
     int rc = advance_ring(ctx, n, cams, planes, overlap);
-    if (rc) return rc;
+    if (rc) { txn.commit(); return rc; }                 // (advance_ring validates before it rotates)
     cudaStream_t st;
     rc = push_stream(ctx, overlap, planes, &st);
     if (rc) return rc;
@@ -647,7 +686,9 @@ int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const
         }
     }
     if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
-    return push_done(ctx, overlap);
+    rc = push_done(ctx, overlap);
+    if (rc == PSNW_OK) txn.commit();
+    return rc;
 }
 
 int psnw_push_frame(psnw_ctx *ctx, int cam, const uint8_t *gray, size_t pitch, uint32_t frame_idx, int mem_flags)
@@ -663,6 +704,8 @@ int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *c
     if (int rc_enter = enter(ctx)) return rc_enter;
     if (n <= 0 || !cams || !bgr || pitch < (size_t)ctx->p.width * 3 || (luma_bits != 14 && luma_bits != 15))
         return fail(ctx, PSNW_EARG, "psnw_push_frames_bgr arguments");
+    for (int i = 0; i < n; ++i)
+        if (!bgr[i]) return fail(ctx, PSNW_EARG, "null frame pointer");
     const bool overlap = (mem_flags & PSNW_MEM_OVERLAP) != 0 && (mem_flags & 0xff) != PSNW_MEM_HOST;
     mem_flags &= 0xff;
     const LevelGeom &l0 = ctx->pyr.lv[0];
@@ -672,8 +715,9 @@ int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *c
         if (rc) return rc;
     }
     std::vector<int> planes;
+    RingTxn txn(ctx, n, cams);
     int rc = advance_ring(ctx, n, cams, planes, overlap);
-    if (rc) return rc;
+    if (rc) { txn.commit(); return rc; }
     cudaStream_t st;
     rc = push_stream(ctx, overlap, planes, &st);
     if (rc) return rc;
@@ -684,7 +728,6 @@ int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *c
     for (int i = 0; i < n; ++i) {
         const uint8_t *src = bgr[i];
         size_t src_pitch = pitch;
-        if (!src) return fail(ctx, PSNW_EARG, "null frame pointer");
         if (mem_flags != PSNW_MEM_DEVICE) {
             uint8_t *dst = reinterpret_cast<uint8_t *>(ctx->bgr.p) + frame * i;
             CK(cudaMemcpy2DAsync(dst, row, bgr[i], pitch, (size_t)l0.w * 3, l0.h, cudaMemcpyHostToDevice, st));
@@ -698,7 +741,9 @@ int psnw_push_frames_bgr(psnw_ctx *ctx, int n, const int *cams, const uint8_t *c
     rc = build_pyramids(ctx, planes, st);
     if (rc) return rc;
     if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
-    return push_done(ctx, overlap);
+    rc = push_done(ctx, overlap);
+    if (rc == PSNW_OK) txn.commit();
+    return rc;
 }
 
 int psnw_rebuild_pyramids(psnw_ctx *ctx, int n, const int *cams)
@@ -726,6 +771,7 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     if (int rc_enter = enter(ctx)) return rc_enter;
     if (!jobs || n_jobs <= 0) return fail(ctx, PSNW_EARG, "psnw_klt_track_batch: no jobs");
     if (int rc_up = join_up(ctx)) return rc_up;          // an overlapped push may still be filling the slots tracked here
+    mem_flags &= 0xff;
     const bool dev = mem_flags == PSNW_MEM_DEVICE;
     int total = 0, total_groups = 0;
     for (int j = 0; j < n_jobs; ++j) {
@@ -746,7 +792,7 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     std::vector<TrackJob> dj(n_jobs);
     std::vector<TrackGroup> dg(total_groups);
     ctx->arena_off = 0;
-    bool all21 = true;
+    bool all21 = true, any_skipped = false;
     int max_win_px = 1;
     int pt = 0, gb = 0;
     const LevelGeom &l0 = ctx->pyr.lv[0];
@@ -755,11 +801,15 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
         const int pf = plane_of(ctx, J.cam, J.slot_from), pt_to = plane_of(ctx, J.cam, J.slot_to);
         for (int t = 0; t < J.n_targets; ++t) {
             const int ww = J.win_wh ? J.win_wh[2 * t] : ctx->p.win_w, wh = J.win_wh ? J.win_wh[2 * t + 1] : ctx->p.win_h;
-            if (ww < 1 || wh < 1 || ww >= l0.w || wh >= l0.h) return fail(ctx, PSNW_EARG, "psnw_klt_track: window must be >= 1 and smaller than the frame");
             TrackGroup &g = dg[gb + t];
             g.plane_from = pf; g.plane_to = pt_to; g.win_w = ww; g.win_h = wh;
-            g.max_level = effective_max_level(ctx, ww, wh);
             g.pad = 0;
+            // A window this path cannot track -- degenerate (< 1), not smaller than the frame, or larger than the template
+            // memory of the generic kernel -- disables ITS target only: the points come back unmoved with status 0 (the
+            // reference tracks every target in its own call, Tracker2D.cpp:776, :871; one bad box must not void the frame).
+            const bool untrackable = ww < 1 || wh < 1 || ww >= l0.w || wh >= l0.h || (((size_t)((ww + 3) & ~3) * wh + 7) & ~(size_t)7) * 6 > kGenericSmemMax;
+            if (untrackable) { g.max_level = -1; any_skipped = true; continue; }
+            g.max_level = effective_max_level(ctx, ww, wh);
             all21 = all21 && ww == 21 && wh == 21;
             max_win_px = std::max(max_win_px, ((ww + 3) & ~3) * wh);      // template rows are padded to 4 pixels (lk.cu)
         }
@@ -831,10 +881,10 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     P.do_fb = do_fb ? 1 : 0;
     P.work = ctx->lk_persistent ? ctx->lk_work : nullptr;
     // (a batch that is all tail would only add the hand-over: small batches keep one item per point)
-    P.split_from = (P.work && P.do_fb && all21 && P.n_pts >= 2 * ctx->lk_tail) ? P.n_pts - ctx->lk_tail : P.n_pts;
+    P.split_from = (P.work && P.do_fb && all21 && !any_skipped && P.n_pts >= 2 * ctx->lk_tail) ? P.n_pts - ctx->lk_tail : P.n_pts;
     P.tmaps = ctx->lk_maps;
     const int r = launch_lk(P, all21 ? 1 : 0, max_win_px, ctx->lk_ctas, ctx->stream);
-    if (r == -2) return fail(ctx, PSNW_EARG, "psnw_klt_track: window too large for shared memory");
+    if (r == -2) return fail(ctx, PSNW_EARG, "psnw_klt_track: window too large for shared memory");      // (unreachable: such targets are skipped)
     if (r < 0) return fail(ctx, PSNW_ECUDA, "lk kernel launch", cudaGetLastError());
     ctx->launches += r;
     {
@@ -897,6 +947,7 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
     if (n_targets < 0 || !boxes_in || !target_offsets || !boxes_out || !inlier_mask || !inlier_counts || mode != PSNW_BOX_REFERENCE)
         return fail(ctx, PSNW_EARG, "psnw_box_update arguments");
     if (n_targets > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_box_update: max_targets exceeded");
+    mem_flags &= 0xff;
     int r;
     if (mem_flags == PSNW_MEM_DEVICE) {
         r = launch_box_update(boxes_in, n_targets, reinterpret_cast<const float2 *>(pre_xy), reinterpret_cast<const float2 *>(cur_xy),
@@ -1101,6 +1152,12 @@ int psnw_klt_track_update(psnw_ctx *ctx, int cam, int slot_from, int slot_to, co
     if (n_targets == 0) return PSNW_OK;
     if (n_targets < 0 || !target_offsets || !boxes_in || !boxes_out || !inlier_mask || !inlier_counts)
         return fail(ctx, PSNW_EARG, "psnw_klt_track_update arguments");
+    mem_flags &= 0xff;
+    if (target_offsets[0] != 0) return fail(ctx, PSNW_EARG, "psnw_klt_track_update: target_offsets[0] must be 0");
+    for (int t = 0; t < n_targets; ++t) {
+        const int k = target_offsets[t + 1] - target_offsets[t];
+        if (k < 0 || k > PSNW_MAX_PTS_PER_TARGET) return fail(ctx, PSNW_EARG, "psnw_klt_track_update: offsets not ascending or > PSNW_MAX_PTS_PER_TARGET points in a target");
+    }
     if (mem_flags != PSNW_MEM_HOST) {
         // pinned / device memory: nothing to merge, the two calls already queue back to back on the context stream
         if (mem_flags == PSNW_MEM_DEVICE) return fail(ctx, PSNW_EARG, "psnw_klt_track_update: with device memory call psnw_klt_track_batch and psnw_box_update (target_offsets must be readable on the host)");
@@ -1108,6 +1165,7 @@ int psnw_klt_track_update(psnw_ctx *ctx, int cam, int slot_from, int slot_to, co
         std::vector<int> tgt(std::max(n, 1));
         for (int t = 0; t < n_targets; ++t)
             for (int i = target_offsets[t]; i < target_offsets[t + 1]; ++i) tgt[i] = t;
+        // (pinned memory is host memory: the pair runs as two synchronous calls, target_of_pt lives on this stack frame)
         int rc = psnw_klt_track(ctx, cam, slot_from, slot_to, pts_xy, tgt.data(), n, win_wh, n_targets, out_xy, status, err, nullptr, PSNW_MEM_HOST);
         if (rc) return rc;
         return psnw_box_update(ctx, boxes_in, n_targets, pts_xy, out_xy, use_status ? status : nullptr, target_offsets, PSNW_BOX_REFERENCE,
@@ -1115,11 +1173,7 @@ int psnw_klt_track_update(psnw_ctx *ctx, int cam, int slot_from, int slot_to, co
     }
     const int n_pts = target_offsets[n_targets];
     int max_per = 1;
-    for (int t = 0; t < n_targets; ++t) {
-        const int k = target_offsets[t + 1] - target_offsets[t];
-        if (k < 0 || k > PSNW_MAX_PTS_PER_TARGET) return fail(ctx, PSNW_EARG, "psnw_klt_track_update: offsets not ascending or > PSNW_MAX_PTS_PER_TARGET points in a target");
-        max_per = std::max(max_per, k);
-    }
+    for (int t = 0; t < n_targets; ++t) max_per = std::max(max_per, target_offsets[t + 1] - target_offsets[t]);
     if (n_pts <= 0)                               // nothing to track: the boxes come back as LocalSearchKLT returns them for no features
         return psnw_box_update(ctx, boxes_in, n_targets, pts_xy, out_xy, nullptr, target_offsets, PSNW_BOX_REFERENCE, boxes_out,
                                inlier_mask, inlier_counts, PSNW_MEM_HOST);
@@ -1178,6 +1232,7 @@ int psnw_points_in_boxes(psnw_ctx *ctx, const float *pts_xy, const int *tracker_
     if (n_trackers < 0 || n_detections < 0 || !tracker_offsets || !det_boxes || !counts)
         return fail(ctx, PSNW_EARG, "psnw_points_in_boxes arguments");
     if (n_trackers > ctx->p.max_targets || n_detections > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_points_in_boxes: max_targets exceeded");
+    mem_flags &= 0xff;
     int r;
     if (mem_flags == PSNW_MEM_DEVICE) {
         r = launch_points_in_boxes(reinterpret_cast<const float2 *>(pts_xy), tracker_offsets, n_trackers, det_boxes, n_detections, counts, ctx->stream);

@@ -89,6 +89,7 @@ box_update_kernel(const double *__restrict__ boxes_in, const float2 *__restrict_
             mvx[pos] = x; mvy[pos] = y; idx[pos] = i;
         }
     }
+    for (int i = n_all + tid; i < end - beg; i += kBoxThreads) mask[beg + i] = 0;   // points past the capacity never vote
     __syncthreads();
     const int n = s_n, n_moving = s_moving;
 

@@ -418,6 +418,12 @@ lk_generic_kernel(const __grid_constant__ LkParams P, int max_win_px)
 
     Solve f, b;
     b.x = b.y = b.err = 0.f; b.st = 1;
+    if (g.max_level < 0) {                       // untrackable window (api.cu): the point comes back unmoved with status 0
+        f.x = p0.x; f.y = p0.y; f.err = 0.f; f.st = 0;
+        b.x = p0.x; b.y = p0.y;
+        finish_point(P, job, k, p0, f, b, tid);
+        return;
+    }
     solve_generic(P, g.plane_from, g.plane_to, g.win_w, g.win_h, g.max_level, p0.x, p0.y, Iw, dIw, tid, red, f);
     if (P.do_fb) solve_generic(P, g.plane_to, g.plane_from, g.win_w, g.win_h, g.max_level, f.x, f.y, Iw, dIw, tid, red, b);
     finish_point(P, job, k, p0, f, b, tid);
@@ -822,6 +828,12 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
             }
             f.st = (int)__shfl_sync(0xffffffffu, v, 0) - 1;
             f.x = __shfl_sync(0xffffffffu, f.x, 0); f.y = __shfl_sync(0xffffffffu, f.y, 0);
+        }
+        if (g.max_level < 0) {                   // untrackable window (api.cu; no split tail then): unmoved, status 0
+            f.x = p0.x; f.y = p0.y; f.st = 0;
+            b.x = p0.x; b.y = p0.y;
+            finish_point(P, job, k, p0, f, b, lane);
+            continue;
         }
         const int first = bwd_only ? 1 : 0, last = (P.do_fb && !fwd_only) ? 2 : 1;
 #pragma unroll 1

@@ -56,7 +56,7 @@ EXPORTS = [
     "psnw_klt_detect_batch", "psnw_join", "psnw_gridfast_detect", "psnw_read_fast_map", "psnw_points_in_boxes", "psnw_default_params", "psnw_create", "psnw_destroy", "psnw_push_frame", "psnw_push_frames",
     "psnw_push_frames_bgr", "psnw_frames_held", "psnw_klt_detect", "psnw_klt_track", "psnw_klt_track_batch",
     "psnw_box_update", "psnw_sync", "psnw_last_error", "psnw_get_stream", "psnw_level_info", "psnw_read_level",
-    "psnw_read_level_apron", "psnw_klt_track_update",
+    "psnw_read_level_apron", "psnw_klt_track_update", "psnw_get_params",
     "psnw_read_min_eig", "psnw_launch_count", "psnw_push_frame_bytes", "psnw_rebuild_pyramids", "psnw_levels_built",
 ]
 
@@ -81,6 +81,7 @@ def load():
         lib.psnw_push_frame_bytes.argtypes = [C.c_void_p]
         lib.psnw_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Params)]
         lib.psnw_destroy.argtypes = [C.c_void_p]
+        lib.psnw_get_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         lib.psnw_sync.argtypes = [C.c_void_p]
         lib.psnw_join.argtypes = [C.c_void_p]
         lib.psnw_frames_held.argtypes = [C.c_void_p, C.c_int]

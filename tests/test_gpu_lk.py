@@ -202,8 +202,8 @@ def test_edge_cases(oracle):
         ctx.push_frame(flat); ctx.push_frame(flat)                               # no texture: min-eig gate rejects all
         o, st, er, _ = ctx.track(pts)
         assert st.sum() == 0
-        with pytest.raises(klt.PsnwError):
-            ctx.track(pts, win_wh=[[w, 5]])                                      # window >= frame
+        o, st, er, _ = ctx.track(pts, win_wh=[[w, 5]])                             # window >= frame: target skipped, not an error
+        assert st.sum() == 0 and np.array_equal(o, pts) and not er.any()
     with klt.KLTContext(w, h, levels=3) as ctx:
         with pytest.raises(klt.PsnwError) as e:
             ctx.track(np.zeros((4, 2), np.float32))                              # ring empty

@@ -37,7 +37,8 @@ def _check_apron(ctx, img, cam, slot, level, apron=26):
 
 @pytest.mark.parametrize("mode", ["level", "fused"])
 @pytest.mark.parametrize("w,h,levels", [(768, 576, 4), (767, 575, 4), (129, 33, 3), (16, 16, 2), (130, 70, 3),
-                                        (1920, 1080, 4), (257, 131, 5), (640, 480, 6), (193, 65, 4), (385, 129, 3)])
+                                        (1920, 1080, 4), (257, 131, 5), (640, 480, 6), (193, 65, 4), (385, 129, 3),
+                                        (3840, 2160, 5)])
 def test_bit_exact_vs_oracle(oracle, monkeypatch, w, h, levels, mode):
     """Both pyramid builders -- one launch per level (pyramid.cu) and the fused multi-level kernel (pyramid_fused.cu) --
     are forced in turn (PSNW_PYR_MODE is read at psnw_create); the default picks by launch size."""

@@ -3,7 +3,7 @@ Run() flow on the GPU."""
 import numpy as np
 import pytest
 
-from mcmtt_opticalflow_b200 import tracker2d
+from integration import tracker2d
 
 
 def test_hungarian_matches_scipy():

@@ -5,7 +5,8 @@ next to the same pattern on the CPU (tools/cpu_variants.py).  Wall clock per Run
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from mcmtt_opticalflow_b200 import klt, synth, tracker2d
+from mcmtt_opticalflow_b200 import klt, synth
+from integration import tracker2d
 
 w, h, ntgt, T = 768, 576, 40, 24
 cam = synth.Camera(w, h, ntgt, cam=0)
