@@ -52,11 +52,17 @@ struct psnw_ctx {
     PyrDesc pyr;
     uint8_t *img_alloc[PSNW_MAX_LEVELS] = {};   // allocation behind pyr.lv[l].img (which points at pixel (0,0) of plane 0)
     CUtensorMap maps[PSNW_MAX_LEVELS];
-    CUtensorMap map_fused;                // level-0 map with the box of the fused multi-level kernel
+    CUtensorMap map_fused[kFusedVariants];   // level-0 maps with the boxes of the fused multi-level kernel's region variants
+    CUtensorMap map_hyb[kFusedVariants];     // the same for level hyb_base: the per-level kernel builds levels < hyb_base, the fused one the rest
+    int hyb_base = 0, hyb_levels = 0;        // hyb_levels = 3 or 4 when that split exists (pyramids of >= 4 levels)
     CUtensorMap *lk_maps = nullptr;       // device copy of the LK kernel's patch maps: 3 per level (LkParams::tmaps)
     int fused_levels = 0;                 // 3 or 4 when the fused kernel is usable, else 0
     size_t fused_max_px = 2200000;   // auto mode: fused kernel up to this many level-0 pixels per launch
-    int pyr_mode = 0;                     // 0 auto, 1 per-level kernels only, 2 fused whenever possible (PSNW_PYR_MODE, bring-up)
+    size_t hybrid_max_frame_px = 600000;   // auto mode: larger launches of frames up to this size take the hybrid builder
+    int pyr_mode = 0;                     // 0 auto, 1 per-level kernels only, 2 fused from level 0, 3 hybrid (PSNW_PYR_MODE, bring-up)
+    int fused_variant = -1;               // -1 auto, else the region variant of the fused kernel (PSNW_FUSED_VARIANT, bring-up)
+    int fused_wide = -1;                  // -1 auto, else threads per CTA of the fused kernel: 256 / 512 / 1024 (PSNW_FUSED_THREADS, bring-up)
+    int sm_count = 148;
     int planes = 0;
     std::vector<int> head, held;
     std::vector<uint64_t> plane_seq;     // push counter per plane (min-eig cache tag)
@@ -189,18 +195,23 @@ int make_tensor_maps(psnw_ctx *ctx)
         }
     }
     ctx->fused_levels = ctx->pyr.levels >= 4 ? 4 : ctx->pyr.levels == 3 ? 3 : 0;
-    if (ctx->fused_levels) {
-        int bw = 0, bh = 0;
-        fused_box(ctx->fused_levels, &bw, &bh);
-        const LevelGeom &g = ctx->pyr.lv[0];
-        const cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)ctx->planes};
-        const cuuint64_t strides[2] = {(cuuint64_t)g.ipitch, (cuuint64_t)g.iplane_px};
-        const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        const CUresult r = encode(&ctx->map_fused, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(ctx, PSNW_ECUDA, "cuTensorMapEncodeTiled(fused level-0 map)");
+    ctx->hyb_levels = ctx->pyr.levels >= 4 ? std::min(4, ctx->pyr.levels - 1) : 0;
+    ctx->hyb_base = ctx->hyb_levels ? ctx->pyr.levels - ctx->hyb_levels : 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int nl = pass ? ctx->hyb_levels : ctx->fused_levels, base = pass ? ctx->hyb_base : 0;
+        for (int v = 0; nl && v < kFusedVariants; ++v) {
+            int bw = 0, bh = 0, ow = 0, oh = 0;
+            fused_geometry(nl, v, &bw, &bh, &ow, &oh);
+            const LevelGeom &g = ctx->pyr.lv[base];
+            const cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)ctx->planes};
+            const cuuint64_t strides[2] = {(cuuint64_t)g.ipitch, (cuuint64_t)g.iplane_px};
+            const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = encode(pass ? &ctx->map_hyb[v] : &ctx->map_fused[v], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, g.img, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(ctx, PSNW_ECUDA, "cuTensorMapEncodeTiled(fused kernel map)");
+        }
     }
     // patch maps of the 21x21 LK kernel: u8 image with the I box (48 x 22) and the J box (48 x 30), (dx,dy) image with the
     // 28 x 22 box.  Apron levels describe the whole padded plane -- the apron is ordinary memory to the copy -- and the
@@ -295,39 +306,71 @@ int effective_max_level(const psnw_ctx *c, int win_w, int win_h)
 
 cudaMemcpyKind h2d(int mem_flags) { return mem_flags == PSNW_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
 
+// region variant of the fused kernel for a launch over n planes of level `base`: the tallest region that still gives every
+// SM its two CTAs for a few rounds -- the halo rows every CTA recomputes weigh less the taller its region -- but never one
+// that leaves SMs without work.  *threads: 512 per CTA (two CTAs per SM) from level 0, 256 (four per SM) for the smaller
+// regions of the coarse-level launch of the hybrid builder.
+int fused_variant_for(const psnw_ctx *ctx, int base, int nl, int n, int *threads)
+{
+    const LevelGeom &g = ctx->pyr.lv[base];
+    int variant = 0;
+    size_t ctas0 = 0;
+    for (int v = kFusedVariants - 1; v >= 0; --v) {
+        int bw, bh, ow, oh;
+        fused_geometry(nl, v, &bw, &bh, &ow, &oh);
+        const size_t ctas = (size_t)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) * n;
+        if (v > 0 && variant == 0 && ctas >= (size_t)ctx->sm_count * 6) variant = v;
+        if (v == 0) ctas0 = ctas;
+    }
+    if (ctx->fused_variant >= 0) variant = ctx->fused_variant;
+    (void)ctas0;
+    *threads = base > 0 ? 256 : 512;
+    if (ctx->fused_wide >= 0) *threads = ctx->fused_wide;
+    return variant;
+}
+
 int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t st)
 {
-    for (size_t b = 0; b < planes.size(); b += 63) {
+    for (size_t b = 0; b < planes.size(); b += kMaxPlanesPerLaunch) {
         PlaneList pl;
-        pl.n = (int)std::min<size_t>(63, planes.size() - b);
+        pl.n = (int)std::min<size_t>(kMaxPlanesPerLaunch, planes.size() - b);
         for (int i = 0; i < pl.n; ++i) pl.plane[i] = planes[b + i];
-        // Small launches (a rig frame of a few small cameras) are latency-bound with one launch per level: there the
-        // fused kernel builds levels 0..3 in one launch.  Large launches keep the per-level kernels, which run at
-        // 70-90 % of the HBM roofline and do not recompute halos.
-        int first = 0;
-        const size_t px = (size_t)ctx->pyr.lv[0].w * ctx->pyr.lv[0].h * pl.n;
-        const bool fused = ctx->fused_levels && (ctx->pyr_mode == 2 || (ctx->pyr_mode == 0 && px <= ctx->fused_max_px));
-        if (fused) {
-            const int r = launch_pyr_fused(ctx->pyr, ctx->fused_levels, &ctx->map_fused, pl, st);
+        // Three builders (PSNW_PYR_MODE forces one):
+        //   fused   levels 0..3 AND their aprons in ONE launch of independent CTAs: a rig frame of a few small cameras, where
+        //           one launch per level would be pure latency;
+        //   hybrid  the per-level kernel for the finest level(s) (no halo recomputed where the pixels are), then ONE fused
+        //           launch for the remaining 3-4 levels and every apron: large batches and large frames;
+        //   level   one launch per level (each writes the apron of its input level with extra CTAs).
+        const LevelGeom &l0 = ctx->pyr.lv[0];
+        const size_t px = (size_t)l0.w * l0.h * pl.n;
+        int mode = ctx->pyr_mode;                                    // 1 level, 2 fused, 3 hybrid
+        // (measured, tools/pyr_sweep.py: 4 x 768x576 fused 14.0 us / level 15.9; 64 x 768x576 hybrid 56 us / level 64 / fused
+        // 62; 32 x 1080p level 93 us / hybrid 99; 16 x 4K level 163 us / hybrid 173)
+        if (mode == 0) mode = (ctx->fused_levels && px <= ctx->fused_max_px) ? 2 : (ctx->hyb_levels && (size_t)l0.w * l0.h <= ctx->hybrid_max_frame_px) ? 3 : 1;
+        if (mode == 2 && !ctx->fused_levels) mode = 1;
+        if (mode == 3 && !ctx->hyb_levels) mode = ctx->fused_levels ? 2 : 1;
+        int first = 0, last = ctx->pyr.levels;                       // levels [first, last) take the per-level kernel
+        if (mode == 2) {
+            int wide = 0;
+            const int variant = fused_variant_for(ctx, 0, ctx->fused_levels, pl.n, &wide);
+            const int r = launch_pyr_fused(ctx->pyr, 0, ctx->fused_levels, variant, wide, &ctx->map_fused[variant], pl, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_fused_kernel launch", cudaGetLastError());
             ctx->launches += r;
-            first = ctx->fused_levels < ctx->pyr.levels ? ctx->fused_levels - 1 : ctx->pyr.levels;   // level 3 again to feed level 4
+            // deeper pyramids: level 3 again (per-level kernel) only to feed level 4; it rewrites its apron with the same values
+            first = ctx->fused_levels < ctx->pyr.levels ? ctx->fused_levels - 1 : ctx->pyr.levels;
+        } else if (mode == 3) {
+            last = ctx->hyb_base;
         }
-        // Aprons (REFLECT_101 border of the levels >= 1, read by the LK kernel): a per-level launch writes the apron of its
-        // own input level with extra CTAs; the levels only the fused kernel produced get one apron launch.  When level
-        // `first` is re-run only to feed the next level (5-level pyramids) it carries its apron as well.
-        if (fused && first >= ctx->pyr.levels) {
-            const int r = launch_apron(ctx->pyr, 1, ctx->pyr.levels - 1, pl, st);
-            if (r < 0) return fail(ctx, PSNW_ECUDA, "apron_kernel launch", cudaGetLastError());
-            ctx->launches += r;
-        } else if (fused && first > 1) {
-            const int r = launch_apron(ctx->pyr, 1, first - 1, pl, st);
-            if (r < 0) return fail(ctx, PSNW_ECUDA, "apron_kernel launch", cudaGetLastError());
-            ctx->launches += r;
-        }
-        for (int l = first; l < ctx->pyr.levels; ++l) {
+        for (int l = first; l < last; ++l) {
             const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, 1, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_scharr_kernel launch", cudaGetLastError());
+            ctx->launches += r;
+        }
+        if (mode == 3) {
+            int wide = 0;
+            const int variant = fused_variant_for(ctx, ctx->hyb_base, ctx->hyb_levels, pl.n, &wide);
+            const int r = launch_pyr_fused(ctx->pyr, ctx->hyb_base, ctx->hyb_levels, variant, wide, &ctx->map_hyb[variant], pl, st);
+            if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_fused_kernel launch", cudaGetLastError());
             ctx->launches += r;
         }
     }
@@ -538,7 +581,11 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     if (const char *m = getenv("PSNW_LK_TAIL")) ctx->lk_tail = atoi(m);
     ctx->lk_tail = std::min(std::max(ctx->lk_tail, 0), kLkTailMax);
     if (const char *m = getenv("PSNW_LK_PERSISTENT")) ctx->lk_persistent = m[0] == '1';
-    if (const char *m = getenv("PSNW_PYR_MODE")) ctx->pyr_mode = !strcmp(m, "level") ? 1 : !strcmp(m, "fused") ? 2 : 0;
+    if (const char *m = getenv("PSNW_PYR_MODE")) ctx->pyr_mode = !strcmp(m, "level") ? 1 : !strcmp(m, "fused") ? 2 : !strcmp(m, "hybrid") ? 3 : 0;
+    if (const char *m = getenv("PSNW_FUSED_THREADS")) ctx->fused_wide = atoi(m);
+    if (const char *m = getenv("PSNW_FUSED_VARIANT")) ctx->fused_variant = std::min(std::max(atoi(m), 0), kFusedVariants - 1);
+    if (const char *m = getenv("PSNW_FUSED_MAX_PX")) ctx->fused_max_px = (size_t)atoll(m);
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, p->device);
     // the side streams outrank the context stream: their short kernels (pyramid, detection) take the SM slots that LK
     // warps free one by one instead of queueing behind the whole LK grid
     int prio_lo = 0, prio_hi = 0;

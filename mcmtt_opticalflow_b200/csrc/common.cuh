@@ -36,9 +36,10 @@ struct PyrDesc {
     int levels;
 };
 
+constexpr int kMaxPlanesPerLaunch = 255;
 struct PlaneList {
     int n;
-    int plane[63];
+    int plane[kMaxPlanesPerLaunch];
 };
 
 // One (job, target) of a klt_track launch.
@@ -93,12 +94,12 @@ int configure_detect_kernels();
 // with_apron: the launch also writes the REFLECT_101 apron of its input level (levels >= 1) with extra CTAs
 int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron,
                      cudaStream_t stream);
-// REFLECT_101 apron of levels first..last (clamped to >= 1) of the listed planes in one launch (after the fused kernel)
-int launch_apron(const PyrDesc &pyr, int first_level, int last_level, const PlaneList &planes, cudaStream_t stream);
-// fused multi-level variant (pyramid_fused.cu): levels 0..nl-1 in one launch; fused_box = TMA box of its level-0 map
-void fused_box(int nl, int *box_w, int *box_h);
+// fused multi-level variant (pyramid_fused.cu): levels 0..nl-1 AND their aprons in one launch.  Three region heights
+// (variant 0 / 1 / 2); fused_geometry = TMA box of the variant's level-0 map and the level-0 region one CTA owns
+constexpr int kFusedVariants = 3;
+void fused_geometry(int nl, int variant, int *box_w, int *box_h, int *own_w, int *own_h);
 int configure_fused_kernels();
-int launch_pyr_fused(const PyrDesc &pyr, int nl, const CUtensorMap *map0, const PlaneList &planes, cudaStream_t stream);
+int launch_pyr_fused(const PyrDesc &pyr, int base, int nl, int variant, int threads, const CUtensorMap *map0, const PlaneList &planes, cudaStream_t stream);
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,
                     int luma_bits, cudaStream_t stream);
 int lk_w21_resident_ctas(int max_per_sm);   // CTAs of the persistent 21x21 kernel resident at once on the current device (capped per SM when > 0), or -1

@@ -30,15 +30,10 @@ constexpr int kRowsPerWarp = 8;
 // arithmetic.  A thread writes one aligned 4-byte word of the apron: LevelGeom::apron rows above and below the image over the
 // padded width, and that many columns (rounded up to words) left and right of every image row; sources are the level's own
 // pixels (L2-resident).
-// The work is cut into regions of one CTA each (apron_regions): with one launch per level the regions of level l ride as
-// extra CTAs in that level's own pyr_scharr_kernel launch (level l is complete by then and nothing in the launch writes
-// it), so the apron costs neither a launch nor a serial tail; after the fused multi-level kernel one apron_kernel launch
-// covers every level >= 1 of every plane (grid.y = level - 1, grid.z = plane).
-constexpr int kApronThreads = 128;
-struct ApronLevels {
-    LevelGeom lv[PSNW_MAX_LEVELS];
-    int n;
-};
+// The work is cut into regions of one CTA each (apron_regions): the regions of level l ride as extra CTAs in that level's
+// own pyr_scharr_kernel launch (level l is complete by then and nothing in the launch writes it), so the apron costs
+// neither a launch nor a serial tail.  (The fused multi-level kernel, pyramid_fused.cu, scatters the apron from the
+// pixels each CTA holds in shared memory instead.)
 
 // a mirrored row is written as whole words: cols = apron rounded up to 4 pixels left of the image; right of it the words
 // start at the one that holds column w (w & ~3), one more than on the left
@@ -107,15 +102,6 @@ __device__ __forceinline__ void apron_region(const LevelGeom &L, int plane, int 
         const int ty = (region - 2 * A) * (nthreads >> sh) + (tid >> sh);
         if (ty < H) *reinterpret_cast<uint32_t *>(plane0 + (ptrdiff_t)ty * pitch + tx) = apron_word_load(plane0, pitch, W, H, tx, ty);
     }
-}
-
-__global__ void __launch_bounds__(kApronThreads)
-apron_kernel(const ApronLevels A, const PlaneList planes)
-{
-    asm volatile("griddepcontrol.wait;" ::: "memory");     // the pyramid launch before this one has completed
-    const LevelGeom &L = A.lv[blockIdx.y];
-    if ((int)blockIdx.x < apron_regions(L.h, L.apron, kApronThreads))
-        apron_region(L, planes.plane[blockIdx.z], blockIdx.x, threadIdx.x, kApronThreads);
 }
 
 template <bool kHasNext>
@@ -302,29 +288,6 @@ int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, c
     const cudaError_t e = has_next ? cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<true>, *map_in, cur, nxt, planes, tiles_y)
                                    : cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<false>, *map_in, cur, nxt, planes, tiles_y);
     return e == cudaSuccess ? 1 : -1;
-}
-
-int launch_apron(const PyrDesc &pyr, int first_level, int last_level, const PlaneList &planes, cudaStream_t stream)
-{
-    first_level = max(first_level, 1);
-    if (last_level < first_level) return 0;
-    ApronLevels A;
-    A.n = last_level - first_level + 1;
-    int regions = 0;
-    for (int l = first_level; l <= last_level; ++l) {
-        A.lv[l - first_level] = pyr.lv[l];
-        regions = max(regions, apron_regions(pyr.lv[l].h, pyr.lv[l].apron, kApronThreads));
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(regions, A.n, planes.n);
-    cfg.blockDim = dim3(kApronThreads);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // PDL: launch latency hides under the previous kernel's tail
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, apron_kernel, A, planes) == cudaSuccess ? 1 : -1;
 }
 
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,

@@ -1,12 +1,21 @@
-// K1f: the whole Gaussian pyramid + Scharr derivatives of a frame in ONE launch (up to 4 levels).
+// K1f: the whole Gaussian pyramid + Scharr derivatives + REFLECT_101 aprons of a batch of frames in ONE launch (up to 4 levels).
 //
-// The per-level kernel (pyramid.cu) is bandwidth-efficient for large launches but a small rig frame (4 x 768x576 =
-// 12 MB) pays four dependent launches of ~3.5 us each for ~2 us of HBM traffic.  Here one CTA owns a 192x64 region of
-// level 0 (96x32, 48x16, 24x8 of the next levels) and produces every level for it from a single TMA box of level 0:
-// the halo each coarser level needs (1 px for Scharr, 2n+2 px for the pyrDown that feeds a level needing n) is
-// recomputed locally -- 22 / 10 / 4 / 1 px at levels 0..3 -- so CTAs never wait for each other.  Intermediate levels
-// live in shared memory only (plus their own part written to HBM); HBM traffic is the algorithmic N(6 S_L - 1) bytes, the
-// overlap between neighbouring boxes is served by L2.
+// The per-level kernel (pyramid.cu) is bandwidth-efficient for large frames but a rig of small cameras (4 x 768x576 =
+// 12 MB, or 64 of them) pays one dependent launch per level, each with its own tail, for a few microseconds of HBM traffic.
+// Here one CTA owns a 192x64 region of level 0 (96x32, 48x16, 24x8 of the next levels) and produces every level for it
+// from a single TMA box of level 0: the halo each coarser level needs (1 px for Scharr, 2n+2 px for the pyrDown that
+// feeds a level needing n) is recomputed locally -- 22 / 10 / 4 / 1 px at levels 0..3 -- so CTAs never wait for each
+// other.  HBM traffic is the algorithmic N(6 S_L - 1) bytes plus the aprons; the overlap between neighbouring boxes is
+// served by L2.
+//
+// Two phases per CTA:
+//   1. the chain: level k -> level k+1 (pyrDown) in shared memory, one block barrier per level.  Every thread owns one
+//      word column (4 pixels) and slides down a band of rows: three shared-memory words per input row, horizontal taps
+//      as dp4a, the five-row window in registers, one 2-pixel store per output row.
+//   2. the outputs, without any barrier: Scharr derivatives of the own region of every level (uniform work items of 4
+//      columns x 4 rows drawn from one flat list over all levels, so that every thread carries the same load), the u8
+//      levels >= 1, and the REFLECT_101 apron (common.cuh) of the levels >= 1: every CTA writes the mirror images of ITS
+//      OWN pixels that lie within `apron` pixels of a frame edge -- no second launch, no dependency between CTAs.
 //
 // Arithmetic is the same integer dp4a code as pyramid.cu: bit-exact with cv::pyrDown / calcSharrDeriv, REFLECT_101
 // applied at every level's own image border (x = -1, -2, W, W+1 and the same rows) inside shared memory.
@@ -17,33 +26,71 @@ namespace psnw {
 
 namespace {
 
-constexpr int kFusedThreads = 512;
-constexpr int kTopW = 24, kTopH = 8;                 // region owned at the coarsest fused level
+constexpr int kTopW = 24;                            // width of the region owned at the coarsest fused level (192 px of level 0:
+                                                     // with its halo the widest TMA box, 256 bytes)
+constexpr int kScharrRows = 4;                       // rows per Scharr work item (every level)
 
-template <int NL> struct FG {
+// NL fused levels; TH = height of the region owned at the coarsest level: 8 (192x64 of level 0: a rig frame of a few small
+// cameras spreads over every SM), 16 or 32 (192x128 / 192x256: large batches, where the halo rows recomputed by every CTA
+// -- 22 above and below at level 0 -- cost less the taller the region is)
+template <int NL, int TH> struct FG {
     static __host__ __device__ constexpr int own_w(int k) { return kTopW << (NL - 1 - k); }
-    static __host__ __device__ constexpr int own_h(int k) { return kTopH << (NL - 1 - k); }
+    static __host__ __device__ constexpr int own_h(int k) { return TH << (NL - 1 - k); }
     static __host__ __device__ constexpr int need(int k) { return k >= NL - 1 ? 1 : 2 * need(k + 1) + 2; }
     // columns kept left (= right) of the own region: >= need, multiple of 4 (words), of 16 at level 0 (TMA start)
     static __host__ __device__ constexpr int left(int k) { return k == 0 ? (need(0) + 15) / 16 * 16 : (need(k) + 3) / 4 * 4; }
     static __host__ __device__ constexpr int pitch(int k) { return own_w(k) + 2 * left(k); }
     static __host__ __device__ constexpr int rows(int k) { return own_h(k) + 2 * need(k); }
     static __host__ __device__ constexpr int offset(int k) { return k == 0 ? 128 : offset(k - 1) + pitch(k - 1) * rows(k - 1); }
-    static __host__ __device__ constexpr int bytes() { return offset(NL - 1) + pitch(NL - 1) * rows(NL - 1) + 16; }
-    static __host__ __device__ constexpr int rb(int k) { return own_h(k) / 8; }      // Scharr rows per item: 8 bands per level
+    // (the tail pad absorbs the reads of a partial last band of the chain, whose results are never stored)
+    static __host__ __device__ constexpr int bytes() { return offset(NL - 1) + pitch(NL - 1) * rows(NL - 1) + 12288; }
+    // level-0 box of the TMA loads: the buffer rows in chunks of at most 256
+    static __host__ __device__ constexpr int n_box() { return (rows(0) + 255) / 256; }
+    static __host__ __device__ constexpr int box_h() { return rows(0) / n_box(); }
+    // Scharr work items of level k: 4 columns x kScharrRows rows
+    static __host__ __device__ constexpr int sch_cols(int k) { return own_w(k) / 4; }
+    static __host__ __device__ constexpr int sch_items(int k) { return sch_cols(k) * (own_h(k) / kScharrRows); }
+    static __host__ __device__ constexpr int sch_begin(int k) { return k == 0 ? 0 : sch_begin(k - 1) + sch_items(k - 1); }
+    // u8 copy items (words) of level k >= 1
+    static __host__ __device__ constexpr int cp_items(int k) { return k == 0 ? 0 : (own_w(k) / 4) * own_h(k); }
+    static __host__ __device__ constexpr int cp_begin(int k) { return k <= 1 ? 0 : cp_begin(k - 1) + cp_items(k - 1); }
 };
 
 struct FusedLevels {
     LevelGeom lv[4];
+    int base;          // pyramid level of lv[0]; > 0: the chain starts from a level that carries an apron, which is written here too
 };
 
+#ifdef PSNW_PYR_TIMELINE          // bring-up aid (tools/pyr_timeline.cu): per-CTA time stamps at the phase boundaries
+__device__ unsigned long long g_timeline[8 * 65536];
+#define PSNW_STAMP(slot)                                                                                           \
+    do {                                                                                                           \
+        __syncthreads();                                                                                           \
+        if (threadIdx.x == 0) {                                                                                    \
+            unsigned long long t_;                                                                                 \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                 \
+            g_timeline[8 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) + (slot)] = t_;        \
+        }                                                                                                          \
+    } while (0)
+#else
+#define PSNW_STAMP(slot) do { } while (0)
+#endif
+
+__device__ __forceinline__ int reflect101c(int p, int n)
+{
+    p = p < 0 ? -p : p;
+    p = p >= n ? 2 * (n - 1) - p : p;
+    return min(max(p, 0), n - 1);
+}
+
 // REFLECT_101 at the border of a level held in shared memory: x = -1 (and -2 when `two`), x = W (and W+1), same rows.
-// Columns first, then whole rows, so that the corners come out right.  Ends with a barrier.
+// Columns first, then whole rows, so that the corners come out right.  Ends with a barrier when it wrote anything.
+template <int NT>
 __device__ __forceinline__ void fix_border(uint8_t *buf, int pitch, int rows, int bx, int by, int W, int H, bool two, int tid)
 {
     const bool el = bx < 0, er = W - bx < pitch, et = by < 0, eb = H - by < rows;
     if (el || er) {
-        for (int r = tid; r < rows; r += kFusedThreads) {
+        for (int r = tid; r < rows; r += NT) {
             uint8_t *row = buf + r * pitch;
             if (el) {
                 row[-1 - bx] = row[1 - bx];
@@ -51,8 +98,10 @@ __device__ __forceinline__ void fix_border(uint8_t *buf, int pitch, int rows, in
             }
             if (er) {
                 const int c = W - bx;
-                row[c] = row[c - 2];
-                if (two && c + 1 < pitch) row[c + 1] = row[c - 3];
+                if (c >= 2) {
+                    row[c] = row[c - 2];
+                    if (two && c + 1 < pitch && c >= 3) row[c + 1] = row[c - 3];
+                }
             }
         }
     }
@@ -60,25 +109,93 @@ __device__ __forceinline__ void fix_border(uint8_t *buf, int pitch, int rows, in
     if (et || eb) {
         uint32_t *w = reinterpret_cast<uint32_t *>(buf);
         const int pw = pitch >> 2;
-        for (int i = tid; i < pw; i += kFusedThreads) {
+        for (int i = tid; i < pw; i += NT) {
             if (et) {
                 w[(-1 - by) * pw + i] = w[(1 - by) * pw + i];
                 if (two && -2 - by >= 0) w[(-2 - by) * pw + i] = w[(2 - by) * pw + i];
             }
             if (eb) {
                 const int r = H - by;
-                w[r * pw + i] = w[(r - 2) * pw + i];
-                if (two && r + 1 < rows) w[(r + 1) * pw + i] = w[(r - 3) * pw + i];
+                if (r >= 2) {
+                    w[r * pw + i] = w[(r - 2) * pw + i];
+                    if (two && r + 1 < rows && r >= 3) w[(r + 1) * pw + i] = w[(r - 3) * pw + i];
+                }
             }
         }
         __syncthreads();
     }
 }
 
-// Scharr of 4 columns x RB rows starting at (x, y0); `src` points at the word holding columns x..x+3 of buffer row y0-1.
-template <int RB>
-__device__ __forceinline__ void scharr_item(const uint32_t *src, int pw, uint4 *dst, int dst_row_u4, int x, int y0, int W, int H)
+// ---- phase 1: level K -> level K+1 in shared memory --------------------------------------------------------------
+// Buffer geometry: column j of buffer K+1 <-> column 2j + 2*left(K+1) - left(K) ... of buffer K; with word column c of
+// buffer K (4 pixels 4u..4u+3) producing outputs 2u, 2u+1 = columns 2c + dj, 2c + dj + 1 of buffer K+1,
+// dj = left(K+1) - left(K)/2; row i of buffer K+1 is centred on row 2i + 2 of buffer K (rows 2i .. 2i+4).
+template <int NL, int TH, int K, int NT>
+__device__ __forceinline__ void pyr_down_level(uint8_t *smem, int tid)
 {
+    using G = FG<NL, TH>;
+    constexpr int pw = G::pitch(K) / 4, R1 = G::rows(K + 1), P1 = G::pitch(K + 1);
+    constexpr int dj = G::left(K + 1) - G::left(K) / 2;
+    constexpr int nbands = NT / pw, OB = (R1 + nbands - 1) / nbands;          // output rows per band
+    static_assert(nbands >= 1 && 2 * OB * G::pitch(K) <= 12288 + (K + 2 < NL ? G::pitch(K + 2) * G::rows(K + 2) : 0) + G::pitch(K + 1) * G::rows(K + 1),
+                  "partial last band would read past the shared-memory allocation");
+    const int band = tid / pw, c = tid - band * pw;
+    const int i0 = band * OB;
+    if (i0 >= R1) return;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(smem + G::offset(K)) + (2 * i0) * pw;
+    uint8_t *dst = smem + G::offset(K + 1) + i0 * P1;
+    const int cm = max(c - 1, 0), cp = min(c + 1, pw - 1);
+    const int j = 2 * c + dj;
+    const bool jok = j >= 0 && j + 1 < P1;
+    int pg[5][2];
+#pragma unroll
+    for (int rr = 0; rr < 2 * OB + 3; ++rr) {
+        const uint32_t wp = src[rr * pw + cm], wc = src[rr * pw + c], wn = src[rr * pw + cp];
+        const uint32_t sc = __funnelshift_r(wp, wc, 16);                      // bytes x-2 .. x+1
+        pg[rr % 5][0] = dp4a_us(sc, kGauss, (int)((wc >> 16) & 0xffu));       // + byte x+2
+        pg[rr % 5][1] = dp4a_us(wc, kGauss, (int)(wn & 0xffu));               // centre x+2: bytes x..x+3, + byte x+4
+        if (rr >= 4 && (rr & 1) == 0) {
+            const int o = (rr - 4) >> 1;
+            int v[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                v[i] = ((pg[(rr - 4) % 5][i] + pg[rr % 5][i]) + 4 * (pg[(rr - 3) % 5][i] + pg[(rr - 1) % 5][i]) +
+                        6 * pg[(rr - 2) % 5][i] + 128) >> 8;
+            if (jok && i0 + o < R1) *reinterpret_cast<uint16_t *>(dst + o * P1 + j) = (uint16_t)(v[0] | (v[1] << 8));
+        }
+    }
+}
+
+template <int NL, int TH, int K, int NT>
+__device__ __forceinline__ void chain(uint8_t *smem, const FusedLevels &L, int tid)
+{
+    using G = FG<NL, TH>;
+    const LevelGeom &lv = L.lv[K];
+    const int bx = (int)blockIdx.x * G::own_w(K) - G::left(K), by = (int)blockIdx.y * G::own_h(K) - G::need(K);
+    fix_border<NT>(smem + G::offset(K), G::pitch(K), G::rows(K), bx, by, lv.w, lv.h, K + 1 < NL, tid);
+    if constexpr (K + 1 < NL) {
+        pyr_down_level<NL, TH, K, NT>(smem, tid);
+        __syncthreads();
+        chain<NL, TH, K + 1, NT>(smem, L, tid);
+    }
+}
+
+// ---- phase 2: outputs ---------------------------------------------------------------------------------------------
+// Scharr of 4 columns x kScharrRows rows of level K's own region (work item `it` of the level) -> HBM
+template <int NL, int TH, int K>
+__device__ __forceinline__ void scharr_item(const uint8_t *smem, const FusedLevels &L, int plane, int it)
+{
+    using G = FG<NL, TH>;
+    constexpr int ncg = G::sch_cols(K), pw = G::pitch(K) / 4, RB = kScharrRows;
+    const LevelGeom &lv = L.lv[K];
+    const int W = lv.w, H = lv.h;
+    const int band = it / ncg, cg = it - band * ncg;
+    const int x = (int)blockIdx.x * G::own_w(K) + 4 * cg, y0 = (int)blockIdx.y * G::own_h(K) + band * RB;
+    if (x >= W || y0 >= H) return;                    // (columns [w, pitch) were zeroed at creation and are never written)
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(smem + G::offset(K)) + (G::need(K) - 1 + band * RB) * pw + G::left(K) / 4 + cg;
+    uint4 *dst = reinterpret_cast<uint4 *>(lv.dxy + (size_t)plane * lv.plane_px + (size_t)y0 * lv.pitch + x);
+    const int dst_row_u4 = lv.pitch / 4;
+    const int nvalid = W - x;                         // >= 4 except in the group that straddles the right edge
     int hd[3][4], hs[3][4];
 #pragma unroll
     for (int rr = 0; rr < RB + 2; ++rr) {
@@ -96,125 +213,215 @@ __device__ __forceinline__ void scharr_item(const uint32_t *src, int pw, uint4 *
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int dx = 3 * (dm[i] + dp[i]) + 10 * d0[i], dy = sp[i] - sm[i];
-                o[i] = (x + i < W) ? __byte_perm((uint32_t)dx, (uint32_t)dy, 0x5410) : 0u;   // pad columns stay zero
+                o[i] = __byte_perm((uint32_t)dx, (uint32_t)dy, 0x5410);
             }
-            if (y0 + rr - 2 < H) dst[(size_t)(rr - 2) * dst_row_u4] = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-    }
-}
-
-// one level of the fused chain: border fix-up, Scharr of the own region -> HBM, pyrDown into the next level's buffer
-template <int NL, int K>
-__device__ __forceinline__ void fused_level(uint8_t *smem, const FusedLevels &L, int plane, int tid)
-{
-    using G = FG<NL>;
-    const LevelGeom &lv = L.lv[K];
-    const int W = lv.w, H = lv.h;
-    const int ox = (int)blockIdx.x * G::own_w(K), oy = (int)blockIdx.y * G::own_h(K);
-    const int bx = ox - G::left(K), by = oy - G::need(K);
-    uint8_t *buf = smem + G::offset(K);
-    constexpr int pitch = G::pitch(K), pw = G::pitch(K) / 4;
-    fix_border(buf, pitch, G::rows(K), bx, by, W, H, K + 1 < NL, tid);
-
-    // ---- Scharr of the own region -> HBM ----
-    {
-        constexpr int RB = G::rb(K), ncg = G::own_w(K) / 4;
-        if (tid < ncg * 8) {
-            const int band = tid / ncg, cg = tid - band * ncg;
-            const int x = ox + 4 * cg, y0 = oy + band * RB;
-            if (x < lv.pitch && x < ((W + 3) & ~3) && y0 < H) {
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(buf) + (y0 - 1 - by) * pw + ((x - bx) >> 2);
-                uint4 *dst = reinterpret_cast<uint4 *>(lv.dxy + (size_t)plane * lv.plane_px + (size_t)y0 * lv.pitch + x);
-                scharr_item<RB>(src, pw, dst, lv.pitch / 4, x, y0, W, H);
-            }
-        }
-    }
-
-    // ---- pyrDown: level K+1 over its own region plus the halo the coarser levels need -> shared memory (+ HBM) ----
-    if constexpr (K + 1 < NL) {
-        const LevelGeom &nx = L.lv[K + 1];
-        const int W1 = nx.w, H1 = nx.h;
-        const int ox1 = (int)blockIdx.x * G::own_w(K + 1), oy1 = (int)blockIdx.y * G::own_h(K + 1);
-        constexpr int n1 = G::need(K + 1), w1 = G::own_w(K + 1), h1 = G::own_h(K + 1);
-        const int bx1 = ox1 - G::left(K + 1), by1 = oy1 - n1;
-        uint8_t *buf1 = smem + G::offset(K + 1);
-        constexpr int pitch1 = G::pitch(K + 1);
-        const int xlo = max(ox1 - n1, 0), xhi = min(ox1 + w1 + n1, W1);          // outputs wanted: [xlo, xhi) x [ylo, yhi)
-        const int ylo = max(oy1 - n1, 0), yhi = min(oy1 + h1 + n1, H1);
-        const int u0 = (ox1 - n1) >> 1;                                          // lane unit u -> outputs 2u, 2u+1
-        constexpr int nu = (w1 + 2 * n1) / 2 + 1, nyi = (h1 + 2 * n1 + 3) / 4;
-        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(buf);
-        for (int it = tid; it < nu * nyi; it += kFusedThreads) {
-            const int yi = it / nu, u = u0 + (it - yi * nu);
-            const int X = 2 * u, Y0 = (oy1 - n1) + 4 * yi;
-            if (X + 1 < xlo || X >= xhi || Y0 >= yhi || Y0 + 3 < ylo) continue;
-            const int wi = (4 * u - bx) >> 2;                                    // word of input columns 4u..4u+3
-            const int r0 = 2 * Y0 - 2 - by;                                      // buffer row of input row 2*Y0 - 2
-            int pg[5][2];
-#pragma unroll
-            for (int rr = 0; rr < 11; ++rr) {
-                const int r = min(max(r0 + rr, 0), G::rows(K) - 1);
-                const uint32_t wp = srcw[r * pw + wi - 1], wc = srcw[r * pw + wi], wn = srcw[r * pw + wi + 1];
-                const uint32_t sc = __funnelshift_r(wp, wc, 16);
-                pg[rr % 5][0] = dp4a_us(sc, kGauss, (int)((wc >> 16) & 0xffu));
-                pg[rr % 5][1] = dp4a_us(wc, kGauss, (int)(wn & 0xffu));
-                if (rr >= 4 && (rr & 1) == 0) {
-                    const int Y = Y0 + ((rr - 4) >> 1);
-                    int v[2];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        v[i] = ((pg[(rr - 4) % 5][i] + pg[rr % 5][i]) + 4 * (pg[(rr - 3) % 5][i] + pg[(rr - 1) % 5][i]) +
-                                6 * pg[(rr - 2) % 5][i] + 128) >> 8;
-                    if (Y >= ylo && Y < yhi) {
-                        const bool a0 = X >= xlo && X < xhi, a1 = X + 1 >= xlo && X + 1 < xhi;
-                        uint8_t *d = buf1 + (Y - by1) * pitch1 + (X - bx1);
-                        if (a0) d[0] = (uint8_t)v[0];
-                        if (a1) d[1] = (uint8_t)v[1];
-                        if (Y >= oy1 && Y < oy1 + h1 && X >= ox1 && X < ox1 + w1) {          // own part of level K+1 -> HBM
-                            uint8_t *g = nx.img + (size_t)plane * nx.iplane_px + (size_t)Y * nx.ipitch + X;
-                            if (a0 && a1) *reinterpret_cast<uint16_t *>(g) = (uint16_t)(v[0] | (v[1] << 8));
-                            else if (a0) g[0] = (uint8_t)v[0];
-                        }
-                    }
+            if (y0 + rr - 2 < H) {
+                if (nvalid >= 4) {
+                    dst[(size_t)(rr - 2) * dst_row_u4] = make_uint4(o[0], o[1], o[2], o[3]);
+                } else {                                  // pad columns stay zero
+                    dst[(size_t)(rr - 2) * dst_row_u4] = make_uint4(o[0], nvalid > 1 ? o[1] : 0u, nvalid > 2 ? o[2] : 0u, 0u);
                 }
             }
         }
-        __syncthreads();
-        fused_level<NL, K + 1>(smem, L, plane, tid);
     }
 }
 
-template <int NL>
-__global__ void __launch_bounds__(kFusedThreads, 1)
-pyr_fused_kernel(const __grid_constant__ CUtensorMap map0, const FusedLevels L, const PlaneList planes)
+template <int NL, int TH, int K>
+__device__ __forceinline__ void scharr_dispatch(const uint8_t *smem, const FusedLevels &L, int plane, int it)
 {
-    using G = FG<NL>;
+    using G = FG<NL, TH>;
+    if (it < G::sch_begin(K) + G::sch_items(K)) {
+        scharr_item<NL, TH, K>(smem, L, plane, it - G::sch_begin(K));
+    } else if constexpr (K + 1 < NL) {
+        scharr_dispatch<NL, TH, K + 1>(smem, L, plane, it);
+    }
+}
+
+// one aligned word of level K's own region (K >= 1): shared memory -> HBM
+template <int NL, int TH, int K>
+__device__ __forceinline__ void copy_item(const uint8_t *smem, const FusedLevels &L, int plane, int it)
+{
+    using G = FG<NL, TH>;
+    constexpr int nw = G::own_w(K) / 4;
+    const LevelGeom &lv = L.lv[K];
+    const int r = it / nw, c = it - r * nw;
+    const int x = (int)blockIdx.x * G::own_w(K) + 4 * c, y = (int)blockIdx.y * G::own_h(K) + r;
+    if (x >= lv.w || y >= lv.h) return;
+    const uint32_t v = *reinterpret_cast<const uint32_t *>(smem + G::offset(K) + (G::need(K) + r) * G::pitch(K) + G::left(K) + 4 * c);
+    uint8_t *g = lv.img + (size_t)plane * lv.iplane_px + (size_t)y * lv.ipitch + x;
+    if (x + 4 <= lv.w) {
+        *reinterpret_cast<uint32_t *>(g) = v;
+    } else {                                          // the frame ends inside this word: the bytes past it belong to the apron
+        for (int k = 0; k < lv.w - x; ++k) g[k] = (uint8_t)(v >> (8 * k));
+    }
+}
+
+template <int NL, int TH, int K>
+__device__ __forceinline__ void copy_dispatch(const uint8_t *smem, const FusedLevels &L, int plane, int it)
+{
+    using G = FG<NL, TH>;
+    if constexpr (K < NL) {
+        if (it < G::cp_begin(K) + G::cp_items(K)) copy_item<NL, TH, K>(smem, L, plane, it - G::cp_begin(K));
+        else copy_dispatch<NL, TH, K + 1>(smem, L, plane, it);
+    }
+}
+
+// REFLECT_101 apron of level K >= 1, scattered from the CTA's own pixels: a CTA handles every apron word (4 aligned
+// pixels) that mirrors at least one pixel of its own region.  If all four sources lie in the part of its buffer that
+// holds true pixels (own region + hv columns) the word is stored whole; otherwise only the bytes whose sources it owns
+// (the neighbouring CTA stores the others).  Words stored by two CTAs carry identical values.
+//   x classes: 0 identity columns (only with mirrored rows), 1 mirrored about x = 0, 2 mirrored about x = W-1; y alike.
+// The destination rectangles of the 8 classes (words x rows) are tabulated once per CTA and level by a single thread
+// while the level-0 box is still in flight: {first item, words per row, first word, first row}.
+struct ApronTable {
+    int4 cls[4][8];
+    int total[4];
+};
+
+template <int NL, int TH>
+__device__ __forceinline__ void apron_table(ApronTable &T, const FusedLevels &L, int K)
+{
+    using G = FG<NL, TH>;
+    const LevelGeom &lv = L.lv[K];
+    const int W = lv.w, H = lv.h, A = lv.apron;
+    const int own_w = kTopW << (NL - 1 - K), own_h = TH << (NL - 1 - K);
+    const int Ax = min(A, W - 1), Ay = min(A, H - 1);
+    const int ox = (int)blockIdx.x * own_w, oy = (int)blockIdx.y * own_h;
+    const int ox1 = min(ox + own_w, W), oy1 = min(oy + own_h, H);                   // own region clipped to the frame
+    int wlo[3], nw[3], rlo[3], nr[3];
+    wlo[0] = ox >> 2; nw[0] = ((ox1 - 1) >> 2) - wlo[0] + 1;
+    { const int a = max(ox, 1), b = min(ox1 - 1, Ax); wlo[1] = (-b) >> 2; nw[1] = a <= b ? ((-a) >> 2) - wlo[1] + 1 : 0; }
+    { const int a = max(ox, W - 1 - Ax), b = min(ox1 - 1, W - 2); wlo[2] = (2 * (W - 1) - b) >> 2; nw[2] = a <= b ? ((2 * (W - 1) - a) >> 2) - wlo[2] + 1 : 0; }
+    rlo[0] = oy; nr[0] = oy1 - oy;
+    { const int a = max(oy, 1), b = min(oy1 - 1, Ay); rlo[1] = -b; nr[1] = a <= b ? b - a + 1 : 0; }
+    { const int a = max(oy, H - 1 - Ay), b = min(oy1 - 1, H - 2); rlo[2] = 2 * (H - 1) - b; nr[2] = a <= b ? b - a + 1 : 0; }
+    const bool none = A <= 0 || ox >= ox1 || oy >= oy1;
+    int begin = 0;
+#pragma unroll
+    for (int c = 1; c < 9; ++c) {
+        const int xc = c % 3, yc = c / 3;
+        const int n = none ? 0 : max(nw[xc], 0) * max(nr[yc], 0);
+        T.cls[K][c - 1] = make_int4(begin, max(nw[xc], 1), wlo[xc], rlo[yc]);
+        begin += n;
+    }
+    T.total[K] = begin;
+}
+
+template <int NL, int TH, int K, int NT>
+__device__ __forceinline__ void apron_level(const uint8_t *smem, const ApronTable &T, const FusedLevels &L, int plane, int tid)
+{
+    using G = FG<NL, TH>;
+    const int total = T.total[K];
+    if (tid >= total) return;
+    const LevelGeom &lv = L.lv[K];
+    const int W = lv.w, H = lv.h;
+    const int Ax = min(lv.apron, W - 1);
+    const int ox = (int)blockIdx.x * G::own_w(K), oy = (int)blockIdx.y * G::own_h(K);
+    const int ox1 = min(ox + G::own_w(K), W);
+    constexpr int hv = G::need(K) >= 3 ? 3 : G::need(K);                          // columns beside the own region that hold true pixels
+    const int vx0 = max(ox - hv, 0), vx1 = min(ox + G::own_w(K) + hv, W);
+    const int bx = ox - G::left(K), by = oy - G::need(K);
+    const uint8_t *buf = smem + G::offset(K);
+    constexpr int pitch = G::pitch(K);
+    uint8_t *plane0 = lv.img + (size_t)plane * lv.iplane_px;
+#pragma unroll 1
+    for (int it = tid; it < total; it += NT) {
+        int e = 0;
+#pragma unroll
+        for (int c = 1; c < 8; ++c) e += it >= T.cls[K][c].x ? 1 : 0;          // (first items ascend; empty classes repeat them)
+        const int4 C = T.cls[K][e];
+        const int xc = (e + 1) % 3, yc = (e + 1) / 3;
+        const int q = it - C.x, r = q / C.y, tx = 4 * (C.z + (q - r * C.y)), ty = C.w + r;
+        const int sy = reflect101c(ty, H);
+        const uint8_t *srow = buf + (sy - by) * pitch - bx;
+        uint8_t *drow = plane0 + (ptrdiff_t)ty * lv.ipitch;
+        if (xc == 0 && tx + 4 <= W) {                     // identity columns, mirrored row: one aligned word
+            *reinterpret_cast<uint32_t *>(drow + tx) = *reinterpret_cast<const uint32_t *>(srow + tx);
+            continue;
+        }
+        uint32_t v = 0;
+        bool all = true, any = false, own[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int px = tx + k;
+            const bool okd = px >= -Ax && px < W + Ax && (yc != 0 || px < 0 || px >= W);
+            const int sx = reflect101c(px, W);
+            own[k] = okd && sx >= ox && sx < ox1;
+            all = all && okd && sx >= vx0 && sx < vx1;
+            any = any || own[k];
+            v |= (uint32_t)srow[min(max(sx, vx0), vx1 - 1)] << (8 * k);
+        }
+        if (all && any) {
+            *reinterpret_cast<uint32_t *>(drow + tx) = v;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (own[k]) drow[tx + k] = (uint8_t)(v >> (8 * k));
+        }
+    }
+}
+
+template <int NL, int TH, int K, int NT>
+__device__ __forceinline__ void apron_all(const uint8_t *smem, const ApronTable &T, const FusedLevels &L, int plane, int tid)
+{
+    if constexpr (K < NL) {
+        apron_level<NL, TH, K, NT>(smem, T, L, plane, tid);
+        apron_all<NL, TH, K + 1, NT>(smem, T, L, plane, tid);
+    }
+}
+
+template <int NL, int TH, int NT>
+__global__ void __launch_bounds__(NT, NT <= 256 ? 4 : 2)
+pyr_fused_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ FusedLevels L, const __grid_constant__ PlaneList planes)
+{
+    using G = FG<NL, TH>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ ApronTable aprons;
     const int tid = threadIdx.x;
     const int plane = planes.plane[blockIdx.z];
     const uint32_t bar_a = smem_u32(&bar);
 
+    PSNW_STAMP(0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) mbar_init(bar_a, 1);
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
-        mbar_expect_tx(bar_a, G::pitch(0) * G::rows(0));
-        tma_load_3d(smem_u32(smem + G::offset(0)), &map0, (int)blockIdx.x * G::own_w(0) - G::left(0),
-                    (int)blockIdx.y * G::own_h(0) - G::need(0), plane, bar_a);
+        mbar_expect_tx(bar_a, G::pitch(0) * G::box_h() * G::n_box());
+#pragma unroll
+        for (int b = 0; b < G::n_box(); ++b)
+            tma_load_3d(smem_u32(smem + G::offset(0) + b * G::pitch(0) * G::box_h()), &map0, (int)blockIdx.x * G::own_w(0) - G::left(0),
+                        (int)blockIdx.y * G::own_h(0) - G::need(0) + b * G::box_h(), plane, bar_a);
     }
+    // (while the box is in flight) the apron work lists of this CTA; the barriers of the chain publish them
+    if (tid >= 32 && tid < 32 + NL) apron_table<NL, TH>(aprons, L, tid - 32);      // (level 0 of a frame has no apron: empty list)
     mbar_wait(bar_a, 0);
-    fused_level<NL, 0>(smem, L, plane, tid);
+    PSNW_STAMP(1);
+
+    // phase 1: every level of the region into shared memory
+    chain<NL, TH, 0, NT>(smem, L, tid);
+    PSNW_STAMP(2);
+
+    // phase 2: outputs (no barriers; the rotation of the thread index spreads the last, partial round of Scharr items)
+    constexpr int n_sch = G::sch_begin(NL - 1) + G::sch_items(NL - 1);
+    for (int it = tid; it < n_sch; it += NT) scharr_dispatch<NL, TH, 0>(smem, L, plane, it);
+    PSNW_STAMP(3);
+    constexpr int n_cp = G::cp_begin(NL - 1) + G::cp_items(NL - 1);
+    const int rot = (tid + NT - (n_sch % NT)) % NT;       // threads that did one Scharr item less go first
+    for (int it = rot; it < n_cp; it += NT) copy_dispatch<NL, TH, 1>(smem, L, plane, it);
+    PSNW_STAMP(4);
+    apron_all<NL, TH, 0, NT>(smem, aprons, L, plane, rot);
+    PSNW_STAMP(5);
 }
 
-template <int NL>
+template <int NL, int TH, int NT>
 int launch_fused_t(const CUtensorMap *map0, const FusedLevels &L, const PlaneList &planes, cudaStream_t stream)
 {
-    using G = FG<NL>;
+    using G = FG<NL, TH>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((L.lv[0].w + G::own_w(0) - 1) / G::own_w(0), (L.lv[0].h + G::own_h(0) - 1) / G::own_h(0), planes.n);
-    cfg.blockDim = dim3(kFusedThreads);
+    cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = G::bytes();
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -222,30 +429,53 @@ int launch_fused_t(const CUtensorMap *map0, const FusedLevels &L, const PlaneLis
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, pyr_fused_kernel<NL>, *map0, L, planes) == cudaSuccess ? 1 : -1;
+    return cudaLaunchKernelEx(&cfg, pyr_fused_kernel<NL, TH, NT>, *map0, L, planes) == cudaSuccess ? 1 : -1;
+}
+
+template <int NL, int TH, int NT>
+int configure_t()
+{
+    return cudaFuncSetAttribute(pyr_fused_kernel<NL, TH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, FG<NL, TH>::bytes()) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace
 
-void fused_box(int nl, int *box_w, int *box_h)
+// region variants: index 0 / 1 / 2 = 64 / 128 / 256 level-0 rows (4 fused levels), half of that with 3
+void fused_geometry(int nl, int variant, int *box_w, int *box_h, int *own_w, int *own_h)
 {
-    if (nl == 4) { *box_w = FG<4>::pitch(0); *box_h = FG<4>::rows(0); }
-    else         { *box_w = FG<3>::pitch(0); *box_h = FG<3>::rows(0); }
+#define PSNW_FG(NL_, TH_) { using G = FG<NL_, TH_>; *box_w = G::pitch(0); *box_h = G::box_h(); *own_w = G::own_w(0); *own_h = G::own_h(0); }
+    if (nl == 4) { if (variant == 0) PSNW_FG(4, 8) else if (variant == 1) PSNW_FG(4, 16) else PSNW_FG(4, 32) }
+    else         { if (variant == 0) PSNW_FG(3, 8) else if (variant == 1) PSNW_FG(3, 16) else PSNW_FG(3, 32) }
+#undef PSNW_FG
 }
 
 int configure_fused_kernels()
 {
-    if (cudaFuncSetAttribute(pyr_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FG<4>::bytes()) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(pyr_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FG<3>::bytes()) != cudaSuccess) return -1;
-    return 0;
+    return configure_t<4, 8, 256>() | configure_t<4, 16, 256>() | configure_t<4, 32, 256>() | configure_t<3, 8, 256>() | configure_t<3, 16, 256>() |
+           configure_t<3, 32, 256>() | configure_t<4, 8, 512>() | configure_t<4, 16, 512>() | configure_t<4, 32, 512>() | configure_t<3, 8, 512>() |
+           configure_t<3, 16, 512>() | configure_t<3, 32, 512>();
 }
 
-// levels 0 .. nl-1 (nl = 3 or 4) of the planes in one launch; `map0` is the level-0 tensor map with the fused box
-int launch_pyr_fused(const PyrDesc &pyr, int nl, const CUtensorMap *map0, const PlaneList &planes, cudaStream_t stream)
+// levels base .. base+nl-1 (nl = 3 or 4) of the planes in one launch, aprons included, from level `base` already in HBM
+// (base = 0: the frame itself); `map0` is the tensor map of level `base` with the box of region variant `variant`
+// (fused_geometry).  threads per CTA: 256 (four CTAs per SM: large launches of small regions) or 512 (two).  (1024 threads
+// and one CTA per SM were measured for the single-wave launch: no gain, the phases of a lone CTA are latency-bound.)
+int launch_pyr_fused(const PyrDesc &pyr, int base, int nl, int variant, int threads, const CUtensorMap *map0, const PlaneList &planes, cudaStream_t stream)
 {
     FusedLevels L;
-    for (int k = 0; k < 4; ++k) L.lv[k] = pyr.lv[k < nl ? k : nl - 1];
-    return nl == 4 ? launch_fused_t<4>(map0, L, planes, stream) : launch_fused_t<3>(map0, L, planes, stream);
+    for (int k = 0; k < 4; ++k) L.lv[k] = pyr.lv[base + (k < nl ? k : nl - 1)];
+    L.base = base;
+#define PSNW_LAUNCH(NL_, TH_)                                                                               \
+    return threads <= 256 ? launch_fused_t<NL_, TH_, 256>(map0, L, planes, stream) : launch_fused_t<NL_, TH_, 512>(map0, L, planes, stream)
+    if (nl == 4) {
+        if (variant == 0) { PSNW_LAUNCH(4, 8); }
+        if (variant == 1) { PSNW_LAUNCH(4, 16); }
+        PSNW_LAUNCH(4, 32);
+    }
+    if (variant == 0) { PSNW_LAUNCH(3, 8); }
+    if (variant == 1) { PSNW_LAUNCH(3, 16); }
+    PSNW_LAUNCH(3, 32);
+#undef PSNW_LAUNCH
 }
 
 }  // namespace psnw

@@ -35,7 +35,7 @@ def _check_apron(ctx, img, cam, slot, level, apron=26):
     assert np.array_equal(got, want), "apron of level %d differs" % level
 
 
-@pytest.mark.parametrize("mode", ["level", "fused"])
+@pytest.mark.parametrize("mode", ["level", "fused", "hybrid"])
 @pytest.mark.parametrize("w,h,levels", [(768, 576, 4), (767, 575, 4), (129, 33, 3), (16, 16, 2), (130, 70, 3),
                                         (1920, 1080, 4), (257, 131, 5), (640, 480, 6), (193, 65, 4), (385, 129, 3),
                                         (3840, 2160, 5)])
@@ -50,7 +50,7 @@ def test_bit_exact_vs_oracle(oracle, monkeypatch, w, h, levels, mode):
         _check_levels(ctx, oracle, img)
 
 
-@pytest.mark.parametrize("mode", ["level", "fused"])
+@pytest.mark.parametrize("mode", ["level", "fused", "hybrid"])
 @pytest.mark.parametrize("apron,w,h,levels", [(64, 768, 576, 4), (40, 333, 97, 4), (160, 640, 480, 5), (5, 130, 70, 3)])
 def test_apron_width_is_a_context_parameter(oracle, monkeypatch, apron, w, h, levels, mode):
     """psnw_params.apron: wider aprons for contexts that track large windows (clamped to [26, 160])."""
@@ -81,7 +81,7 @@ def test_golden_fixture(golden):
             assert np.array_equal(dxy[..., 1], golden["dy_odd_%d" % l])
 
 
-@pytest.mark.parametrize("mode", ["level", "fused"])
+@pytest.mark.parametrize("mode", ["level", "fused", "hybrid"])
 def test_batched_cameras_and_ring_rotation(oracle, monkeypatch, mode):
     monkeypatch.setenv("PSNW_PYR_MODE", mode)
     w, h, ncam = 384, 288, 3

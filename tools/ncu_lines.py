@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Join an ncu SASS source page with nvdisasm line info: per-source-line executed-instruction counts.
 usage: tools/ncu_lines.py <report.ncu-rep> <object.o> <kernel-substring> [per_unit_divisor]"""
-import csv, io, re, subprocess, sys, collections
+import csv, io, os, re, subprocess, sys, collections
 rep, obj, kern = sys.argv[1:4]
 div = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
-sass = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], stderr=subprocess.DEVNULL).decode()
+sass = subprocess.check_output(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + os.environ.get("NCU_K", kern)], stderr=subprocess.DEVNULL).decode()
 rows = list(csv.reader(io.StringIO(sass)))
 hi = [i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r][0]
 hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}

@@ -10,7 +10,7 @@ stream = torch.cuda.Stream()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = []
 ONLY = os.environ.get("PYR_SWEEP_ONLY")        # e.g. "768,576,4,64": a single configuration (profiling aid)
-CFGS = [tuple(int(v) for v in ONLY.split(","))] if ONLY else [(768, 576, 4, 1), (768, 576, 4, 4), (768, 576, 4, 16), (768, 576, 4, 64), (1920, 1080, 4, 1),
+CFGS = [tuple(int(v) for v in c.split(",")) for c in ONLY.split(";")] if ONLY else [(768, 576, 4, 1), (768, 576, 4, 4), (768, 576, 4, 16), (768, 576, 4, 64), (1920, 1080, 4, 1),
                              (1920, 1080, 4, 8), (1920, 1080, 4, 32), (3840, 2160, 5, 1), (3840, 2160, 5, 4), (3840, 2160, 5, 16)]
 for (w, h, levels, ncam) in CFGS:
     ctx = klt.KLTContext(w, h, n_cameras=ncam, levels=levels, ring_slots=1, stream=stream.cuda_stream, max_points=1024, max_targets=64)
@@ -35,4 +35,4 @@ for (w, h, levels, ncam) in CFGS:
          "ms_min": round(float(ms.min()), 4), "GBs_mean": round(alg / ms.mean() / 1e6, 1), "frac": round(alg / ms.mean() / 1e6 / PEAK, 3)}
     print(json.dumps(r), flush=True); out.append(r)
     ctx.close()
-json.dump(out, open("gpurun_out/pyr_sweep.json", "w"), indent=1)
+json.dump(out, open(os.environ.get("PYR_SWEEP_OUT", "gpurun_out/pyr_sweep.json"), "w"), indent=1)

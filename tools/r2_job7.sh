@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_pyramid.py -x -q 2>&1 | tail -3
+for v in 1 2; do PSNW_FUSED_VARIANT=$v timeout 600 python -m pytest tests/test_gpu_pyramid.py -x -q -k hybrid 2>&1 | tail -1; done
+S="768,576,4,1;768,576,4,4;768,576,4,16;768,576,4,64;1920,1080,4,1;1920,1080,4,8;1920,1080,4,32;3840,2160,5,1;3840,2160,5,4;3840,2160,5,16"
+for v in 0 1 2; do
+  echo hybrid variant=$v
+  PYR_SWEEP_ONLY="$S" PYR_SWEEP_OUT=gpurun_out/r2_j7_hyb_v$v.json PSNW_PYR_MODE=hybrid PSNW_FUSED_VARIANT=$v timeout 300 python tools/pyr_sweep.py 2>&1
+done
