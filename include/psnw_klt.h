@@ -272,6 +272,14 @@ PSNW_API uint64_t psnw_push_frame_bytes(psnw_ctx *ctx);
 /* Re-runs the pyramid + Scharr build of the frames already in slot 0 of `cams` (no copy): lets bench.py time
  * the HBM-bound kernels alone with CUDA events on the context stream. */
 PSNW_API int psnw_rebuild_pyramids(psnw_ctx *ctx, int n, const int *cams);
+/* The same for the frames in ring slot `slot`: bench.py walks the ring so that a stream of launches touches more bytes than
+ * the L2 holds. */
+PSNW_API int psnw_rebuild_pyramids_slot(psnw_ctx *ctx, int n, const int *cams, int slot);
+/* Work counters of the 21 x 21 LK kernel.  enable != 0: the launches that follow run the counting build of the kernel
+ * (same results, three atomics per solve); enable == 0: back to the product kernel.  out (may be NULL) receives the
+ * counters gathered since the previous call -- {LK solves, template passes (levels on which the 2x2 system was formed),
+ * Gauss-Newton iterations} -- and they are reset.  bench.py derives the kernel's arithmetic roofline from them. */
+PSNW_API int psnw_lk_stats(psnw_ctx *ctx, int enable, uint64_t *out);
 /* Levels actually built (levels whose smaller side would drop under 8 px are skipped). */
 PSNW_API int psnw_levels_built(psnw_ctx *ctx);
 

@@ -73,6 +73,7 @@ struct psnw_ctx {
     unsigned *lk_work = nullptr;          // [2] work counters of the persistent 21x21 LK kernel (self-resetting)
     int lk_ctas = 0;                      // resident CTAs of that kernel on this device
     int lk_tail = 0;                      // points at the end of a large batch whose two passes are separate work items
+    unsigned long long *lk_stats = nullptr;   // psnw_lk_stats: device counters of the counting build of the 21x21 kernel, or null
     bool lk_persistent = true;            // persistent warps + work counter; PSNW_LK_PERSISTENT=0 (bring-up): one point per warp
     DevBuf det_desc;                      // target descriptors + staged outputs (detect; may run on the aux stream)
     DevBuf cand;                          // detect candidate scratch
@@ -314,16 +315,13 @@ int fused_variant_for(const psnw_ctx *ctx, int base, int nl, int n, int *threads
 {
     const LevelGeom &g = ctx->pyr.lv[base];
     int variant = 0;
-    size_t ctas0 = 0;
-    for (int v = kFusedVariants - 1; v >= 0; --v) {
+    for (int v = kFusedVariants - 1; v > 0 && variant == 0; --v) {
         int bw, bh, ow, oh;
         fused_geometry(nl, v, &bw, &bh, &ow, &oh);
         const size_t ctas = (size_t)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) * n;
-        if (v > 0 && variant == 0 && ctas >= (size_t)ctx->sm_count * 6) variant = v;
-        if (v == 0) ctas0 = ctas;
+        if (ctas >= (size_t)ctx->sm_count * 6) variant = v;
     }
     if (ctx->fused_variant >= 0) variant = ctx->fused_variant;
-    (void)ctas0;
     *threads = base > 0 ? 256 : 512;
     if (ctx->fused_wide >= 0) *threads = ctx->fused_wide;
     return variant;
@@ -669,6 +667,7 @@ int psnw_destroy(psnw_ctx *ctx)
     if (ctx->arena.p) cudaFree(ctx->arena.p);
     if (ctx->desc.p) cudaFree(ctx->desc.p);
     if (ctx->lk_work) cudaFree(ctx->lk_work);
+    if (ctx->lk_stats) cudaFree(ctx->lk_stats);
     if (ctx->lk_maps) cudaFree(ctx->lk_maps);
     if (ctx->cand.p) cudaFree(ctx->cand.p);
     if (ctx->bgr.p) cudaFree(ctx->bgr.p);
@@ -806,6 +805,34 @@ int psnw_rebuild_pyramids(psnw_ctx *ctx, int n, const int *cams)
     return build_pyramids(ctx, planes, ctx->stream);
 }
 
+int psnw_rebuild_pyramids_slot(psnw_ctx *ctx, int n, const int *cams, int slot)
+{
+    if (!ctx || n <= 0 || !cams) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
+    std::vector<int> planes(n);
+    for (int i = 0; i < n; ++i) {
+        if (!slot_ok(ctx, cams[i], slot)) return fail(ctx, PSNW_ESTATE, "psnw_rebuild_pyramids_slot: camera/slot holds no frame");
+        planes[i] = plane_of(ctx, cams[i], slot);
+    }
+    if (int rc = join_aux(ctx)) return rc;
+    return build_pyramids(ctx, planes, ctx->stream);
+}
+
+int psnw_lk_stats(psnw_ctx *ctx, int enable, uint64_t *out)
+{
+    if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->lk_stats && out) CK(cudaMemcpy(out, ctx->lk_stats, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    else if (out) out[0] = out[1] = out[2] = 0;
+    if (enable && !ctx->lk_stats) {
+        if (cudaMalloc(&ctx->lk_stats, 3 * sizeof(unsigned long long)) != cudaSuccess) return fail(ctx, PSNW_ENOMEM, "cudaMalloc LK counters", cudaGetLastError());
+    }
+    if (ctx->lk_stats) CK(cudaMemset(ctx->lk_stats, 0, 3 * sizeof(unsigned long long)));
+    if (!enable && ctx->lk_stats) { CK(cudaFree(ctx->lk_stats)); ctx->lk_stats = nullptr; }
+    return PSNW_OK;
+}
+
 int psnw_frames_held(psnw_ctx *ctx, int cam)
 {
     if (!ctx || cam < 0 || cam >= ctx->p.n_cameras) return PSNW_EARG;
@@ -930,6 +957,7 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     // (a batch that is all tail would only add the hand-over: small batches keep one item per point)
     P.split_from = (P.work && P.do_fb && all21 && !any_skipped && P.n_pts >= 2 * ctx->lk_tail) ? P.n_pts - ctx->lk_tail : P.n_pts;
     P.tmaps = ctx->lk_maps;
+    P.stats = ctx->lk_stats;
     const int r = launch_lk(P, all21 ? 1 : 0, max_win_px, ctx->lk_ctas, ctx->stream);
     if (r == -2) return fail(ctx, PSNW_EARG, "psnw_klt_track: window too large for shared memory");      // (unreachable: such targets are skipped)
     if (r < 0) return fail(ctx, PSNW_ECUDA, "lk kernel launch", cudaGetLastError());

@@ -82,6 +82,7 @@ struct LkParams {
     unsigned *work;           // [2 + kLkTailMax] item counter / finished-warp counter of the persistent 21x21 kernel, then the
                               // hand-over flags of the split tail (all zero between launches)
     int split_from;           // points >= split_from are tracked as two work items (forward, then backward); = n_pts: none
+    unsigned long long *stats; // null, or [3] counters {solves, template passes, iterations} (psnw_lk_stats: the counting build of the 21x21 kernel)
 };
 constexpr int kLkTailMax = 16384;   // capacity of the split tail (points)
 

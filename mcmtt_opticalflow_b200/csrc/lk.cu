@@ -603,9 +603,12 @@ __device__ __forceinline__ int stage_tgt(const LkParams &P, int level, int plane
     return off;
 }
 
+// kStats (bench / inspection build of the kernel only, psnw_lk_stats): counts the template passes (levels on which the
+// 2x2 system was formed) and the Gauss-Newton iterations of the solve in n_tmpl / n_iter.
+template <bool kStats>
 __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int plane_b, int max_level, float px, float py,
                                        uint32_t *ip, uint32_t *jp, uint32_t *dxp, Stage &S, const WarpRole &R, bool want_err,
-                                       Solve &o)
+                                       Solve &o, unsigned &n_tmpl, unsigned &n_iter)
 {
     constexpr float half = (kW - 1) * 0.5f;
     float next_x = 0.f, next_y = 0.f, er = 0.f;
@@ -672,6 +675,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             // lane 31 owns a single run: its second one re-reads run 62 and is dropped from every sum
             if (!R.two) { a11[1] = 0; a12[1] = 0; a22[1] = 0; }
         }
+        if (kStats) ++n_tmpl;
         __syncwarp();                            // every lane is done with the I / dI patches ...
         prefetch_src(P, plane_a, level - 1, px, py, ip, dxp, S, R);   // ... so the next level's copies may overwrite them
         stage_wait_tgt(S);                       // the target patch has landed
@@ -694,6 +698,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             const int jt = (w00 & 0xffff) | (w01 << 16), jb = (w10 & 0xffff) | (w11 << 16);
+            if (kStats) ++n_iter;
             if (!staged || (unsigned)(inx - sx0) > 2u * kMargin || (unsigned)(iny - sy0) > 2u * kMargin) {
                 sx0 = patch_origin(inx, Lw); sy0 = patch_origin(iny, Lh);
                 __syncwarp();
@@ -760,6 +765,7 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
 // Persistent warps: every warp draws point indices from a device counter until the batch is exhausted, so a slow point
 // (many iterations, re-staging) never holds three idle warps of its CTA and the last wave has no tail of empty slots.
 // The last warp to finish resets the two counters, which keeps launches on one context self-contained.
+template <bool kStats>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, PSNW_LK_MINB)
 lk_w21_kernel(const __grid_constant__ LkParams P)
 {
@@ -839,8 +845,14 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
 #pragma unroll 1
         for (int pass = first; pass < last; ++pass) {
             const float sx = pass ? f.x : p0.x, sy = pass ? f.y : p0.y;
-            solve_w21(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, S, R, pass == 0, cur);
+            unsigned n_tmpl = 0, n_iter = 0;
+            solve_w21<kStats>(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, S, R, pass == 0, cur, n_tmpl, n_iter);
             if (pass) b = cur; else f = cur;
+            if (kStats && lane == 0) {
+                atomicAdd(P.stats, 1ull);
+                atomicAdd(P.stats + 1, (unsigned long long)n_tmpl);
+                atomicAdd(P.stats + 2, (unsigned long long)n_iter);
+            }
         }
         if (fwd_only) {
             if (lane == 0) {
@@ -871,7 +883,7 @@ int lk_w21_resident_ctas(int max_per_sm)
 {
     int dev = 0, sms = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk_w21_kernel, kWarpsPerCta * 32, 0) != cudaSuccess)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lk_w21_kernel<false>, kWarpsPerCta * 32, 0) != cudaSuccess)
         return -1;
     if (max_per_sm > 0) per_sm = min(per_sm, max_per_sm);
     return sms * per_sm;
@@ -883,7 +895,8 @@ int launch_lk(const LkParams &P, int all_21x21, int max_win_px, int resident_cta
     if (all_21x21) {
         int grid = (P.n_pts + kWarpsPerCta - 1) / kWarpsPerCta;
         if (P.work) grid = min(grid, max(resident_ctas, 1));
-        lk_w21_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(P);
+        if (P.stats) lk_w21_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(P);
+        else         lk_w21_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(P);
     } else {
         const int stride = (max_win_px + 7) & ~7;
         const size_t smem = (size_t)stride * 6;

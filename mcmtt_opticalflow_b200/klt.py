@@ -58,6 +58,7 @@ EXPORTS = [
     "psnw_box_update", "psnw_sync", "psnw_last_error", "psnw_get_stream", "psnw_level_info", "psnw_read_level",
     "psnw_read_level_apron", "psnw_klt_track_update", "psnw_get_params",
     "psnw_read_min_eig", "psnw_launch_count", "psnw_push_frame_bytes", "psnw_rebuild_pyramids", "psnw_levels_built",
+    "psnw_rebuild_pyramids_slot", "psnw_lk_stats",
 ]
 
 _lib = None
@@ -91,6 +92,8 @@ def load():
                                              C.c_int, C.c_int]
         lib.psnw_push_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int]
         lib.psnw_rebuild_pyramids.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.psnw_rebuild_pyramids_slot.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        lib.psnw_lk_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.psnw_klt_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                         C.c_float, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_klt_detect_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
@@ -232,9 +235,15 @@ class KLTContext:
         self._ck(self.lib.psnw_push_frames_bgr(self._h, n, cams.ctypes.data, ptrs, fr[0].strides[0], frame_idx,
                                                luma_bits, mem))
 
-    def rebuild_pyramids(self, cams):
+    def rebuild_pyramids(self, cams, slot=0):
         cams = np.ascontiguousarray(cams, np.int32)
-        self._ck(self.lib.psnw_rebuild_pyramids(self._h, len(cams), cams.ctypes.data))
+        self._ck(self.lib.psnw_rebuild_pyramids_slot(self._h, len(cams), cams.ctypes.data, slot))
+
+    def lk_stats(self, enable):
+        """-> dict(solves, template_passes, iterations) gathered since the previous call; switches the counting kernel on / off."""
+        out = (C.c_uint64 * 3)()
+        self._ck(self.lib.psnw_lk_stats(self._h, 1 if enable else 0, out))
+        return {"solves": int(out[0]), "template_passes": int(out[1]), "iterations": int(out[2])}
 
     def read_level(self, cam, slot, level):
         w, h, _ = self.level_info(level)
