@@ -181,7 +181,9 @@ PSNW_API int psnw_read_fast_map(psnw_ctx *ctx, int cam, uint8_t *map_out);
  *   out_xy, status, err   as calcOpticalFlowPyrLK's nextPts / status / err (err = 0 where status = 0)
  *   fb_err                if the context was created with fb_thresh >= 0 the kernel also runs the backward
  *                         pass out_xy -> p'' and sets status = st_f & st_b & (|p - p''| <= fb_thresh),
- *                         fb_err = |p - p''| (may be NULL to drop it).  With fb_thresh < 0 it is ignored.
+ *                         fb_err = |p - p''| (may be NULL to drop it).  A point the forward pass already lost keeps
+ *                         status 0: the backward pass is not run for it and its fb_err is 0.  With fb_thresh < 0
+ *                         fb_err is ignored.
  * Pyramid levels are truncated per window exactly like buildOpticalFlowPyramid (level kept while both
  * dimensions stay > window).  A target whose window cannot be tracked here (side < 1, not smaller than the frame, or more
  * than ~34 000 pixels) is skipped, not an error: its points come back unmoved with status 0, the other targets of the
@@ -244,6 +246,38 @@ PSNW_API int psnw_klt_track_update(psnw_ctx *ctx, int cam, int slot_from, int sl
  */
 PSNW_API int psnw_points_in_boxes(psnw_ctx *ctx, const float *pts_xy, const int *tracker_offsets, int n_trackers,
                                   const double *det_boxes, int n_detections, int *counts, int mem_flags);
+
+/*
+ * The backward chain of a frame's detections (Tracker2D.cpp:763-811) as ONE call: no host round trip between its
+ * dependent steps.  Step k = 1 .. n_steps (clamped to the frames held - 1, the reference stops at the first empty FIFO
+ * slot, :768) tracks every live target's current points from ring slot k-1 into slot k (window win_wh[t]; the LK status is
+ * ignored like at :787), runs LocalSearchKLT with boxes_in[t] -- always the detection box, :770 -- and
+ *   - a target with fewer than min_inliers inliers stops for good (:788; reference value 4),
+ *   - else its box of step k is recorded and its points become the inliers' tracked positions in index order (:802-807).
+ * Points are padded per target: pts_xy[t][0 .. counts[t]) of [n_targets][cap][2] (the layout psnw_klt_detect writes).
+ *   boxes_steps[n_steps][n_targets][4]   box of step k at [k-1] (zeros where the target had stopped)
+ *   steps_done[n_targets]                last step the target completed (0 .. n_steps)
+ *   pts_steps[n_steps][n_targets][cap][2], counts_steps[n_steps][n_targets]
+ *                                        the target's points AFTER step k (= vecvecTrackedFeatures[k], :807)
+ *   first_inlier_mask[n_targets][cap]    inliers of step 1 among the input points (the reference also keeps those, :792-800)
+ * mem_flags: PSNW_MEM_HOST / PSNW_MEM_PINNED / PSNW_MEM_DEVICE (win_wh is always host memory).  n_targets * cap <= max_points.
+ */
+PSNW_API int psnw_klt_backward_chain(psnw_ctx *ctx, int cam, int n_steps, const float *pts_xy, const int *counts,
+                                     int n_targets, int cap, const int *win_wh, const double *boxes_in, int min_inliers,
+                                     double *boxes_steps, int *steps_done, float *pts_steps, int *counts_steps,
+                                     uint8_t *first_inlier_mask, int mem_flags);
+
+/*
+ * "Next" row, the whole check: the optical-flow majority rule of Tracker2D.cpp:931-944 and :981-1022 on the
+ * device.  counts[d][t] = tracked points of tracker t (pts_xy, CSR by tracker_offsets) inside detection box d, for the
+ * trackers that reach the comparison (tracker_ok[t] != 0: at least 4 status-ok pairs, :889) and whose new box
+ * tracker_boxes[t] overlaps the detection box (PSN_Rect::overlap, :937), else 0; wipe[d] = 1 where the reference resets the
+ * detection's row of the cost matrix to infinity: its run-length rule over featuresInDetectionBox (first run whole, later
+ * runs minus one, last run never compared unless alone) leaves no run above ratio x all points (reference ratio 0.5).
+ */
+PSNW_API int psnw_flow_majority(psnw_ctx *ctx, const float *pts_xy, const int *tracker_offsets, int n_trackers,
+                                const double *tracker_boxes, const uint8_t *tracker_ok, const double *det_boxes,
+                                int n_detections, double ratio, int *counts, uint8_t *wipe, int mem_flags);
 
 PSNW_API int psnw_sync(psnw_ctx *ctx);
 /* Device-side join of an overlapped detect / push into the context stream (see PSNW_MEM_OVERLAP): work enqueued on the

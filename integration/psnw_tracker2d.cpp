@@ -198,47 +198,44 @@ size_t CPSNWhere_Tracker2D::Track2D_BackwardFeatureTracking(std::vector<stDetect
     }
     m_vecDetection2D.swap(kept);
     const int N = (int)m_vecDetection2D.size();
-    std::vector<char> alive(N, 1);
 
-    // backward feature tracking, :763-811
+    // backward feature tracking, :763-811: every detection, every step, ONE call -- the three dependent steps (LK into the
+    // older frame, LocalSearchKLT against the detection box, inliers carried on) stay on the device
     const int held = psnw_frames_held(m_klt, m_nKltCam);
-    for (int k = 1; k < PSN_2D_BACKTRACKING_INTERVAL && k < held; ++k) {
-        std::vector<int> idx;
-        for (int d = 0; d < N; ++d) if (alive[d]) idx.push_back(d);
-        if (idx.empty()) break;
-        std::vector<Point2f> pts;
-        std::vector<int> tgt, win(2 * idx.size()), off(idx.size() + 1, 0);
-        std::vector<double> bin(4 * idx.size());
-        for (size_t i = 0; i < idx.size(); ++i) {
-            const stDetectedObject &det = m_vecDetection2D[idx[i]];
-            const PSN_Rect &b = det.detection.box;
-            win[2 * i] = (int)b.w; win[2 * i + 1] = (int)b.w;                              // cv::Size(w, w), :782
-            bin[4 * i] = b.x; bin[4 * i + 1] = b.y; bin[4 * i + 2] = b.w; bin[4 * i + 3] = b.h;   // always the detection box, :770
-            pts.insert(pts.end(), curPts[idx[i]].begin(), curPts[idx[i]].end());
-            tgt.insert(tgt.end(), curPts[idx[i]].size(), (int)i);
-            off[i + 1] = (int)pts.size();
+    const int steps = std::min(PSN_2D_BACKTRACKING_INTERVAL - 1, held - 1);
+    if (N > 0 && steps > 0) {
+        std::vector<float> pts(2 * (size_t)N * K, -1.0e6f);
+        std::vector<int> cnt(N), win(2 * (size_t)N), done(N, 0), cnt_steps((size_t)steps * N, 0);
+        std::vector<double> bin(4 * (size_t)N), bsteps(4 * (size_t)steps * N, 0.0);
+        std::vector<float> pts_steps(2 * (size_t)steps * N * K);
+        std::vector<unsigned char> first((size_t)N * K, 0);
+        for (int d = 0; d < N; ++d) {
+            const PSN_Rect &b = m_vecDetection2D[d].detection.box;
+            win[2 * d] = (int)b.w; win[2 * d + 1] = (int)b.w;                                      // cv::Size(w, w), :782
+            bin[4 * d] = b.x; bin[4 * d + 1] = b.y; bin[4 * d + 2] = b.w; bin[4 * d + 3] = b.h;    // always the detection box, :770
+            cnt[d] = (int)curPts[d].size();
+            memcpy(&pts[2 * (size_t)d * K], curPts[d].data(), sizeof(Point2f) * curPts[d].size());
         }
-        const int n = (int)pts.size();
-        std::vector<Point2f> out(n);
-        std::vector<unsigned char> st(n), inl(n);
-        std::vector<float> err(n);
-        std::vector<double> bout(4 * idx.size());
-        std::vector<int> ninl(idx.size());
-        // calcOpticalFlowPyrLK (:776-782) + LocalSearchKLT (:787) of every live detection as one call; position estimation
-        // ignores the LK status in the backward pass (:787)
-        if (!Check(psnw_klt_track_update(m_klt, m_nKltCam, k - 1, k, &pts[0].x, off.data(), (int)idx.size(), win.data(), bin.data(),
-                                         /*use_status=*/0, &out[0].x, st.data(), err.data(), bout.data(), inl.data(), ninl.data(),
-                                         PSNW_MEM_HOST), "psnw_klt_track_update(backward)")) break;
-        for (size_t i = 0; i < idx.size(); ++i) {
-            stDetectedObject &det = m_vecDetection2D[idx[i]];
-            if ((size_t)ninl[i] < PSN_2D_FEATURE_MIN_NUM_TRACK) { alive[idx[i]] = 0; continue; }   // :788
-            det.boxes.push_back(PSN_Rect(bout[4 * i], bout[4 * i + 1], bout[4 * i + 2], bout[4 * i + 3]));
-            std::vector<Point2f> curInl, prevInl;
-            for (int j = off[i]; j < off[i + 1]; ++j)
-                if (inl[j]) { curInl.push_back(pts[j]); prevInl.push_back(out[j]); }
-            if (det.vecvecTrackedFeatures.empty()) det.vecvecTrackedFeatures.push_back(curInl);    // :792-800
-            det.vecvecTrackedFeatures.push_back(prevInl);                                          // :807
-            curPts[idx[i]].swap(prevInl);
+        if (Check(psnw_klt_backward_chain(m_klt, m_nKltCam, steps, pts.data(), cnt.data(), N, K, win.data(), bin.data(),
+                                          (int)PSN_2D_FEATURE_MIN_NUM_TRACK, bsteps.data(), done.data(), pts_steps.data(), cnt_steps.data(),
+                                          first.data(), PSNW_MEM_HOST), "psnw_klt_backward_chain")) {
+            for (int d = 0; d < N; ++d) {
+                stDetectedObject &det = m_vecDetection2D[d];
+                for (int k = 1; k <= done[d]; ++k) {
+                    const double *bo = &bsteps[4 * ((size_t)(k - 1) * N + d)];
+                    det.boxes.push_back(PSN_Rect(bo[0], bo[1], bo[2], bo[3]));                     // :789
+                    if (k == 1) {                                                                  // :792-800
+                        std::vector<Point2f> curInl;
+                        for (int j = 0; j < cnt[d]; ++j)
+                            if (first[(size_t)d * K + j]) curInl.push_back(curPts[d][j]);
+                        det.vecvecTrackedFeatures.push_back(curInl);
+                    }
+                    const Point2f *pp = reinterpret_cast<const Point2f *>(&pts_steps[2 * (((size_t)(k - 1) * N + d) * K)]);
+                    std::vector<Point2f> prevInl(pp, pp + cnt_steps[(size_t)(k - 1) * N + d]);     // :802-807
+                    det.vecvecTrackedFeatures.push_back(prevInl);
+                    curPts[d].swap(prevInl);
+                }
+            }
         }
     }
     for (int d = 0; d < N; ++d)                                                                    // :814-817
@@ -257,7 +254,6 @@ size_t CPSNWhere_Tracker2D::Track2D_BackwardFeatureTracking(std::vector<stDetect
 std::vector<float> CPSNWhere_Tracker2D::Track2D_ForwardTrackingAndGetMatchingScore()
 {
     const size_t numDetection = m_vecDetection2D.size(), T = m_queueActiveTracker2D.size();
-    std::vector<std::deque<int>> featuresInDetectionBox(numDetection);
     std::vector<float> matchingCostArray(numDetection * T, std::numeric_limits<float>::infinity());
     if (T == 0 || psnw_frames_held(m_klt, m_nKltCam) < 2) return matchingCostArray;
 
@@ -287,6 +283,26 @@ std::vector<float> CPSNWhere_Tracker2D::Track2D_ForwardTrackingAndGetMatchingSco
                                          PSNW_MEM_HOST), "psnw_klt_track_update(forward)")) return matchingCostArray;
     }
 
+    // points of every tracker inside every detection box + the majority rule (:931-944, :981-1022) on the device: the
+    // tracked points of all trackers go up once more as one array, D x T counts and D flags come back
+    std::vector<unsigned char> trkOk(T, 0), wipe(numDetection, 0);
+    std::vector<int> inBox(numDetection * T, 0);
+    for (size_t t = 0; t < T; ++t) {
+        size_t okPts = 0;
+        for (int j = off[t]; j < off[t + 1]; ++j) okPts += st[j] ? 1 : 0;
+        trkOk[t] = okPts >= PSN_2D_FEATURE_MIN_NUM_TRACK ? 1 : 0;                                  // :889
+    }
+    if (n > 0 && numDetection > 0) {
+        std::vector<double> dbox(4 * numDetection);
+        for (size_t d = 0; d < numDetection; ++d) {
+            const PSN_Rect &b = m_vecDetection2D[d].detection.box;
+            dbox[4 * d] = b.x; dbox[4 * d + 1] = b.y; dbox[4 * d + 2] = b.w; dbox[4 * d + 3] = b.h;
+        }
+        if (!Check(psnw_flow_majority(m_klt, &out[0].x, off.data(), (int)T, bout.data(), trkOk.data(), dbox.data(), (int)numDetection,
+                                      PSN_2D_MIN_OPTICAL_FLOW_MAJORITY_RATIO, inBox.data(), wipe.data(), PSNW_MEM_HOST),
+                   "psnw_flow_majority")) return matchingCostArray;
+    }
+
     for (size_t t = 0; t < T; ++t) {
         stTracker2D *curTracker = m_queueActiveTracker2D[t];
         std::vector<Point2f> vecPrev, vecCurr;
@@ -303,9 +319,7 @@ std::vector<float> CPSNWhere_Tracker2D::Track2D_ForwardTrackingAndGetMatchingSco
         for (size_t d = 0; d < numDetection; ++d) {
             const stDetectedObject &det = m_vecDetection2D[d];
             const size_t costPos = d * T + t;
-            if (!newBox.overlap(det.detection.box)) continue;
-            for (size_t f = 0; f < curTracker->trackedPoints.size(); ++f)
-                if (det.detection.box.contain(curTracker->trackedPoints[f])) featuresInDetectionBox[d].push_back((int)t);
+            if (!newBox.overlap(det.detection.box)) continue;                                      // (the point counts of :940-944: inBox)
             double boxCost = 0.0;
             const size_t len = std::min((size_t)PSN_2D_BACKTRACKING_INTERVAL, std::min(curTracker->boxes.size(), det.boxes.size()));
             size_t tb = (size_t)curTracker->duration;                                              // duration = # of boxes - 1
@@ -329,19 +343,9 @@ std::vector<float> CPSNWhere_Tracker2D::Track2D_ForwardTrackingAndGetMatchingSco
         curTracker->trackedPoints = vecCurr;
     }
 
-    // feature point majority check, :981-1022
+    // feature point majority check, :981-1022 (decided on the device above)
     for (size_t d = 0; d < numDetection; ++d) {
-        const std::deque<int> &q = featuresInDetectionBox[d];
-        if (q.empty()) continue;
-        int numMajor = 0, numCur = 0, curIdx = q.front();
-        for (size_t f = 0; f < q.size(); ++f) {
-            if (curIdx == q[f]) { numCur++; continue; }
-            if (numCur > numMajor) numMajor = numCur;
-            curIdx = q[f];
-            numCur = 0;
-        }
-        if (q.front() == curIdx) numMajor = numCur;                                                // sole tracker
-        if (numMajor > q.size() * PSN_2D_MIN_OPTICAL_FLOW_MAJORITY_RATIO) continue;
+        if (!wipe[d]) continue;
         for (size_t t = 0; t < T; ++t) matchingCostArray[d * T + t] = std::numeric_limits<float>::infinity();
     }
     return matchingCostArray;

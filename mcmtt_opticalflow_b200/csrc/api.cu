@@ -1298,6 +1298,143 @@ int psnw_klt_track_update(psnw_ctx *ctx, int cam, int slot_from, int slot_to, co
     return PSNW_OK;
 }
 
+// The reference's backward chain (Tracker2D.cpp:763-811) for every detection of a camera without a host round trip between
+// the dependent steps: per step one LK launch, one LocalSearchKLT launch and one compaction launch, all enqueued at once.
+int psnw_klt_backward_chain(psnw_ctx *ctx, int cam, int n_steps, const float *pts_xy, const int *counts, int n_targets, int cap,
+                            const int *win_wh, const double *boxes_in, int min_inliers, double *boxes_steps, int *steps_done,
+                            float *pts_steps, int *counts_steps, uint8_t *first_inlier_mask, int mem_flags)
+{
+    if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
+    if (n_targets == 0) return PSNW_OK;
+    if (n_targets < 0 || cap < 1 || cap > PSNW_MAX_PTS_PER_TARGET || n_steps < 1 || !pts_xy || !counts || !boxes_in || !boxes_steps ||
+        !steps_done || !pts_steps || !counts_steps || !first_inlier_mask)
+        return fail(ctx, PSNW_EARG, "psnw_klt_backward_chain arguments");
+    if (cam < 0 || cam >= ctx->p.n_cameras) return fail(ctx, PSNW_EARG, "psnw_klt_backward_chain: camera index out of range");
+    mem_flags &= 0xff;
+    const bool dev = mem_flags == PSNW_MEM_DEVICE;
+    const size_t n = (size_t)n_targets * cap;
+    if (n > (size_t)ctx->p.max_points || n_targets > ctx->p.max_targets)
+        return fail(ctx, PSNW_ENOMEM, "psnw_klt_backward_chain: n_targets * cap exceeds max_points (or n_targets max_targets)");
+    // the reference stops at the first empty FIFO slot (:768-769): steps beyond the frames held are simply not run
+    const int steps = std::min(n_steps, ctx->held[cam] - 1);
+    if (ctx->held[cam] < 1) return fail(ctx, PSNW_ESTATE, "psnw_klt_backward_chain: camera holds no frame");
+
+    // scratch (the LK launches below run on device pointers and take nothing from the arena)
+    const size_t a256 = 256;
+    size_t need = 16 * a256 + n * 8 /*P0*/ + n * (8 + 1 + 4 + 4 + 1 + 1 + 4) /*O, st, err, fb, live x2, tgt*/ + (size_t)n_targets * (32 + 16) + (size_t)(n_targets + 1) * 4;
+    if (!dev) need += (size_t)n_steps * (n * 8 + (size_t)n_targets * (32 + 4) + 2 * a256) + n + (size_t)n_targets * 36 + 4 * a256;
+    int rc = ensure(ctx, ctx->arena, need + (1 << 16));
+    if (rc) return rc;
+    ctx->arena_off = 0;
+    float2 *P0 = take<float2>(ctx, n), *O = take<float2>(ctx, n);
+    uint8_t *st = take<uint8_t>(ctx, n), *liveA = take<uint8_t>(ctx, n), *liveB = take<uint8_t>(ctx, n), *mask_k = take<uint8_t>(ctx, n);
+    float *err = take<float>(ctx, n), *fb = ctx->p.fb_thresh >= 0.f ? take<float>(ctx, n) : nullptr;
+    int *tgt = take<int>(ctx, n), *offs = take<int>(ctx, n_targets + 1), *alive = take<int>(ctx, n_targets), *ninl = take<int>(ctx, n_targets);
+    double *box_k = take<double>(ctx, (size_t)n_targets * 4);
+    int *d_counts = dev ? const_cast<int *>(counts) : take<int>(ctx, n_targets);
+    double *d_boxes_in = dev ? const_cast<double *>(boxes_in) : take<double>(ctx, (size_t)n_targets * 4);
+    double *d_boxes_steps = dev ? boxes_steps : take<double>(ctx, (size_t)n_steps * n_targets * 4);
+    int *d_steps_done = dev ? steps_done : take<int>(ctx, n_targets);
+    float2 *d_pts_steps = dev ? reinterpret_cast<float2 *>(pts_steps) : take<float2>(ctx, (size_t)n_steps * n);
+    int *d_counts_steps = dev ? counts_steps : take<int>(ctx, (size_t)n_steps * n_targets);
+    uint8_t *d_first = dev ? first_inlier_mask : take<uint8_t>(ctx, n);
+    if (ctx->arena_off > ctx->arena.cap) return fail(ctx, PSNW_ENOMEM, "psnw_klt_backward_chain: scratch arena exhausted");
+
+    CK(cudaMemcpyAsync(P0, pts_xy, n * sizeof(float2), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (!dev) {
+        CK(cudaMemcpyAsync(d_counts, counts, sizeof(int) * n_targets, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_boxes_in, boxes_in, sizeof(double) * 4 * n_targets, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // steps that are not run report no points / no boxes
+    CK(cudaMemsetAsync(d_counts_steps, 0, sizeof(int) * (size_t)n_steps * n_targets, ctx->stream));
+    CK(cudaMemsetAsync(d_boxes_steps, 0, sizeof(double) * 4 * (size_t)n_steps * n_targets, ctx->stream));
+    CK(cudaMemsetAsync(d_first, 0, n, ctx->stream));
+    int r = launch_chain_init(P0, d_counts, n_targets, cap, liveA, tgt, offs, alive, d_steps_done, ctx->stream);
+    if (r < 0) return fail(ctx, PSNW_ECUDA, "chain_init_kernel launch", cudaGetLastError());
+    ctx->launches += r;
+
+    const float2 *cur = P0;
+    uint8_t *live = liveA, *live_next = liveB;
+    for (int k = 1; k <= steps; ++k) {
+        psnw_track_job j;
+        j.cam = cam; j.slot_from = k - 1; j.slot_to = k;
+        j.n_pts = (int)n; j.pts_xy = reinterpret_cast<const float *>(cur); j.target_of_pt = tgt;
+        j.n_targets = n_targets; j.win_wh = win_wh;
+        j.out_xy = reinterpret_cast<float *>(O); j.status = st; j.err = err; j.fb_err = fb;
+        rc = psnw_klt_track_batch(ctx, &j, 1, PSNW_MEM_DEVICE);
+        if (rc) return rc;
+        uint8_t *mask = k == 1 ? d_first : mask_k;
+        r = launch_box_update(d_boxes_in, n_targets, cur, O, live, offs, box_k, mask, ninl, cap, ctx->stream);       // :787, always the detection box (:770)
+        if (r < 0) return fail(ctx, PSNW_ECUDA, "box_update_kernel launch", cudaGetLastError());
+        ctx->launches += r;
+        float2 *next = d_pts_steps + (size_t)(k - 1) * n;
+        r = launch_chain_compact(O, mask, ninl, box_k, n_targets, cap, min_inliers, k, next, live_next, d_counts_steps + (size_t)(k - 1) * n_targets,
+                                 d_boxes_steps + (size_t)(k - 1) * n_targets * 4, alive, d_steps_done, ctx->stream);
+        if (r < 0) return fail(ctx, PSNW_ECUDA, "chain_compact_kernel launch", cudaGetLastError());
+        ctx->launches += r;
+        cur = next;
+        std::swap(live, live_next);
+    }
+    if (!dev) {
+        CK(cudaMemcpyAsync(boxes_steps, d_boxes_steps, sizeof(double) * 4 * (size_t)n_steps * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(steps_done, d_steps_done, sizeof(int) * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+        if (steps > 0) CK(cudaMemcpyAsync(pts_steps, d_pts_steps, sizeof(float2) * (size_t)steps * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(counts_steps, d_counts_steps, sizeof(int) * (size_t)n_steps * n_targets, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(first_inlier_mask, d_first, n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return PSNW_OK;
+}
+
+// "next" row f-3 in full: the optical-flow majority check of Tracker2D.cpp:931-944 / :981-1022 on the device
+int psnw_flow_majority(psnw_ctx *ctx, const float *pts_xy, const int *tracker_offsets, int n_trackers, const double *tracker_boxes,
+                       const uint8_t *tracker_ok, const double *det_boxes, int n_detections, double ratio, int *counts,
+                       uint8_t *wipe, int mem_flags)
+{
+    if (!ctx) return PSNW_EARG;
+    if (int rc_enter = enter(ctx)) return rc_enter;
+    if (n_trackers == 0 || n_detections == 0) return PSNW_OK;
+    if (n_trackers < 0 || n_detections < 0 || !tracker_offsets || !tracker_boxes || !tracker_ok || !det_boxes || !counts || !wipe)
+        return fail(ctx, PSNW_EARG, "psnw_flow_majority arguments");
+    if (n_trackers > ctx->p.max_targets || n_detections > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_flow_majority: max_targets exceeded");
+    mem_flags &= 0xff;
+    int r;
+    if (mem_flags == PSNW_MEM_DEVICE) {
+        r = launch_flow_majority(reinterpret_cast<const float2 *>(pts_xy), tracker_offsets, n_trackers, tracker_boxes, tracker_ok, det_boxes,
+                                 n_detections, ratio, counts, wipe, ctx->stream);
+        if (r < 0) return fail(ctx, PSNW_ECUDA, "flow majority launch", cudaGetLastError());
+        ctx->launches += r;
+        return PSNW_OK;
+    }
+    if (tracker_offsets[0] != 0) return fail(ctx, PSNW_EARG, "psnw_flow_majority: tracker_offsets[0] must be 0");
+    for (int t = 0; t < n_trackers; ++t)
+        if (tracker_offsets[t + 1] < tracker_offsets[t]) return fail(ctx, PSNW_EARG, "psnw_flow_majority: offsets not ascending");
+    const int n_pts = tracker_offsets[n_trackers];
+    if (n_pts > ctx->p.max_points) return fail(ctx, PSNW_ENOMEM, "psnw_flow_majority: max_points exceeded");
+    if (n_pts > 0 && !pts_xy) return fail(ctx, PSNW_EARG, "psnw_flow_majority: null points");
+    const size_t ncnt = (size_t)n_trackers * n_detections;
+    int rc = ensure(ctx, ctx->arena, (size_t)n_pts * 8 + (size_t)(n_trackers + 1) * 4 + (size_t)(n_detections + n_trackers) * 33 + ncnt * 4 + n_detections + 8192);
+    if (rc) return rc;
+    ctx->arena_off = 0;
+    float2 *d_pts = take<float2>(ctx, n_pts);
+    int *d_off = take<int>(ctx, n_trackers + 1), *d_cnt = take<int>(ctx, ncnt);
+    double *d_det = take<double>(ctx, (size_t)n_detections * 4), *d_trk = take<double>(ctx, (size_t)n_trackers * 4);
+    uint8_t *d_ok = take<uint8_t>(ctx, n_trackers), *d_wipe = take<uint8_t>(ctx, n_detections);
+    if (n_pts > 0) CK(cudaMemcpyAsync(d_pts, pts_xy, sizeof(float2) * n_pts, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_off, tracker_offsets, sizeof(int) * (n_trackers + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_det, det_boxes, sizeof(double) * 4 * n_detections, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_trk, tracker_boxes, sizeof(double) * 4 * n_trackers, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_ok, tracker_ok, n_trackers, cudaMemcpyHostToDevice, ctx->stream));
+    r = launch_flow_majority(d_pts, d_off, n_trackers, d_trk, d_ok, d_det, n_detections, ratio, d_cnt, d_wipe, ctx->stream);
+    if (r < 0) return fail(ctx, PSNW_ECUDA, "flow majority launch", cudaGetLastError());
+    ctx->launches += r;
+    CK(cudaMemcpyAsync(counts, d_cnt, sizeof(int) * ncnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(wipe, d_wipe, n_detections, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return PSNW_OK;
+}
+
 int psnw_points_in_boxes(psnw_ctx *ctx, const float *pts_xy, const int *tracker_offsets, int n_trackers,
                          const double *det_boxes, int n_detections, int *counts, int mem_flags)
 {

@@ -180,6 +180,132 @@ points_in_boxes_kernel(const float2 *__restrict__ pts, const int *__restrict__ o
     if (tid == 0) counts[(size_t)d * n_trk + t] = s_cnt;
 }
 
+
+// ---- device-resident backward chain (Tracker2D.cpp:763-811) --------------------------------------------------------
+// Points of target t live in the padded slots [t * cap, (t + 1) * cap); `live` marks the slots in use (the LK status is
+// ignored in the backward pass, :787: the status array handed to box_update_kernel is this liveness).  Dead slots hold a
+// far-away sentinel, which the LK kernels reject at once.
+constexpr float kDeadSlot = -1.0e6f;
+
+// first step: liveness and target index of every slot from the per-target counts; dead slots get the sentinel
+__global__ void chain_init_kernel(float2 *__restrict__ pts, const int *__restrict__ counts, int n_targets, int cap,
+                                  uint8_t *__restrict__ live, int *__restrict__ tgt, int *__restrict__ offsets,
+                                  int *__restrict__ alive, int *__restrict__ steps_done)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_targets) offsets[i] = i * cap;
+    if (i < n_targets) { alive[i] = 1; steps_done[i] = 0; }
+    if (i >= n_targets * cap) return;
+    const int t = i / cap, k = i - t * cap;
+    const bool on = k < min(max(counts[t], 0), cap);
+    live[i] = on ? 1 : 0;
+    tgt[i] = t;
+    if (!on) pts[i] = make_float2(kDeadSlot, kDeadSlot);
+}
+
+// after LocalSearchKLT of step k: a target with >= min_inliers inliers records its box and continues with the inliers'
+// tracked positions, compacted in index order (:788-807); any other target stops for good (:788 break)
+__global__ void __launch_bounds__(256)
+chain_compact_kernel(const float2 *__restrict__ tracked, const uint8_t *__restrict__ mask, const int *__restrict__ n_inl,
+                     const double *__restrict__ box_step, int cap, int min_inliers, int step,
+                     float2 *__restrict__ next_pts, uint8_t *__restrict__ next_live, int *__restrict__ next_count,
+                     double *__restrict__ boxes_steps, int *__restrict__ alive, int *__restrict__ steps_done)
+{
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool go = alive[t] != 0 && n_inl[t] >= min_inliers;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    if (tid == 0) {
+        if (go) {
+            steps_done[t] = step;
+            for (int k = 0; k < 4; ++k) boxes_steps[4 * t + k] = box_step[4 * t + k];
+        } else {
+            alive[t] = 0;
+        }
+        next_count[t] = go ? n_inl[t] : 0;
+    }
+    for (int i0 = 0; i0 < cap; i0 += 256) {
+        const int i = i0 + tid;
+        const bool in = go && i < cap && mask[(size_t)t * cap + i] != 0;
+        const unsigned b = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_warp[warp] = __popc(b);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (in) next_pts[(size_t)t * cap + before + __popc(b & ((1u << lane) - 1u))] = tracked[(size_t)t * cap + i];
+        __syncthreads();
+        if (tid == 0) { int s = 0; for (int w = 0; w < 8; ++w) s += s_warp[w]; s_base += s; }
+        __syncthreads();
+    }
+    const int n = go ? s_base : 0;
+    for (int i = tid; i < cap; i += 256) {
+        next_live[(size_t)t * cap + i] = i < n ? 1 : 0;
+        if (i >= n) next_pts[(size_t)t * cap + i] = make_float2(kDeadSlot, kDeadSlot);
+    }
+}
+
+// ---- optical-flow majority check on the device ("next" row f-3; Tracker2D.cpp:931-944 and :981-1022) ----------------
+// counts[d][t] = tracked points of tracker t inside detection box d, for the trackers that reach the comparison (ok[t]:
+// >= 4 status-ok pairs, :889) and whose new box overlaps the detection box (:937); 0 otherwise.
+__global__ void __launch_bounds__(128)
+gated_points_in_boxes_kernel(const float2 *__restrict__ pts, const int *__restrict__ offsets, const double *__restrict__ trk_boxes,
+                             const uint8_t *__restrict__ ok, const double *__restrict__ det_boxes, int n_det, int n_trk,
+                             int *__restrict__ counts)
+{
+    __shared__ int s_cnt;
+    const int t = blockIdx.x, d = blockIdx.y, tid = threadIdx.x;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const double bx = det_boxes[4 * d], by = det_boxes[4 * d + 1], bw = det_boxes[4 * d + 2], bh = det_boxes[4 * d + 3];
+    const double tx = trk_boxes[4 * t], ty = trk_boxes[4 * t + 1], tw = trk_boxes[4 * t + 2], th = trk_boxes[4 * t + 3];
+    // PSN_Rect::overlap (PSNWhere_Types.h:160-163), newBox.overlap(detection.box)
+    const bool gate = ok[t] != 0 &&
+                      (__dsub_rn(fmax(__dadd_rn(tx, tw), __dadd_rn(bx, bw)), fmin(tx, bx)) < __dadd_rn(tw, bw)) &&
+                      (__dsub_rn(fmax(__dadd_rn(ty, th), __dadd_rn(by, bh)), fmin(ty, by)) < __dadd_rn(th, bh));
+    const double x1 = __dadd_rn(bx, bw), y1 = __dadd_rn(by, bh);
+    int c = 0;
+    if (gate) {
+        for (int i = offsets[t] + tid; i < offsets[t + 1]; i += 128) {
+            const float2 p = pts[i];
+            const double x = (double)p.x, y = (double)p.y;
+            c += (x >= bx && x < x1 && y >= by && y < y1) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (tid == 0) counts[(size_t)d * n_trk + t] = s_cnt;
+}
+
+// The reference walks featuresInDetectionBox[d] -- tracker indices, one entry per point, in tracker order -- with a
+// run-length rule (:991-1013): the first run counts all its points, a later run one less (the counter restarts at 0 on
+// the run's first point), the LAST run is never compared unless it is the only one; the detection's row of the cost
+// matrix is wiped unless the largest counted run exceeds ratio x all points.  One thread per detection restates it on
+// the per-tracker counts.
+__global__ void majority_kernel(const int *__restrict__ counts, int n_det, int n_trk, double ratio, uint8_t *__restrict__ wipe)
+{
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_det) return;
+    int total = 0, runs = 0, num_major = 0, num_cur = 0;
+    for (int t = 0; t < n_trk; ++t) {
+        const int c = counts[(size_t)d * n_trk + t];
+        if (c <= 0) continue;
+        if (runs > 0) {                          // switch to a new tracker: the run before is compared, the counter restarts
+            if (num_cur > num_major) num_major = num_cur;
+            num_cur = c - 1;
+        } else {
+            num_cur = c;
+        }
+        total += c;
+        ++runs;
+    }
+    if (runs == 1) num_major = num_cur;          // sole tracker, :1008-1011
+    wipe[d] = (total > 0 && !((double)num_major > __dmul_rn((double)total, ratio))) ? 1 : 0;
+}
+
 }  // namespace
 
 int launch_points_in_boxes(const float2 *pts, const int *offsets, int n_trk, const double *det_boxes, int n_det, int *counts,
@@ -188,6 +314,33 @@ int launch_points_in_boxes(const float2 *pts, const int *offsets, int n_trk, con
     if (n_trk <= 0 || n_det <= 0) return 0;
     points_in_boxes_kernel<<<dim3(n_trk, n_det), 128, 0, stream>>>(pts, offsets, det_boxes, n_det, n_trk, counts);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_chain_init(float2 *pts, const int *counts, int n_targets, int cap, uint8_t *live, int *tgt, int *offsets, int *alive,
+                      int *steps_done, cudaStream_t stream)
+{
+    const int n = std::max(n_targets * cap, n_targets + 1);
+    chain_init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pts, counts, n_targets, cap, live, tgt, offsets, alive, steps_done);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_chain_compact(const float2 *tracked, const uint8_t *mask, const int *n_inl, const double *box_step, int n_targets, int cap,
+                         int min_inliers, int step, float2 *next_pts, uint8_t *next_live, int *next_count, double *boxes_steps,
+                         int *alive, int *steps_done, cudaStream_t stream)
+{
+    if (n_targets <= 0) return 0;
+    chain_compact_kernel<<<n_targets, 256, 0, stream>>>(tracked, mask, n_inl, box_step, cap, min_inliers, step, next_pts, next_live,
+                                                         next_count, boxes_steps, alive, steps_done);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+int launch_flow_majority(const float2 *pts, const int *offsets, int n_trk, const double *trk_boxes, const uint8_t *ok,
+                         const double *det_boxes, int n_det, double ratio, int *counts, uint8_t *wipe, cudaStream_t stream)
+{
+    if (n_trk <= 0 || n_det <= 0) return 0;
+    gated_points_in_boxes_kernel<<<dim3(n_trk, n_det), 128, 0, stream>>>(pts, offsets, trk_boxes, ok, det_boxes, n_det, n_trk, counts);
+    majority_kernel<<<(n_det + 127) / 128, 128, 0, stream>>>(counts, n_det, n_trk, ratio, wipe);
+    return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }
 
 // opt-in shared-memory sizes are a per-device attribute: psnw_create calls this for the context's device

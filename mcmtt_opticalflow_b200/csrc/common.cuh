@@ -108,6 +108,13 @@ int launch_lk(const LkParams &P, int all_21x21, int max_win_px, int resident_cta
 int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
                       const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,
                       int *counts, int max_pts_per_target, cudaStream_t stream);
+int launch_chain_init(float2 *pts, const int *counts, int n_targets, int cap, uint8_t *live, int *tgt, int *offsets, int *alive,
+                      int *steps_done, cudaStream_t stream);
+int launch_chain_compact(const float2 *tracked, const uint8_t *mask, const int *n_inl, const double *box_step, int n_targets, int cap,
+                         int min_inliers, int step, float2 *next_pts, uint8_t *next_live, int *next_count, double *boxes_steps,
+                         int *alive, int *steps_done, cudaStream_t stream);
+int launch_flow_majority(const float2 *pts, const int *offsets, int n_trk, const double *trk_boxes, const uint8_t *ok,
+                         const double *det_boxes, int n_det, double ratio, int *counts, uint8_t *wipe, cudaStream_t stream);
 struct EigList {
     int n;
     int plane[24];

@@ -89,6 +89,7 @@ min_eig_kernel(const uint8_t *__restrict__ img_base, int w, int h, int pitch, in
 constexpr int kSelThreads = 512;
 constexpr float kUnusedSlot = -1.0e6f;
 constexpr int kMaxAccepted = 1024;        // accepted-corner list kept in shared memory by the sorted path
+constexpr int kHistBins = 2048;           // radix-select histogram: 11 bits of the score per pass
 
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 {
@@ -100,9 +101,42 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
+// Radix-select step over a histogram of kHistBins counts in shared memory: the kept set is the largest set of TOP bins whose
+// total stays <= budget.  Returns (through sel[0], sel[1]) the lowest kept bin (kHistBins if none fits) and the total of the
+// kept bins.  Every thread owns 4 adjacent bins; suffix sums across threads by a reverse scan (shuffles + one array).
+__device__ __forceinline__ void top_bins(const int *hist, int budget, int *sel, int *scratch, int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    const int c0 = hist[4 * tid], c1 = hist[4 * tid + 1], c2 = hist[4 * tid + 2], c3 = hist[4 * tid + 3];
+    const int mine = c0 + c1 + c2 + c3;
+    int incl = mine;                                   // sum over this lane and the lanes above it in the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += v;
+    }
+    if (lane == 0) scratch[warp] = incl;               // total of the warp
+    if (tid == 0) { sel[0] = kHistBins; sel[1] = 0; }
+    __syncthreads();
+    int above = incl - mine;                           // every bin above this thread's four
+    for (int w = warp + 1; w < kSelThreads / 32; ++w) above += scratch[w];
+    // suffix(i) = total of the bins >= i grows as i falls: bin i is kept iff suffix(i) <= budget, the kept set is an upper set
+    const int s3 = above + c3, s2 = s3 + c2, s1 = s2 + c1, s0 = s1 + c0;
+    int lo = kHistBins;
+    if (s3 <= budget) lo = 4 * tid + 3;
+    if (s2 <= budget) lo = 4 * tid + 2;
+    if (s1 <= budget) lo = 4 * tid + 1;
+    if (s0 <= budget) lo = 4 * tid;
+    if (lo < kHistBins) atomicMin(&sel[0], lo);
+    __syncthreads();
+    const int L = sel[0];
+    if (L >= 4 * tid && L < 4 * tid + 4) sel[1] = L == 4 * tid ? s0 : L == 4 * tid + 1 ? s1 : L == 4 * tid + 2 ? s2 : s3;
+    __syncthreads();
+}
+
 // key = (float bits of the score << 32) | raster index: scores are positive, so unsigned order == (score, address)
 // order and "largest key first" is exactly cv2's greaterThanPtr (score descending, ties: higher address first).
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(kSelThreads, 2)
 detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ targets,
                      int max_per_target, float quality, float min_dist, unsigned long long *__restrict__ cand_all,
                      int smem_cap, int tile_cap)
@@ -113,6 +147,9 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     __shared__ __align__(16) unsigned s_acc[kMaxAccepted + 4];   // accepted corners (x | y << 16), padded with far-away sentinels
     __shared__ int s_nc, s_nout;
     __shared__ __align__(16) unsigned s_near[32];                // chunk-local "too close to an earlier lane" masks of the walk
+    __shared__ __align__(16) unsigned long long s_top[kSelThreads];   // the strongest <= 512 candidates of a long list (radix select)
+    __shared__ int s_hist[kHistBins];
+    __shared__ int s_sel[4];                                      // {lowest kept bin, kept count above the bin, compaction cursor, -}
 
     const DetectTarget T = targets[blockIdx.x];
     const float *__restrict__ eig = T.eig;
@@ -151,9 +188,20 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     const float *mp = tiled ? tile - (ty0 * tw + tx0) : eig;     // map pointer such that mp[y * ms + x] is pixel (x, y)
     const int ms = tiled ? tw : pitch;
     if (!tiled) {
-#pragma unroll 2
-        for (int y = T.y0 + warp; y < T.y1; y += nwarps)
-            for (int x = T.x0 + lane; x < T.x1; x += 32) m = fmaxf(m, mp[y * ms + x]);
+        // linear walk over the ROI (every lane busy whatever its width), four independent loads in flight per thread
+        const int rw = T.x1 - T.x0, npx = rw * (T.y1 - T.y0);
+        const int sy = kSelThreads / rw, sx = kSelThreads - sy * rw;
+        int y = tid / rw, x = tid - y * rw;
+        float m4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int i = tid; i < npx; i += 4 * kSelThreads) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i + u * kSelThreads < npx) m4[u] = fmaxf(m4[u], eig[(size_t)(T.y0 + y) * pitch + T.x0 + x]);
+                x += sx; y += sy;
+                if (x >= rw) { x -= rw; y++; }
+            }
+        }
+        m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -167,43 +215,69 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     // 2. candidates: above threshold, 3x3 local maximum of the thresholded map, not on the frame border
     unsigned long long *glist = cand_all + T.cand_begin;
     const int cx0 = max(T.x0, 1), cx1 = min(T.x1, w - 1), cy0 = max(T.y0, 1), cy1 = min(T.y1, h - 1);
-    const int cw = max(cx1 - cx0, 1), n_cand_px = (cx1 > cx0 && cy1 > cy0) ? cw * (cy1 - cy0) : 0;
-    const int csy = kSelThreads / cw, csx = kSelThreads - csy * cw;
+    const int cw = max(cx1 - cx0, 1);
+    // A thread tests a run of 4 adjacent pixels: 3 rows x 6 columns loaded once serve the four 3x3 neighbourhoods.
+    //   cv2: THRESH_TOZERO at thr, then "equal to its 3x3 dilation" -- with thr >= 0 a neighbour at or below thr can not
+    //   exceed a pixel above it, so the neighbours need no thresholding; a negative threshold (a ROI without any positive
+    //   response) keeps the literal rule.
+    const int cw4 = (cw + 3) >> 2, nruns = (cx1 > cx0 && cy1 > cy0) ? cw4 * (cy1 - cy0) : 0;
+    const int rsy = kSelThreads / cw4, rsx = kSelThreads - rsy * cw4;
+    const int xlim = (tiled ? tx1 : w) - 1;                       // last column that may be read
+    const bool literal = !(thr >= 0.f);
     // Pass 0 keeps the keys in shared memory only; the global list (for the rounds of 3b) is written by a second pass in
     // the rare case that they do not fit -- the usual target sends nothing to HBM here.
     int nc = 0;
     for (int pass = 0; pass < 2; ++pass) {
-        int cyy = cy0 + tid / cw, cxx = cx0 + (tid - (tid / cw) * cw);
+        int ry = tid / cw4, rx = tid - ry * cw4;
         // uniform trip count: the list slots of a warp's candidates are reserved with one atomic per warp and step
-        for (int i0 = 0; i0 < n_cand_px; i0 += kSelThreads, cxx += csx, cyy += csy) {
-            if (cxx >= cx1) { cxx -= cw; cyy++; }
-            const int x = cxx, y = cyy;
-            bool is_max = false;
-            float v = 0.f;
-            if (i0 + tid < n_cand_px) {
-                const float *p = mp + y * ms + x;
-                v = p[0];
-                if (v > thr) {
-                    is_max = true;
+        for (int i0 = 0; i0 < nruns; i0 += kSelThreads, rx += rsx, ry += rsy) {
+            if (rx >= cw4) { rx -= cw4; ry++; }
+            const int x = cx0 + 4 * rx, y = cy0 + ry;
+            unsigned mine = 0u;                                   // bit k: pixel x + k is a candidate
+            float v4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (i0 + tid < nruns) {
+                const float *p = mp + y * ms;
+                float t[6], c[6], b[6];
 #pragma unroll
-                    for (int j = -1; j <= 1; ++j)
+                for (int k = 0; k < 6; ++k) {
+                    const int col = min(x - 1 + k, xlim);
+                    t[k] = p[col - ms]; c[k] = p[col]; b[k] = p[col + ms];
+                }
 #pragma unroll
-                        for (int i = -1; i <= 1; ++i) {
-                            float u = p[j * ms + i];
-                            u = (u > thr) ? u : 0.f;
-                            is_max = is_max && !(u > v);
-                        }
+                for (int k = 0; k < 4; ++k) v4[k] = c[k + 1];
+                if (literal) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        t[k] = t[k] > thr ? t[k] : 0.f; c[k] = c[k] > thr ? c[k] : 0.f; b[k] = b[k] > thr ? b[k] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float nb = fmaxf(fmaxf(fmaxf(t[k], t[k + 1]), fmaxf(t[k + 2], c[k])),
+                                           fmaxf(fmaxf(b[k], b[k + 1]), fmaxf(b[k + 2], c[k + 2])));
+                    if (x + k < cx1 && v4[k] > thr && !(nb > v4[k])) mine |= 1u << k;
                 }
             }
-            const unsigned found = __ballot_sync(0xffffffffu, is_max);
-            if (found) {
+            unsigned f[4];
+            int before = 0, total = 0;                            // candidates of lower lanes / lower k; of the whole warp
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                f[k] = __ballot_sync(0xffffffffu, (mine >> k) & 1u);
+                total += __popc(f[k]);
+            }
+            if (total) {
                 int pos = 0;
-                if (lane == 0) pos = atomicAdd(&s_nc, __popc(found));
-                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(found & ((1u << lane) - 1u));
-                if (is_max) {
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
-                    if (pass == 0) { if (pos < smem_cap) s_list[pos] = key; }
-                    else if (pos < T.cand_cap) glist[pos] = key;
+                if (lane == 0) pos = atomicAdd(&s_nc, total);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if ((mine >> k) & 1u) {
+                        const int slot = pos + before + __popc(f[k] & ((1u << lane) - 1u));
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(v4[k]) << 32) | (unsigned)(y * w + x + k);
+                        if (pass == 0) { if (slot < smem_cap) s_list[slot] = key; }
+                        else if (slot < T.cand_cap) glist[slot] = key;
+                    }
+                    before += __popc(f[k]);
                 }
             }
         }
@@ -221,9 +295,61 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     if (nc <= smem_cap && max_per_target <= kMaxAccepted) {
         // ---- 3a. sorted path: bitonic sort (descending) in shared memory, then one warp walks the sorted list in
         //          chunks of 32: test against the accepted list, resolve the chunk in order with ballots ----
+        // A long list (the large ROIs of a 1080p / 4K rig: thousands of local maxima) is first cut to its strongest <= 512
+        // keys by a two-pass radix select on the score bits (11 + 11 bits, histograms in shared memory): the greedy rule only
+        // ever looks at stronger candidates, so the walk over that prefix takes exactly the decisions of the walk over the
+        // whole list; if it ends short of max_per_target with candidates left out, the whole list is sorted after all.
+        unsigned long long *LST = s_list;
+        int m = nc;
+        const bool try_top = nc > kSelThreads && 2 * max_per_target <= 3 * kSelThreads / 2;
+        for (int attempt = try_top ? 0 : 1; attempt < 2; ++attempt) {
+        if (attempt == 0) {
+            int budget = kSelThreads, base_bits = 0;         // keys whose score bits >= base_bits are kept
+            for (int pass = 0; pass < 2; ++pass) {
+                const int shift = pass ? 10 : 21;
+                for (int i = tid; i < kHistBins; i += kSelThreads) s_hist[i] = 0;
+                __syncthreads();
+                for (int i = tid; i < nc; i += kSelThreads) {
+                    const unsigned sb = (unsigned)(s_list[i] >> 32);
+                    // pass 1 counts only the keys of the bin pass 0 could not take whole
+                    if (pass == 0 || (int)(sb >> 21) == base_bits - 1) atomicAdd(&s_hist[(sb >> shift) & (kHistBins - 1)], 1);
+                }
+                __syncthreads();
+                top_bins(s_hist, budget, s_sel, reinterpret_cast<int *>(s_red), tid);
+                const int lo = s_sel[0], kept = s_sel[1];
+                __syncthreads();
+                if (pass == 0) { base_bits = lo; budget -= kept; }        // bins >= lo whole; bin lo - 1 goes to pass 1
+                else           { base_bits = lo < kHistBins ? (((base_bits - 1) << 11) | lo) : (base_bits << 11); }
+                if (pass == 0 && lo == 0) { base_bits = 0; break; }       // (cannot happen with nc > 512: kept for safety)
+            }
+            // base_bits is now a 22-bit prefix threshold (score bits >> 10), or an 11-bit one shifted when pass 1 kept nothing
+            if (tid == 0) s_sel[2] = 0;
+            __syncthreads();
+            for (int i0 = 0; i0 < nc; i0 += kSelThreads) {
+                const int i = i0 + tid;
+                const unsigned long long key = i < nc ? s_list[i] : 0ull;
+                const bool keep = i < nc && (int)((unsigned)(key >> 32) >> 10) >= base_bits;
+                const unsigned found = __ballot_sync(0xffffffffu, keep);
+                if (found) {
+                    int pos = 0;
+                    if (lane == 0) pos = atomicAdd(&s_sel[2], __popc(found));
+                    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(found & ((1u << lane) - 1u));
+                    if (keep && pos < kSelThreads) s_top[pos] = key;
+                }
+            }
+            __syncthreads();
+            m = min(s_sel[2], kSelThreads);
+            LST = s_top;
+            if (m < max_per_target && m < nc) continue;       // the prefix cannot fill the quota: sort everything
+        } else {
+            LST = s_list;
+            m = nc;
+            n_out = 0;
+            __syncthreads();
+        }
         int n2 = kSelThreads;
-        while (n2 < nc) n2 <<= 1;
-        for (int i = nc + tid; i < n2; i += kSelThreads) s_list[i] = 0ull;
+        while (n2 < m) n2 <<= 1;
+        for (int i = m + tid; i < n2; i += kSelThreads) LST[i] = 0ull;
         __syncthreads();
         // each warp owns a contiguous segment of n2 / nwarps keys: compare distances inside a segment only need
         // __syncwarp; the few stages that cross segments take a block barrier (6 instead of ~60)
@@ -231,14 +357,14 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
         if (n2 == kSelThreads) {
             // the usual case, one key per thread: the key stays in a register, partners inside the warp are exchanged with
             // shuffles (35 of the 45 stages), partners in other warps through shared memory
-            unsigned long long key = s_list[tid];
+            unsigned long long key = LST[tid];
             for (int k = 2; k <= n2; k <<= 1)
                 for (int j = k >> 1; j > 0; j >>= 1) {
                     unsigned long long other;
                     if (j >= 32) {
-                        s_list[tid] = key;
+                        LST[tid] = key;
                         __syncthreads();
-                        other = s_list[tid ^ j];
+                        other = LST[tid ^ j];
                         __syncthreads();
                     } else {
                         other = __shfl_xor_sync(0xffffffffu, key, j);
@@ -247,7 +373,7 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
                     const bool keep_max = ((tid & j) == 0) == ((tid & k) == 0);
                     key = keep_max ? (key > other ? key : other) : (key < other ? key : other);
                 }
-            s_list[tid] = key;
+            LST[tid] = key;
         } else
         for (int k = 2; k <= n2; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
@@ -256,8 +382,8 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
                     for (int i = tid; i < n2; i += kSelThreads) {
                         const int l = i ^ j;
                         if (l > i) {
-                            const unsigned long long a = s_list[i], b = s_list[l];
-                            if (((i & k) == 0) ? (a < b) : (a > b)) { s_list[i] = b; s_list[l] = a; }
+                            const unsigned long long a = LST[i], b = LST[l];
+                            if (((i & k) == 0) ? (a < b) : (a > b)) { LST[i] = b; LST[l] = a; }
                         }
                     }
                     __syncthreads();
@@ -265,8 +391,8 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
                     for (int t = lane; t < seg; t += 32) {
                         const int i = sbase + t, l = i ^ j;
                         if (l > i) {
-                            const unsigned long long a = s_list[i], b = s_list[l];
-                            if (((i & k) == 0) ? (a < b) : (a > b)) { s_list[i] = b; s_list[l] = a; }
+                            const unsigned long long a = LST[i], b = LST[l];
+                            if (((i & k) == 0) ? (a < b) : (a > b)) { LST[i] = b; LST[l] = a; }
                         }
                     }
                     __syncwarp();
@@ -281,8 +407,8 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
             // none of its close predecessors was accepted.
             // Coordinates are integers: distances are exact in int32 and d2 < min_dist^2 <=> d2 < ceil(min_dist^2).
             const int md2i = (int)fminf(ceilf(md2), 2.0e9f);
-            for (int base = 0; base < nc && n_out < max_per_target; base += 32) {
-                const unsigned long long key = (base + lane < nc) ? s_list[base + lane] : 0ull;
+            for (int base = 0; base < m && n_out < max_per_target; base += 32) {
+                const unsigned long long key = (base + lane < m) ? LST[base + lane] : 0ull;
                 const unsigned idx = (unsigned)key;
                 const int xi = (int)(idx % (unsigned)w), yi = (int)(idx / (unsigned)w);
                 const unsigned xy = (unsigned)xi | ((unsigned)yi << 16);
@@ -332,6 +458,9 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
         }
         __syncthreads();
         n_out = s_nout;
+        if (attempt == 0 && n_out < max_per_target && m < nc) continue;      // prefix exhausted short of the quota: whole list
+        break;
+        }
     } else {
         // ---- 3b. any size: max_per_target rounds of block-wide arg-max over the candidate list in global memory,
         //          killing the candidates within min_dist of the last accepted corner on the way ----

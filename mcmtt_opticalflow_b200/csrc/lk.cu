@@ -425,7 +425,9 @@ lk_generic_kernel(const __grid_constant__ LkParams P, int max_win_px)
         return;
     }
     solve_generic(P, g.plane_from, g.plane_to, g.win_w, g.win_h, g.max_level, p0.x, p0.y, Iw, dIw, tid, red, f);
-    if (P.do_fb) solve_generic(P, g.plane_to, g.plane_from, g.win_w, g.win_h, g.max_level, f.x, f.y, Iw, dIw, tid, red, b);
+    // (a point the forward pass lost keeps status 0 whatever the way back says: no backward pass, fb_err = 0)
+    if (P.do_fb && f.st) solve_generic(P, g.plane_to, g.plane_from, g.win_w, g.win_h, g.max_level, f.x, f.y, Iw, dIw, tid, red, b);
+    else { b.x = p0.x; b.y = p0.y; }
     finish_point(P, job, k, p0, f, b, tid);
 }
 
@@ -842,8 +844,12 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
             continue;
         }
         const int first = bwd_only ? 1 : 0, last = (P.do_fb && !fwd_only) ? 2 : 1;
+        b.x = p0.x; b.y = p0.y;                  // without a backward pass fb_err = 0
 #pragma unroll 1
         for (int pass = first; pass < last; ++pass) {
+            // a point the forward pass lost keeps status 0 whatever the way back says: the backward pass is not run for it
+            // (7 % of the seeds of the c2 rig, 20 % at c3) and fb_err is defined as 0 (oracle: psnwo_fb_check)
+            if (pass && !f.st) break;
             const float sx = pass ? f.x : p0.x, sy = pass ? f.y : p0.y;
             unsigned n_tmpl = 0, n_iter = 0;
             solve_w21<kStats>(P, pass ? g.plane_to : g.plane_from, pass ? g.plane_from : g.plane_to, g.max_level, sx, sy, ip, jp, dxp, S, R, pass == 0, cur, n_tmpl, n_iter);

@@ -58,7 +58,7 @@ EXPORTS = [
     "psnw_box_update", "psnw_sync", "psnw_last_error", "psnw_get_stream", "psnw_level_info", "psnw_read_level",
     "psnw_read_level_apron", "psnw_klt_track_update", "psnw_get_params",
     "psnw_read_min_eig", "psnw_launch_count", "psnw_push_frame_bytes", "psnw_rebuild_pyramids", "psnw_levels_built",
-    "psnw_rebuild_pyramids_slot", "psnw_lk_stats",
+    "psnw_rebuild_pyramids_slot", "psnw_lk_stats", "psnw_klt_backward_chain", "psnw_flow_majority",
 ]
 
 _lib = None
@@ -94,6 +94,10 @@ def load():
         lib.psnw_rebuild_pyramids.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.psnw_rebuild_pyramids_slot.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         lib.psnw_lk_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.psnw_klt_backward_chain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.psnw_flow_majority.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_double, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_klt_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                         C.c_float, C.c_void_p, C.c_void_p, C.c_int]
         lib.psnw_klt_detect_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
@@ -357,6 +361,33 @@ class KLTContext:
         counts = np.zeros((max(nd, 1), max(nt, 1)), np.int32)
         self._ck(self.lib.psnw_points_in_boxes(self._h, _ptr(pts), _ptr(off), nt, _ptr(boxes), nd, _ptr(counts), MEM_HOST))
         return counts[:nd, :nt]
+
+    def backward_chain(self, pts, counts, boxes, win_wh=None, n_steps=3, min_inliers=4, cam=0):
+        """pts [n_targets, cap, 2] padded per target -> (boxes_steps [n_steps, n, 4], steps_done [n], pts_steps [n_steps, n, cap, 2],
+        counts_steps [n_steps, n], first_inlier_mask [n, cap])."""
+        pts = np.ascontiguousarray(pts, np.float32)
+        n, cap = pts.shape[0], pts.shape[1]
+        counts = np.ascontiguousarray(counts, np.int32)
+        boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
+        win = None if win_wh is None else np.ascontiguousarray(win_wh, np.int32).reshape(-1, 2)
+        bs, sd = np.zeros((n_steps, n, 4), np.float64), np.zeros(n, np.int32)
+        ps, cs = np.zeros((n_steps, n, cap, 2), np.float32), np.zeros((n_steps, n), np.int32)
+        fm = np.zeros((n, cap), np.uint8)
+        self._ck(self.lib.psnw_klt_backward_chain(self._h, cam, n_steps, _ptr(pts), _ptr(counts), n, cap, _ptr(win), _ptr(boxes), min_inliers,
+                                                  _ptr(bs), _ptr(sd), _ptr(ps), _ptr(cs), _ptr(fm), MEM_HOST))
+        return bs, sd, ps, cs, fm
+
+    def flow_majority(self, pts, tracker_offsets, tracker_boxes, tracker_ok, det_boxes, ratio=0.5):
+        """-> (counts int32 [n_detections, n_trackers], wipe uint8 [n_detections])."""
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        off = np.ascontiguousarray(tracker_offsets, np.int32)
+        tb = np.ascontiguousarray(tracker_boxes, np.float64).reshape(-1, 4)
+        ok = np.ascontiguousarray(tracker_ok, np.uint8)
+        db = np.ascontiguousarray(det_boxes, np.float64).reshape(-1, 4)
+        nt, nd = len(off) - 1, len(db)
+        counts, wipe = np.zeros((max(nd, 1), max(nt, 1)), np.int32), np.zeros(max(nd, 1), np.uint8)
+        self._ck(self.lib.psnw_flow_majority(self._h, _ptr(pts), _ptr(off), nt, _ptr(tb), _ptr(ok), _ptr(db), nd, ratio, _ptr(counts), _ptr(wipe), MEM_HOST))
+        return counts[:nd, :nt], wipe[:nd]
 
     def box_update_raw(self, boxes_in, n_targets, pre, cur, status, offsets, boxes_out, mask, counts, mem):
         self._ck(self.lib.psnw_box_update(self._h, _ptr(boxes_in), n_targets, _ptr(pre), _ptr(cur), _ptr(status),

@@ -30,6 +30,7 @@ def track_fb(img_a, img_b, pts, win=(21, 21), max_level=3, max_iters=30, epsilon
     p2, st_b, _ = lk(img_b, img_a, p1, win, max_level, max_iters, epsilon, min_eig_thresh)
     d = pts - p2
     fb = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32)
+    fb[st_f == 0] = 0.0          # points the forward pass lost: no backward pass, fb_err defined as 0 (oracle/klt_oracle.c::psnwo_fb_check)
     ok = (st_f != 0) & (st_b != 0)
     if fb_thresh >= 0:
         ok &= fb <= np.float32(fb_thresh)

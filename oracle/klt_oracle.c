@@ -301,9 +301,61 @@ PSNWO_API void psnwo_fb_check(const float *p, const float *p2, const uint8_t *st
     for (int i = 0; i < n; i++) {
         float dx = p[2 * i] - p2[2 * i], dy = p[2 * i + 1] - p2[2 * i + 1];
         float e = sqrtf(dx * dx + dy * dy);
+        /* a point the forward pass lost has status 0 whatever the backward pass says: the backward pass is not run for it
+           and fb_err is defined as 0 (north_star defines the check; the reference has none) */
+        if (!st_f[i]) e = 0.f;
         fb_err[i] = e;
         status[i] = (uint8_t)(st_f[i] && st_b[i] && (thr < 0.f || e <= thr));
     }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* f-3  optical-flow majority check  (reference code, psn_where/PSNWhere_Tracker2D.cpp:931-944, :981-1022) */
+/* Literal restatement on the feature lists: featuresInDetectionBox[d] receives tracker index t once per   */
+/* tracked point of t inside detection box d, for the trackers that reach the comparison (ok[t]: >= 4       */
+/* status-ok pairs, :889) and whose new box overlaps the detection box (:937); then the run-length walk.    */
+/* counts[d][t] (may be NULL) = entries of t in the list of d; wipe[d] = 1 where :1018-1021 resets the row. */
+/* ------------------------------------------------------------------------------------------------ */
+static int rect_overlap(const double *a, const double *b)                           /* PSN_Rect::overlap, PSNWhere_Types.h:160-163 */
+{
+    double ax1 = a[0] + a[2], bx1 = b[0] + b[2], ay1 = a[1] + a[3], by1 = b[1] + b[3];
+    double mx = ax1 > bx1 ? ax1 : bx1, nx = a[0] < b[0] ? a[0] : b[0];
+    double my = ay1 > by1 ? ay1 : by1, ny = a[1] < b[1] ? a[1] : b[1];
+    return (mx - nx < a[2] + b[2]) && (my - ny < a[3] + b[3]);
+}
+
+PSNWO_API void psnwo_flow_majority(const float *pts, const int *offsets, int n_trk, const double *trk_boxes, const uint8_t *ok,
+                                   const double *det_boxes, int n_det, double ratio, int *counts, uint8_t *wipe)
+{
+    int total_pts = offsets[n_trk];
+    int *list = (int *)malloc(sizeof(int) * (size_t)(total_pts > 0 ? total_pts : 1));
+    for (int d = 0; d < n_det; d++) {
+        const double *db = det_boxes + 4 * d;
+        int n = 0;
+        for (int t = 0; t < n_trk; t++) {                                           /* tracker loop :860, detection loop :934 */
+            int c = 0;
+            if (ok[t] && rect_overlap(trk_boxes + 4 * t, db)) {                     /* :889, :937 */
+                for (int i = offsets[t]; i < offsets[t + 1]; i++) {                 /* :940-944, PSN_Rect::contain(cv::Point2f) */
+                    double x = (double)pts[2 * i], y = (double)pts[2 * i + 1];
+                    if (x >= db[0] && x < db[0] + db[2] && y >= db[1] && y < db[1] + db[3]) { list[n++] = t; c++; }
+                }
+            }
+            if (counts) counts[(size_t)d * n_trk + t] = c;
+        }
+        wipe[d] = 0;
+        if (n == 0) continue;                                                       /* :985 */
+        int numMajor = 0, numCur = 0, curIdx = list[0];                             /* :987-990 */
+        for (int f = 0; f < n; f++) {                                               /* :991-1006 */
+            if (curIdx == list[f]) { numCur++; continue; }
+            if (numCur > numMajor) numMajor = numCur;
+            curIdx = list[f];
+            numCur = 0;
+        }
+        if (list[0] == curIdx) numMajor = numCur;                                   /* :1009-1012 sole tracker */
+        if ((double)numMajor > (double)n * ratio) continue;                         /* :1014-1015 */
+        wipe[d] = 1;                                                                /* :1017-1020 */
+    }
+    free(list);
 }
 
 /* ------------------------------------------------------------------------------------------------ */

@@ -137,6 +137,19 @@ def local_search_klt(box, pre, cur, valid=None):
     return out, idx[:k].copy()
 
 
+def flow_majority(pts, tracker_offsets, tracker_boxes, tracker_ok, det_boxes, ratio=0.5):
+    """Optical-flow majority check (Tracker2D.cpp:931-944, :981-1022) -> (counts int32 [n_det, n_trk], wipe uint8 [n_det])."""
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    off = np.ascontiguousarray(tracker_offsets, np.int32)
+    tb = np.ascontiguousarray(tracker_boxes, np.float64).reshape(-1, 4)
+    ok = np.ascontiguousarray(tracker_ok, np.uint8)
+    db = np.ascontiguousarray(det_boxes, np.float64).reshape(-1, 4)
+    nt, nd = len(off) - 1, len(db)
+    counts, wipe = np.zeros((max(nd, 1), max(nt, 1)), np.int32), np.zeros(max(nd, 1), np.uint8)
+    lib().psnwo_flow_majority(_p(pts), _p(off), C.c_int(nt), _p(tb), _p(ok), _p(db), C.c_int(nd), C.c_double(ratio), _p(counts), _p(wipe))
+    return counts[:nd, :nt], wipe[:nd]
+
+
 def min_eig_map(img):
     img = np.ascontiguousarray(img, np.uint8)
     h, w = img.shape

@@ -84,3 +84,22 @@ def test_gftt_tie_order(oracle):
         img[y:y + 6, x:x + 6] = 200
     c = cv2_ref.gftt(img, [0, 0, 200, 200], 50, 0.01, 3.0)
     assert np.array_equal(oracle.detect(img, [0, 0, 200, 200], 50, 0.01, 3.0), c)
+
+
+def test_flow_majority_rule_hand_cases(oracle):
+    """The run-length rule of Tracker2D.cpp:991-1013 on lists small enough to walk by hand."""
+    det = np.array([[0.0, 0.0, 100.0, 100.0]])
+    box = np.array([[10.0, 10.0, 20.0, 20.0]])
+
+    def run(sizes, ok=None):
+        n = len(sizes)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        pts = np.full((off[-1], 2), 50.0, np.float32)                 # every point inside the detection box
+        return oracle.flow_majority(pts, off, np.repeat(box, n, 0), np.ones(n, np.uint8) if ok is None else ok, det, 0.5)
+
+    c, w = run([7]);            assert c.tolist() == [[7]] and w.tolist() == [0]            # sole tracker: 7 > 3.5
+    c, w = run([6, 4]);         assert w.tolist() == [0]                                     # first run 6 > 5
+    c, w = run([5, 5]);         assert w.tolist() == [1]                                     # 5 > 5 fails: the row is wiped
+    c, w = run([2, 9]);         assert w.tolist() == [1]                                     # the last run is never compared: 2 > 5.5 fails
+    c, w = run([2, 9, 1]);      assert w.tolist() == [0]                                     # a middle run counts 9 - 1 = 8 > 6
+    c, w = run([3, 0, 5], ok=np.array([1, 1, 0], np.uint8)); assert c.tolist() == [[3, 0, 0]] and w.tolist() == [0]   # gated tracker: sole run
