@@ -305,6 +305,8 @@ int effective_max_level(const psnw_ctx *c, int win_w, int win_h)
     return level;
 }
 
+inline bool do_fb_early(const psnw_ctx *c) { return c->p.fb_thresh >= 0.f; }
+
 cudaMemcpyKind h2d(int mem_flags) { return mem_flags == PSNW_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice; }
 
 // region variant of the fused kernel for a launch over n planes of level `base`: the tallest region that still gives every
@@ -866,6 +868,21 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
     std::vector<TrackJob> dj(n_jobs);
     std::vector<TrackGroup> dg(total_groups);
     ctx->arena_off = 0;
+    // host / pinned arrays are staged in the arena BY ARRAY TYPE, the jobs' points back to back inside each: jobs whose host
+    // arrays are slices of one array (a rig's cameras) then travel as one copy per array instead of one per job and array
+    float2 *a_pts = nullptr, *a_out = nullptr;
+    int *a_tgt = nullptr;
+    uint8_t *a_st = nullptr;
+    float *a_err = nullptr, *a_fb = nullptr;
+    if (!dev) {
+        bool any_tgt = false, any_fb = false;
+        for (int j = 0; j < n_jobs; ++j) { any_tgt = any_tgt || jobs[j].target_of_pt; any_fb = any_fb || (do_fb_early(ctx) && jobs[j].fb_err); }
+        a_pts = take<float2>(ctx, total); a_out = take<float2>(ctx, total);
+        a_tgt = any_tgt ? take<int>(ctx, total) : nullptr;
+        a_st = take<uint8_t>(ctx, total); a_err = take<float>(ctx, total);
+        a_fb = any_fb ? take<float>(ctx, total) : nullptr;
+        if (ctx->arena_off > ctx->arena.cap) return fail(ctx, PSNW_ENOMEM, "psnw_klt_track: scratch arena exhausted");
+    }
     bool all21 = true, any_skipped = false;
     int max_win_px = 1;
     int pt = 0, gb = 0;
@@ -893,20 +910,25 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
             D.pts = reinterpret_cast<const float2 *>(J.pts_xy); D.target_of_pt = J.target_of_pt;
             D.out = reinterpret_cast<float2 *>(J.out_xy); D.status = J.status; D.err = J.err; D.fb_err = do_fb ? J.fb_err : nullptr;
         } else {
-            float2 *d_pts = take<float2>(ctx, J.n_pts);
-            int *d_tgt = J.target_of_pt ? take<int>(ctx, J.n_pts) : nullptr;
-            D.pts = d_pts; D.target_of_pt = d_tgt;
-            D.out = take<float2>(ctx, J.n_pts); D.status = take<uint8_t>(ctx, J.n_pts); D.err = take<float>(ctx, J.n_pts);
-            D.fb_err = (do_fb && J.fb_err) ? take<float>(ctx, J.n_pts) : nullptr;
-            if (ctx->arena_off > ctx->arena.cap) return fail(ctx, PSNW_ENOMEM, "psnw_klt_track: scratch arena exhausted");
-            if (J.n_pts > 0 && !host) {
-                CK(cudaMemcpyAsync(d_pts, J.pts_xy, sizeof(float2) * J.n_pts, cudaMemcpyHostToDevice, ctx->stream));
-                if (d_tgt) CK(cudaMemcpyAsync(d_tgt, J.target_of_pt, sizeof(int) * J.n_pts, cudaMemcpyHostToDevice, ctx->stream));
-            }
+            D.pts = a_pts + pt; D.target_of_pt = J.target_of_pt ? a_tgt + pt : nullptr;
+            D.out = a_out + pt; D.status = a_st + pt; D.err = a_err + pt;
+            D.fb_err = (do_fb && J.fb_err) ? a_fb + pt : nullptr;
         }
         pt += J.n_pts; gb += J.n_targets;
     }
 
+    if (!dev && !host) {                      // pinned (or oversize pageable) arrays: one upload per run of adjacent host slices
+        for (int j = 0; j < n_jobs;) {
+            int e = j + 1;
+            size_t npts = (size_t)jobs[j].n_pts;
+            while (e < n_jobs && jobs[e].pts_xy == jobs[j].pts_xy + 2 * npts) npts += (size_t)jobs[e++].n_pts;
+            if (npts) CK(cudaMemcpyAsync(const_cast<float2 *>(dj[j].pts), jobs[j].pts_xy, sizeof(float2) * npts, cudaMemcpyHostToDevice, ctx->stream));
+            j = e;
+        }
+        for (int j = 0; j < n_jobs; ++j)
+            if (jobs[j].target_of_pt && jobs[j].n_pts > 0)
+                CK(cudaMemcpyAsync(const_cast<int *>(dj[j].target_of_pt), jobs[j].target_of_pt, sizeof(int) * jobs[j].n_pts, cudaMemcpyHostToDevice, ctx->stream));
+    }
     StageSlot *blob = nullptr;                // PSNW_MEM_HOST: all inputs up as one pinned blob (see mirror())
     if (host) {
         int rcb = stage_acquire(ctx, ctx->arena_off, &blob);
@@ -986,14 +1008,22 @@ int psnw_klt_track_batch(psnw_ctx *ctx, const psnw_track_job *jobs, int n_jobs, 
         return PSNW_OK;
     }
     if (!dev) {
-        for (int j = 0; j < n_jobs; ++j) {
+        // downloads: one copy per array and run of jobs whose host arrays are adjacent slices
+        for (int j = 0; j < n_jobs;) {
             const psnw_track_job &J = jobs[j];
-            const TrackJob &D = dj[j];
-            if (J.n_pts == 0) continue;
-            CK(cudaMemcpyAsync(J.out_xy, D.out, sizeof(float2) * J.n_pts, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(J.status, D.status, J.n_pts, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(J.err, D.err, sizeof(float) * J.n_pts, cudaMemcpyDeviceToHost, ctx->stream));
-            if (D.fb_err) CK(cudaMemcpyAsync(J.fb_err, D.fb_err, sizeof(float) * J.n_pts, cudaMemcpyDeviceToHost, ctx->stream));
+            int e = j + 1;
+            size_t npts = (size_t)J.n_pts;
+            while (e < n_jobs && jobs[e].out_xy == J.out_xy + 2 * npts && jobs[e].status == J.status + npts && jobs[e].err == J.err + npts &&
+                   ((dj[j].fb_err != nullptr) == (dj[e].fb_err != nullptr)) && (!dj[j].fb_err || jobs[e].fb_err == J.fb_err + npts))
+                npts += (size_t)jobs[e++].n_pts;
+            if (npts) {
+                const TrackJob &D = dj[j];
+                CK(cudaMemcpyAsync(J.out_xy, D.out, sizeof(float2) * npts, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(J.status, D.status, npts, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaMemcpyAsync(J.err, D.err, sizeof(float) * npts, cudaMemcpyDeviceToHost, ctx->stream));
+                if (D.fb_err) CK(cudaMemcpyAsync(J.fb_err, D.fb_err, sizeof(float) * npts, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            j = e;
         }
         if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -1192,13 +1222,18 @@ int psnw_klt_detect_batch(psnw_ctx *ctx, const psnw_detect_job *jobs, int n_jobs
     }
     if (!dev) {
         t0 = 0;
-        for (int j = 0; j < n_jobs; ++j) {
+        for (int j = 0; j < n_jobs;) {                 // one copy per array and run of jobs whose host arrays are adjacent slices
             const psnw_detect_job &J = jobs[j];
-            if (J.n_targets == 0) continue;
-            CK(cudaMemcpyAsync(J.pts_xy, s_out + (size_t)t0 * max_per_target, (size_t)J.n_targets * max_per_target * sizeof(float2),
-                               cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(J.counts, s_cnt + t0, sizeof(int) * J.n_targets, cudaMemcpyDeviceToHost, st));
-            t0 += J.n_targets;
+            int e = j + 1;
+            size_t nt = (size_t)std::max(J.n_targets, 0);
+            while (e < n_jobs && (jobs[e].n_targets == 0 || (nt > 0 && jobs[e].pts_xy == J.pts_xy + 2 * nt * max_per_target && jobs[e].counts == J.counts + nt)))
+                nt += (size_t)std::max(jobs[e++].n_targets, 0);
+            if (nt) {
+                CK(cudaMemcpyAsync(J.pts_xy, s_out + (size_t)t0 * max_per_target, nt * max_per_target * sizeof(float2), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(J.counts, s_cnt + t0, sizeof(int) * nt, cudaMemcpyDeviceToHost, st));
+            }
+            t0 += (int)nt;
+            j = e;
         }
         if (mem_flags == PSNW_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
     }
