@@ -49,6 +49,101 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
+// ---- REFLECT_101 apron of a level >= 1 (common.cuh), scattered from the pixels a CTA holds in shared memory --------------
+// What copyMakeBorder builds around every pyramid level inside cv::calcOpticalFlowPyrLK, written once per pushed frame so that
+// the LK kernel stages coarse-level patches without border arithmetic.  Every CTA of a pyramid kernel owns a region of the
+// level (its tile) and holds it -- plus a few halo columns -- in shared memory; it writes the mirror images of ITS OWN pixels
+// that lie within `apron` pixels of a frame edge: no extra launch, no extra CTAs, no dependency between CTAs.
+// A CTA handles every apron word (4 aligned pixels) that mirrors at least one pixel of its region.  If all four sources lie in
+// the part of its buffer that holds true pixels (region + hv columns) the word is stored whole; otherwise only the bytes whose
+// sources it owns (the neighbouring CTA stores the others).  Words stored by two CTAs carry identical values.
+//   x classes: 0 identity columns (only with mirrored rows), 1 mirrored about x = 0, 2 mirrored about x = W-1; y alike.
+// The destination rectangles of the 8 classes (words x rows) are tabulated once per CTA by a single thread while the tile is
+// still in flight: {first item, words per row, first word, first row}.
+struct ApronWork {
+    int4 cls[8];
+    int total;
+};
+
+__device__ __forceinline__ int reflect101c(int p, int n)
+{
+    p = p < 0 ? -p : p;
+    p = p >= n ? 2 * (n - 1) - p : p;
+    return min(max(p, 0), n - 1);
+}
+
+// region [ox, ox + own_w) x [oy, oy + own_h) of a W x H level with an apron of A pixels
+__device__ __forceinline__ void apron_work_fill(ApronWork &T, int W, int H, int A, int ox, int oy, int own_w, int own_h)
+{
+    const int Ax = min(A, W - 1), Ay = min(A, H - 1);
+    const int ox1 = min(ox + own_w, W), oy1 = min(oy + own_h, H);                   // region clipped to the frame
+    int wlo[3], nw[3], rlo[3], nr[3];
+    wlo[0] = ox >> 2; nw[0] = ((ox1 - 1) >> 2) - wlo[0] + 1;
+    { const int a = max(ox, 1), b = min(ox1 - 1, Ax); wlo[1] = (-b) >> 2; nw[1] = a <= b ? ((-a) >> 2) - wlo[1] + 1 : 0; }
+    { const int a = max(ox, W - 1 - Ax), b = min(ox1 - 1, W - 2); wlo[2] = (2 * (W - 1) - b) >> 2; nw[2] = a <= b ? ((2 * (W - 1) - a) >> 2) - wlo[2] + 1 : 0; }
+    rlo[0] = oy; nr[0] = oy1 - oy;
+    { const int a = max(oy, 1), b = min(oy1 - 1, Ay); rlo[1] = -b; nr[1] = a <= b ? b - a + 1 : 0; }
+    { const int a = max(oy, H - 1 - Ay), b = min(oy1 - 1, H - 2); rlo[2] = 2 * (H - 1) - b; nr[2] = a <= b ? b - a + 1 : 0; }
+    const bool none = A <= 0 || ox >= ox1 || oy >= oy1;
+    int begin = 0;
+#pragma unroll
+    for (int c = 1; c < 9; ++c) {
+        const int xc = c % 3, yc = c / 3;
+        const int n = none ? 0 : max(nw[xc], 0) * max(nr[yc], 0);
+        T.cls[c - 1] = make_int4(begin, max(nw[xc], 1), wlo[xc], rlo[yc]);
+        begin += n;
+    }
+    T.total = begin;
+}
+
+// buf: the CTA's shared-memory buffer of the level, row pitch `pitch` bytes, holding pixel (bx, by) at its first byte; hv =
+// columns beside the region that hold true pixels (where they are inside the frame); plane0 = pixel (0,0) of the plane in HBM.
+// Threads tid, tid + nt, ... of the CTA share the work list.
+__device__ __forceinline__ void apron_scatter(const ApronWork &T, const uint8_t *buf, int pitch, int bx, int by, int ox, int own_w, int hv,
+                                              int W, int H, int A, uint8_t *plane0, int ipitch, int tid, int nt)
+{
+    const int total = T.total;
+    if (tid >= total) return;
+    const int Ax = min(A, W - 1);
+    const int ox1 = min(ox + own_w, W);
+    const int vx0 = max(ox - hv, 0), vx1 = min(ox + own_w + hv, W);
+#pragma unroll 1
+    for (int it = tid; it < total; it += nt) {
+        int e = 0;
+#pragma unroll
+        for (int c = 1; c < 8; ++c) e += it >= T.cls[c].x ? 1 : 0;                   // (first items ascend; empty classes repeat them)
+        const int4 C = T.cls[e];
+        const int xc = (e + 1) % 3, yc = (e + 1) / 3;
+        const int q = it - C.x, r = q / C.y, tx = 4 * (C.z + (q - r * C.y)), ty = C.w + r;
+        const int sy = reflect101c(ty, H);
+        const uint8_t *srow = buf + (sy - by) * pitch - bx;
+        uint8_t *drow = plane0 + (ptrdiff_t)ty * ipitch;
+        if (xc == 0 && tx + 4 <= W) {                     // identity columns, mirrored row: one aligned word
+            *reinterpret_cast<uint32_t *>(drow + tx) = *reinterpret_cast<const uint32_t *>(srow + tx);
+            continue;
+        }
+        uint32_t v = 0;
+        bool all = true, any = false, own[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int px = tx + k;
+            const bool okd = px >= -Ax && px < W + Ax && (yc != 0 || px < 0 || px >= W);
+            const int sx = reflect101c(px, W);
+            own[k] = okd && sx >= ox && sx < ox1;
+            all = all && okd && sx >= vx0 && sx < vx1;
+            any = any || own[k];
+            v |= (uint32_t)srow[min(max(sx, vx0), vx1 - 1)] << (8 * k);
+        }
+        if (all && any) {
+            *reinterpret_cast<uint32_t *>(drow + tx) = v;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (own[k]) drow[tx + k] = (uint8_t)(v >> (8 * k));
+        }
+    }
+}
+
 // dp4a coefficient words (byte 0 = lowest address)
 constexpr int kDiffLo = 0x000100FF;     // (-1, 0, 1, 0)
 constexpr int kDiffHi = 0x0100FF00;     // ( 0,-1, 0, 1)

@@ -76,13 +76,6 @@ __device__ unsigned long long g_timeline[8 * 65536];
 #define PSNW_STAMP(slot) do { } while (0)
 #endif
 
-__device__ __forceinline__ int reflect101c(int p, int n)
-{
-    p = p < 0 ? -p : p;
-    p = p >= n ? 2 * (n - 1) - p : p;
-    return min(max(p, 0), n - 1);
-}
-
 // REFLECT_101 at the border of a level held in shared memory: x = -1 (and -2 when `two`), x = W (and W+1), same rows.
 // Columns first, then whole rows, so that the corners come out right.  Ends with a barrier when it wrote anything.
 template <int NT>
@@ -266,99 +259,28 @@ __device__ __forceinline__ void copy_dispatch(const uint8_t *smem, const FusedLe
     }
 }
 
-// REFLECT_101 apron of level K >= 1, scattered from the CTA's own pixels: a CTA handles every apron word (4 aligned
-// pixels) that mirrors at least one pixel of its own region.  If all four sources lie in the part of its buffer that
-// holds true pixels (own region + hv columns) the word is stored whole; otherwise only the bytes whose sources it owns
-// (the neighbouring CTA stores the others).  Words stored by two CTAs carry identical values.
-//   x classes: 0 identity columns (only with mirrored rows), 1 mirrored about x = 0, 2 mirrored about x = W-1; y alike.
-// The destination rectangles of the 8 classes (words x rows) are tabulated once per CTA and level by a single thread
-// while the level-0 box is still in flight: {first item, words per row, first word, first row}.
+// REFLECT_101 apron of the levels that carry one, scattered from the CTA's own pixels (pyr_common.cuh)
 struct ApronTable {
-    int4 cls[4][8];
-    int total[4];
+    ApronWork lv[4];
 };
 
 template <int NL, int TH>
 __device__ __forceinline__ void apron_table(ApronTable &T, const FusedLevels &L, int K)
 {
-    using G = FG<NL, TH>;
     const LevelGeom &lv = L.lv[K];
-    const int W = lv.w, H = lv.h, A = lv.apron;
     const int own_w = kTopW << (NL - 1 - K), own_h = TH << (NL - 1 - K);
-    const int Ax = min(A, W - 1), Ay = min(A, H - 1);
-    const int ox = (int)blockIdx.x * own_w, oy = (int)blockIdx.y * own_h;
-    const int ox1 = min(ox + own_w, W), oy1 = min(oy + own_h, H);                   // own region clipped to the frame
-    int wlo[3], nw[3], rlo[3], nr[3];
-    wlo[0] = ox >> 2; nw[0] = ((ox1 - 1) >> 2) - wlo[0] + 1;
-    { const int a = max(ox, 1), b = min(ox1 - 1, Ax); wlo[1] = (-b) >> 2; nw[1] = a <= b ? ((-a) >> 2) - wlo[1] + 1 : 0; }
-    { const int a = max(ox, W - 1 - Ax), b = min(ox1 - 1, W - 2); wlo[2] = (2 * (W - 1) - b) >> 2; nw[2] = a <= b ? ((2 * (W - 1) - a) >> 2) - wlo[2] + 1 : 0; }
-    rlo[0] = oy; nr[0] = oy1 - oy;
-    { const int a = max(oy, 1), b = min(oy1 - 1, Ay); rlo[1] = -b; nr[1] = a <= b ? b - a + 1 : 0; }
-    { const int a = max(oy, H - 1 - Ay), b = min(oy1 - 1, H - 2); rlo[2] = 2 * (H - 1) - b; nr[2] = a <= b ? b - a + 1 : 0; }
-    const bool none = A <= 0 || ox >= ox1 || oy >= oy1;
-    int begin = 0;
-#pragma unroll
-    for (int c = 1; c < 9; ++c) {
-        const int xc = c % 3, yc = c / 3;
-        const int n = none ? 0 : max(nw[xc], 0) * max(nr[yc], 0);
-        T.cls[K][c - 1] = make_int4(begin, max(nw[xc], 1), wlo[xc], rlo[yc]);
-        begin += n;
-    }
-    T.total[K] = begin;
+    apron_work_fill(T.lv[K], lv.w, lv.h, lv.apron, (int)blockIdx.x * own_w, (int)blockIdx.y * own_h, own_w, own_h);
 }
 
 template <int NL, int TH, int K, int NT>
 __device__ __forceinline__ void apron_level(const uint8_t *smem, const ApronTable &T, const FusedLevels &L, int plane, int tid)
 {
     using G = FG<NL, TH>;
-    const int total = T.total[K];
-    if (tid >= total) return;
     const LevelGeom &lv = L.lv[K];
-    const int W = lv.w, H = lv.h;
-    const int Ax = min(lv.apron, W - 1);
     const int ox = (int)blockIdx.x * G::own_w(K), oy = (int)blockIdx.y * G::own_h(K);
-    const int ox1 = min(ox + G::own_w(K), W);
     constexpr int hv = G::need(K) >= 3 ? 3 : G::need(K);                          // columns beside the own region that hold true pixels
-    const int vx0 = max(ox - hv, 0), vx1 = min(ox + G::own_w(K) + hv, W);
-    const int bx = ox - G::left(K), by = oy - G::need(K);
-    const uint8_t *buf = smem + G::offset(K);
-    constexpr int pitch = G::pitch(K);
-    uint8_t *plane0 = lv.img + (size_t)plane * lv.iplane_px;
-#pragma unroll 1
-    for (int it = tid; it < total; it += NT) {
-        int e = 0;
-#pragma unroll
-        for (int c = 1; c < 8; ++c) e += it >= T.cls[K][c].x ? 1 : 0;          // (first items ascend; empty classes repeat them)
-        const int4 C = T.cls[K][e];
-        const int xc = (e + 1) % 3, yc = (e + 1) / 3;
-        const int q = it - C.x, r = q / C.y, tx = 4 * (C.z + (q - r * C.y)), ty = C.w + r;
-        const int sy = reflect101c(ty, H);
-        const uint8_t *srow = buf + (sy - by) * pitch - bx;
-        uint8_t *drow = plane0 + (ptrdiff_t)ty * lv.ipitch;
-        if (xc == 0 && tx + 4 <= W) {                     // identity columns, mirrored row: one aligned word
-            *reinterpret_cast<uint32_t *>(drow + tx) = *reinterpret_cast<const uint32_t *>(srow + tx);
-            continue;
-        }
-        uint32_t v = 0;
-        bool all = true, any = false, own[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int px = tx + k;
-            const bool okd = px >= -Ax && px < W + Ax && (yc != 0 || px < 0 || px >= W);
-            const int sx = reflect101c(px, W);
-            own[k] = okd && sx >= ox && sx < ox1;
-            all = all && okd && sx >= vx0 && sx < vx1;
-            any = any || own[k];
-            v |= (uint32_t)srow[min(max(sx, vx0), vx1 - 1)] << (8 * k);
-        }
-        if (all && any) {
-            *reinterpret_cast<uint32_t *>(drow + tx) = v;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (own[k]) drow[tx + k] = (uint8_t)(v >> (8 * k));
-        }
-    }
+    apron_scatter(T.lv[K], smem + G::offset(K), G::pitch(K), ox - G::left(K), oy - G::need(K), ox, G::own_w(K), hv, lv.w, lv.h, lv.apron,
+                  lv.img + (size_t)plane * lv.iplane_px, lv.ipitch, tid, NT);
 }
 
 template <int NL, int TH, int K, int NT>
