@@ -59,7 +59,19 @@ struct psnw_ctx {
     int fused_levels = 0;                 // 3 or 4 when the fused kernel is usable, else 0
     size_t fused_max_px = 2200000;   // auto mode: fused kernel up to this many level-0 pixels per launch
     size_t hybrid_max_frame_px = 600000;   // auto mode: larger launches of frames up to this size take the hybrid builder
-    int pyr_mode = 0;                     // 0 auto, 1 per-level kernels only, 2 fused from level 0, 3 hybrid (PSNW_PYR_MODE, bring-up)
+    int pyr_mode = 0;                     // 0 auto, 1 per-level kernels only, 2 fused from level 0, 3 hybrid, 4 level walker (PSNW_PYR_MODE, bring-up)
+    static constexpr int kWalkBlocks = 8; // control blocks of the level walker, used in turn (each launch leaves its block zeroed)
+    unsigned *walk_ctl = nullptr;
+    size_t walk_ctl_stride = 0;
+    unsigned walk_next = 0;
+    int walk_ctas = 0;                    // CTAs per SM of the walker (0: what fits; PSNW_WALK_CTAS, bring-up)
+    size_t walk_min_px = 2200000;         // auto mode: launches above this many level-0 pixels take the walker
+    // Consecutive fused builds of disjoint planes on one stream overlap (launch_pyr_fused late_wait): the count of this
+    // context's launches after the last such build, its stream, and the planes built since the last build that waited first
+    uint64_t pyr_chain_launches = ~(uint64_t)0;
+    cudaStream_t pyr_chain_stream = nullptr;
+    std::vector<uint8_t> pyr_chain_planes;
+    bool pyr_overlap = true;              // PSNW_PYR_OVERLAP=0 (bring-up): every build waits for its predecessors first
     int fused_variant = -1;               // -1 auto, else the region variant of the fused kernel (PSNW_FUSED_VARIANT, bring-up)
     int fused_wide = -1;                  // -1 auto, else threads per CTA of the fused kernel: 256 / 512 / 1024 (PSNW_FUSED_THREADS, bring-up)
     int sm_count = 148;
@@ -347,17 +359,33 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
         // (measured, tools/pyr_sweep.py: 4 x 768x576 fused 14.0 us / level 15.9; 64 x 768x576 hybrid 56 us / level 64 / fused
         // 62; 32 x 1080p level 93 us / hybrid 99; 16 x 4K level 163 us / hybrid 173)
         if (mode == 0) mode = (ctx->fused_levels && px <= ctx->fused_max_px) ? 2 : (ctx->hyb_levels && (size_t)l0.w * l0.h <= ctx->hybrid_max_frame_px) ? 3 : 1;
+        if (mode == 4) {
+            unsigned *ctl = ctx->walk_ctl + (ctx->walk_next++ % psnw_ctx::kWalkBlocks) * ctx->walk_ctl_stride;
+            const int r = launch_pyr_walk(ctx->pyr, ctx->maps, pl, ctl, ctx->walk_ctas, ctx->sm_count, st);
+            if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_walk_kernel launch", cudaGetLastError());
+            ctx->launches += r;
+            continue;
+        }
         if (mode == 2 && !ctx->fused_levels) mode = 1;
         if (mode == 3 && !ctx->hyb_levels) mode = ctx->fused_levels ? 2 : 1;
         int first = 0, last = ctx->pyr.levels;                       // levels [first, last) take the per-level kernel
         if (mode == 2) {
             int wide = 0;
             const int variant = fused_variant_for(ctx, 0, ctx->fused_levels, pl.n, &wide);
-            const int r = launch_pyr_fused(ctx->pyr, 0, ctx->fused_levels, variant, wide, &ctx->map_fused[variant], pl, st);
-            if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_fused_kernel launch", cudaGetLastError());
-            ctx->launches += r;
             // deeper pyramids: level 3 again (per-level kernel) only to feed level 4; it rewrites its apron with the same values
             first = ctx->fused_levels < ctx->pyr.levels ? ctx->fused_levels - 1 : ctx->pyr.levels;
+            // the build reads only the frames (complete: a copy or an earlier call put them there) and writes only the levels of
+            // its own planes: straight after a fused build of OTHER planes on the same stream it need not wait for it
+            const bool alone = first == ctx->pyr.levels;
+            bool late = alone && ctx->pyr_overlap && ctx->launches == ctx->pyr_chain_launches && st == ctx->pyr_chain_stream;
+            if (ctx->pyr_chain_planes.size() != (size_t)ctx->planes) ctx->pyr_chain_planes.assign(ctx->planes, 0);
+            for (int i = 0; late && i < pl.n; ++i) late = !ctx->pyr_chain_planes[pl.plane[i]];
+            if (!late) std::fill(ctx->pyr_chain_planes.begin(), ctx->pyr_chain_planes.end(), 0);
+            for (int i = 0; i < pl.n; ++i) ctx->pyr_chain_planes[pl.plane[i]] = 1;
+            const int r = launch_pyr_fused(ctx->pyr, 0, ctx->fused_levels, variant, wide, &ctx->map_fused[variant], pl, late ? 1 : 0, st);
+            if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_fused_kernel launch", cudaGetLastError());
+            ctx->launches += r;
+            if (alone) { ctx->pyr_chain_launches = ctx->launches; ctx->pyr_chain_stream = st; }
         } else if (mode == 3) {
             last = ctx->hyb_base;
         }
@@ -369,7 +397,7 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
         if (mode == 3) {
             int wide = 0;
             const int variant = fused_variant_for(ctx, ctx->hyb_base, ctx->hyb_levels, pl.n, &wide);
-            const int r = launch_pyr_fused(ctx->pyr, ctx->hyb_base, ctx->hyb_levels, variant, wide, &ctx->map_hyb[variant], pl, st);
+            const int r = launch_pyr_fused(ctx->pyr, ctx->hyb_base, ctx->hyb_levels, variant, wide, &ctx->map_hyb[variant], pl, 0, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_fused_kernel launch", cudaGetLastError());
             ctx->launches += r;
         }
@@ -576,12 +604,18 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     ctx->lk_ctas = lk_w21_resident_ctas(0);
     if (ctx->lk_ctas <= 0) return bail(PSNW_ECUDA);
     if (cudaMalloc(&ctx->lk_work, (2 + kLkTailMax) * sizeof(unsigned)) != cudaSuccess) return bail(PSNW_ENOMEM);
+    ctx->walk_ctl_stride = (walk_ctl_words(PSNW_MAX_LEVELS, kMaxPlanesPerLaunch) + 63) & ~(size_t)63;
+    if (cudaMalloc(&ctx->walk_ctl, psnw_ctx::kWalkBlocks * ctx->walk_ctl_stride * sizeof(unsigned)) != cudaSuccess) return bail(PSNW_ENOMEM);
+    cudaMemsetAsync(ctx->walk_ctl, 0, psnw_ctx::kWalkBlocks * ctx->walk_ctl_stride * sizeof(unsigned), ctx->stream);
     cudaMemsetAsync(ctx->lk_work, 0, (2 + kLkTailMax) * sizeof(unsigned), ctx->stream);
     ctx->lk_tail = 2 * ctx->lk_ctas * 4;  // two waves of warps
     if (const char *m = getenv("PSNW_LK_TAIL")) ctx->lk_tail = atoi(m);
     ctx->lk_tail = std::min(std::max(ctx->lk_tail, 0), kLkTailMax);
     if (const char *m = getenv("PSNW_LK_PERSISTENT")) ctx->lk_persistent = m[0] == '1';
-    if (const char *m = getenv("PSNW_PYR_MODE")) ctx->pyr_mode = !strcmp(m, "level") ? 1 : !strcmp(m, "fused") ? 2 : !strcmp(m, "hybrid") ? 3 : 0;
+    if (const char *m = getenv("PSNW_PYR_MODE")) ctx->pyr_mode = !strcmp(m, "level") ? 1 : !strcmp(m, "fused") ? 2 : !strcmp(m, "hybrid") ? 3 : !strcmp(m, "walk") ? 4 : 0;
+    if (const char *m = getenv("PSNW_PYR_OVERLAP")) ctx->pyr_overlap = atoi(m) != 0;
+    if (const char *m = getenv("PSNW_WALK_CTAS")) ctx->walk_ctas = atoi(m);
+    if (const char *m = getenv("PSNW_WALK_MIN_PX")) ctx->walk_min_px = (size_t)atoll(m);
     if (const char *m = getenv("PSNW_FUSED_THREADS")) ctx->fused_wide = atoi(m);
     if (const char *m = getenv("PSNW_FUSED_VARIANT")) ctx->fused_variant = std::min(std::max(atoi(m), 0), kFusedVariants - 1);
     if (const char *m = getenv("PSNW_FUSED_MAX_PX")) ctx->fused_max_px = (size_t)atoll(m);
@@ -669,6 +703,7 @@ int psnw_destroy(psnw_ctx *ctx)
     if (ctx->arena.p) cudaFree(ctx->arena.p);
     if (ctx->desc.p) cudaFree(ctx->desc.p);
     if (ctx->lk_work) cudaFree(ctx->lk_work);
+    if (ctx->walk_ctl) cudaFree(ctx->walk_ctl);
     if (ctx->lk_stats) cudaFree(ctx->lk_stats);
     if (ctx->lk_maps) cudaFree(ctx->lk_maps);
     if (ctx->cand.p) cudaFree(ctx->cand.p);

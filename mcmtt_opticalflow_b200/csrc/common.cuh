@@ -100,7 +100,14 @@ int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, c
 constexpr int kFusedVariants = 3;
 void fused_geometry(int nl, int variant, int *box_w, int *box_h, int *own_w, int *own_h);
 int configure_fused_kernels();
-int launch_pyr_fused(const PyrDesc &pyr, int base, int nl, int variant, int threads, const CUtensorMap *map0, const PlaneList &planes, cudaStream_t stream);
+// late_wait: the launch touches no data of the kernels before it in the stream (pyramid builds of other planes): it runs
+// beside them and only completes after them
+int launch_pyr_fused(const PyrDesc &pyr, int base, int nl, int variant, int threads, const CUtensorMap *map0, const PlaneList &planes, int late_wait,
+                     cudaStream_t stream);
+// level walker (pyramid.cu): every level and apron of the planes in one persistent launch; ctl = walk_ctl_words() zeroed words
+size_t walk_ctl_words(int levels, int n_planes);
+int launch_pyr_walk(const PyrDesc &pyr, const CUtensorMap *maps, const PlaneList &planes, unsigned *ctl, int ctas_per_sm, int sm_count,
+                    cudaStream_t stream);
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,
                     int luma_bits, cudaStream_t stream);
 int lk_w21_resident_ctas(int max_per_sm);   // CTAs of the persistent 21x21 kernel resident at once on the current device (capped per SM when > 0), or -1

@@ -14,6 +14,9 @@
 // u8 words (no byte unpacking), the vertical taps run on registers.  Stores are 16-byte (4 x short2) per
 // lane = 512 contiguous bytes per warp row for the derivative image and 2 bytes per lane for the next
 // u8 level.  HBM traffic per level-l pixel: 1 B read, 4 B + 0.25 B written.
+#include <algorithm>
+#include <cstring>
+
 #include "common.cuh"
 #include "pyr_common.cuh"
 
@@ -104,51 +107,11 @@ __device__ __forceinline__ void apron_region(const LevelGeom &L, int plane, int 
     }
 }
 
+// Fix-up + arithmetic of one 128x32 tile of level `cur` held (with its halo) in `tile`: Scharr derivatives of the tile and,
+// with kHasNext, the 64x16 tile of the next level.  Shared by the per-level kernel and the level walker below.
 template <bool kHasNext>
-__global__ void __launch_bounds__(128)
-pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, const LevelGeom nxt,
-                  const PlaneList planes, const int tiles_y)
+__device__ __forceinline__ void tile_body(uint32_t *tile, const LevelGeom &cur, const LevelGeom &nxt, int plane, int x0, int y0, int tid)
 {
-    if ((int)blockIdx.y >= tiles_y) {
-        // extra CTAs of a level >= 1: the REFLECT_101 apron of this (input) level, complete since the previous launch
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        const int region = ((int)blockIdx.y - tiles_y) * (int)gridDim.x + (int)blockIdx.x;
-        if (region < apron_regions(cur.h, cur.apron, 128)) apron_region(cur, planes.plane[blockIdx.z], region, threadIdx.x, 128);
-        return;
-    }
-    __shared__ __align__(128) uint32_t tile[kBoxH * kRowWords];
-    __shared__ __align__(8) uint64_t bar;
-
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
-    const int plane = planes.plane[blockIdx.z];
-    const uint32_t bar_a = smem_u32(&bar);
-
-#ifndef PSNW_DEBUG_NO_TMA
-    // Programmatic dependent launch: let the next level's grid start its prologue now, and wait for the previous
-    // level's grid (which wrote this level's u8 image) to complete before the first read.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid == 0) mbar_init(bar_a, 1);
-    __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (tid == 0) {
-        mbar_expect_tx(bar_a, kBoxW * kBoxH);
-        tma_load_3d(smem_u32(tile), &map, x0 - kHaloL, y0 - kHaloT, plane, bar_a);
-    }
-    mbar_wait(bar_a, 0);
-#else   // bring-up aid only (never built into libpsnw_klt.so): same tile contents through plain loads
-    (void)bar_a;
-    for (int i = tid; i < kBoxW * kBoxH; i += 128) {
-        const int r = i / kBoxW, c = i - r * kBoxW;
-        const int gx = x0 - kHaloL + c, gy = y0 - kHaloT + r;
-        uint8_t v = 0;
-        if (gx >= 0 && gy >= 0 && gx < cur.w && gy < cur.h) v = cur.img[(size_t)plane * cur.iplane_px + (size_t)gy * cur.ipitch + gx];
-        reinterpret_cast<uint8_t *>(tile)[i] = v;
-    }
-    __syncthreads();
-#endif
-
     // ---- REFLECT_101 fix-up of halo bytes that fell outside the image (TMA wrote zeros there) ----
     const int W = cur.w, H = cur.h;
     const bool edge_l = (x0 == 0), edge_r = (W - x0 + kHaloL + 1 < kBoxW);
@@ -242,6 +205,152 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
     }
 }
 
+template <bool kHasNext>
+__global__ void __launch_bounds__(128)
+pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, const LevelGeom nxt,
+                  const PlaneList planes, const int tiles_y)
+{
+    if ((int)blockIdx.y >= tiles_y) {
+        // extra CTAs of a level >= 1: the REFLECT_101 apron of this (input) level, complete since the previous launch
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int region = ((int)blockIdx.y - tiles_y) * (int)gridDim.x + (int)blockIdx.x;
+        if (region < apron_regions(cur.h, cur.apron, 128)) apron_region(cur, planes.plane[blockIdx.z], region, threadIdx.x, 128);
+        return;
+    }
+    __shared__ __align__(128) uint32_t tile[kBoxH * kRowWords];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+    const int plane = planes.plane[blockIdx.z];
+    const uint32_t bar_a = smem_u32(&bar);
+
+#ifndef PSNW_DEBUG_NO_TMA
+    // Programmatic dependent launch: let the next level's grid start its prologue now, and wait for the previous
+    // level's grid (which wrote this level's u8 image) to complete before the first read.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) mbar_init(bar_a, 1);
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tid == 0) {
+        mbar_expect_tx(bar_a, kBoxW * kBoxH);
+        tma_load_3d(smem_u32(tile), &map, x0 - kHaloL, y0 - kHaloT, plane, bar_a);
+    }
+    mbar_wait(bar_a, 0);
+#else   // bring-up aid only (never built into libpsnw_klt.so): same tile contents through plain loads
+    (void)bar_a;
+    for (int i = tid; i < kBoxW * kBoxH; i += 128) {
+        const int r = i / kBoxW, c = i - r * kBoxW;
+        const int gx = x0 - kHaloL + c, gy = y0 - kHaloT + r;
+        uint8_t v = 0;
+        if (gx >= 0 && gy >= 0 && gx < cur.w && gy < cur.h) v = cur.img[(size_t)plane * cur.iplane_px + (size_t)gy * cur.ipitch + gx];
+        reinterpret_cast<uint8_t *>(tile)[i] = v;
+    }
+    __syncthreads();
+#endif
+
+    tile_body<kHasNext>(tile, cur, nxt, plane, x0, y0, tid);
+}
+
+// ---- level walker: every level of every frame of a batch in ONE persistent launch ------------------------------------------
+// The per-level kernel is bandwidth-efficient, but a batch pays one dependent launch (and one tail) per level, and the coarse
+// levels of small frames are mostly launch latency.  Here the tiles of all levels form one ordered work list (level-major,
+// then plane, then tile); a grid that just fills the machine draws items from a device counter.  A tile of level l >= 1 waits
+// until every tile of level l-1 of its frame has signalled completion (one counter per (level, frame); items are drawn in
+// order and an item only ever waits for items drawn before it, so the wait always ends).  Level l tiles of one frame run
+// while level l-1 tiles of the following frames are still being produced: no launch boundary, no per-level tail.  The
+// REFLECT_101 apron of a level >= 1 is scattered from the tile the CTA already holds in shared memory (pyr_common.cuh).
+// The inputs of the levels >= 1 were written with generic stores by other CTAs and are read by the TMA unit: the consumer
+// orders its acquire before the copy with fence.proxy.async.
+struct WalkParams {
+    CUtensorMap map[PSNW_MAX_LEVELS];
+    LevelGeom lv[PSNW_MAX_LEVELS];
+    int tiles_x[PSNW_MAX_LEVELS], tiles[PSNW_MAX_LEVELS];    // tiles per row / per plane of a level
+    int begin[PSNW_MAX_LEVELS + 1];                             // first work item of a level
+    int levels, n_planes;
+    unsigned *ctl;                                              // [0] next item, [1] CTAs that left, [2 + l * n_planes + i] finished tiles
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+constexpr int kWalkThreads = 128;
+
+__global__ void __launch_bounds__(kWalkThreads, 8)
+pyr_walk_kernel(const __grid_constant__ WalkParams P, const __grid_constant__ PlaneList planes)
+{
+    __shared__ __align__(128) uint32_t tile[kBoxH * kRowWords];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ ApronWork apron;
+    __shared__ int s_item[2];
+    const int tid = threadIdx.x;
+    const uint32_t bar_a = smem_u32(&bar);
+    const int total = P.begin[P.levels];
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) mbar_init(bar_a, 1);
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // the control block and the frames belong to the launch before
+    if (tid == 0) s_item[0] = (int)atomicAdd(&P.ctl[0], 1u);
+    __syncthreads();
+    uint32_t phase = 0;
+    int it = s_item[0];
+    for (int round = 0; it < total; ++round) {
+        int l = 0;
+#pragma unroll
+        for (int k = 1; k < PSNW_MAX_LEVELS; ++k) l += (k < P.levels && it >= P.begin[k]) ? 1 : 0;
+        const int q = it - P.begin[l], pi = q / P.tiles[l], t = q - pi * P.tiles[l];
+        const int ty = t / P.tiles_x[l], tx = t - ty * P.tiles_x[l];
+        const int x0 = tx * kTileW, y0 = ty * kTileH;
+        const int plane = planes.plane[pi];
+        const LevelGeom &cur = P.lv[l];
+        const bool has_next = l + 1 < P.levels;
+        const LevelGeom &nxt = P.lv[has_next ? l + 1 : l];
+        const int A = cur.apron;
+        const bool edge = A > 0 && (x0 <= A || x0 + kTileW >= cur.w - 1 - A || y0 <= A || y0 + kTileH >= cur.h - 1 - A);
+        if (tid == 0) {
+            if (l > 0) {
+                const unsigned *flag = &P.ctl[2 + (l - 1) * P.n_planes + pi];
+                const unsigned want = (unsigned)P.tiles[l - 1];
+                while (ld_acquire_u32(flag) < want) __nanosleep(64);
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");     // generic writes (other CTAs' pixels, this buffer's fix-ups) before the copy
+            mbar_expect_tx(bar_a, kBoxW * kBoxH);
+            tma_load_3d(smem_u32(tile), &P.map[l], x0 - kHaloL, y0 - kHaloT, plane, bar_a);
+            s_item[(round + 1) & 1] = (int)atomicAdd(&P.ctl[0], 1u);          // the next item, drawn under this tile's copy
+        } else if (tid == 32) {
+            if (edge) apron_work_fill(apron, cur.w, cur.h, A, x0, y0, kTileW, kTileH);
+        }
+        mbar_wait(bar_a, phase);
+        phase ^= 1u;
+        __syncthreads();                                           // publishes the apron list and the next item
+        if (has_next) tile_body<true>(tile, cur, nxt, plane, x0, y0, tid);
+        else          tile_body<false>(tile, cur, nxt, plane, x0, y0, tid);
+        if (edge)
+            apron_scatter(apron, reinterpret_cast<const uint8_t *>(tile), kBoxW, x0 - kHaloL, y0 - kHaloT, x0, kTileW, 3, cur.w, cur.h, A,
+                          cur.img + (size_t)plane * cur.iplane_px, cur.ipitch, tid, kWalkThreads);
+        it = s_item[(round + 1) & 1];
+        __syncthreads();                                           // every store of the tile is issued; the buffers are free
+        if (tid == 0 && has_next) {
+            __threadfence();
+            atomicAdd(&P.ctl[2 + l * P.n_planes + pi], 1u);
+        }
+    }
+    // the last CTA to leave returns the control block to zero for the next launch
+    if (tid == 0) {
+        __threadfence();
+        s_item[0] = atomicAdd(&P.ctl[1], 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_item[0]) {
+        for (int i = tid; i < 2 + P.levels * P.n_planes; i += kWalkThreads) P.ctl[i] = 0u;
+    }
+}
+
 // BGR (8UC3) -> gray, cv::cvtColor(BGR2GRAY) fixed point (Tracker2D.cpp:257):
 //   15 bit: (3735 B + 19235 G + 9798 R + 2^14) >> 15 (OpenCV 4.x);  14 bit: (1868 B + 9617 G + 4899 R + 2^13) >> 14 (2.4.6)
 __global__ void __launch_bounds__(256)
@@ -288,6 +397,43 @@ int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, c
     const cudaError_t e = has_next ? cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<true>, *map_in, cur, nxt, planes, tiles_y)
                                    : cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<false>, *map_in, cur, nxt, planes, tiles_y);
     return e == cudaSuccess ? 1 : -1;
+}
+
+// all levels of the planes in one persistent launch (pyr_walk_kernel).  ctl: device control block of walk_ctl_words(levels,
+// planes.n) zeroed words, exclusively this launch's until it completes (the kernel leaves it zeroed).
+size_t walk_ctl_words(int levels, int n_planes) { return 2 + (size_t)levels * n_planes; }
+
+int launch_pyr_walk(const PyrDesc &pyr, const CUtensorMap *maps, const PlaneList &planes, unsigned *ctl, int ctas_per_sm, int sm_count,
+                    cudaStream_t stream)
+{
+    static int occ = 0;
+    if (!occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pyr_walk_kernel, kWalkThreads, 0) != cudaSuccess) return -1;
+    WalkParams P;
+    memset(&P, 0, sizeof P);
+    P.levels = pyr.levels;
+    P.n_planes = planes.n;
+    P.ctl = ctl;
+    int begin = 0;
+    for (int l = 0; l < pyr.levels; ++l) {
+        P.map[l] = maps[l];
+        P.lv[l] = pyr.lv[l];
+        P.tiles_x[l] = (pyr.lv[l].w + kTileW - 1) / kTileW;
+        P.tiles[l] = P.tiles_x[l] * ((pyr.lv[l].h + kTileH - 1) / kTileH);
+        P.begin[l] = begin;
+        begin += P.tiles[l] * planes.n;
+    }
+    for (int l = pyr.levels; l <= PSNW_MAX_LEVELS; ++l) P.begin[l] = begin;
+    const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : occ;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(std::min(begin, per_sm * sm_count));
+    cfg.blockDim = dim3(kWalkThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, pyr_walk_kernel, P, planes) == cudaSuccess ? 1 : -1;
 }
 
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,

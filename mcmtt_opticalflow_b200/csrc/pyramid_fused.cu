@@ -59,6 +59,8 @@ template <int NL, int TH> struct FG {
 struct FusedLevels {
     LevelGeom lv[4];
     int base;          // pyramid level of lv[0]; > 0: the chain starts from a level that carries an apron, which is written here too
+    int late_wait;     // the launch shares no data with the kernels before it in its stream (a build of other planes): it starts
+                       // at once and waits for them only before it completes, so that stream order still holds for what follows
 };
 
 #ifdef PSNW_PYR_TIMELINE          // bring-up aid (tools/pyr_timeline.cu): per-CTA time stamps at the phase boundaries
@@ -305,10 +307,15 @@ pyr_fused_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const uint32_t bar_a = smem_u32(&bar);
 
     PSNW_STAMP(0);
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Programmatic dependent launch.  A launch that depends on its predecessors waits first and only then lets its own
+    // dependents start: a dependent with late_wait therefore never runs beside anything older than this launch's wait.
+    if (L.late_wait) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) mbar_init(bar_a, 1);
     __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!L.late_wait) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     if (tid == 0) {
         mbar_expect_tx(bar_a, G::pitch(0) * G::box_h() * G::n_box());
 #pragma unroll
@@ -335,6 +342,7 @@ pyr_fused_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     PSNW_STAMP(4);
     apron_all<NL, TH, 0, NT>(smem, aprons, L, plane, rot);
     PSNW_STAMP(5);
+    if (L.late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 template <int NL, int TH, int NT>
@@ -382,11 +390,13 @@ int configure_fused_kernels()
 // (base = 0: the frame itself); `map0` is the tensor map of level `base` with the box of region variant `variant`
 // (fused_geometry).  threads per CTA: 256 (four CTAs per SM: large launches of small regions) or 512 (two).  (1024 threads
 // and one CTA per SM were measured for the single-wave launch: no gain, the phases of a lone CTA are latency-bound.)
-int launch_pyr_fused(const PyrDesc &pyr, int base, int nl, int variant, int threads, const CUtensorMap *map0, const PlaneList &planes, cudaStream_t stream)
+int launch_pyr_fused(const PyrDesc &pyr, int base, int nl, int variant, int threads, const CUtensorMap *map0, const PlaneList &planes, int late_wait,
+                     cudaStream_t stream)
 {
     FusedLevels L;
     for (int k = 0; k < 4; ++k) L.lv[k] = pyr.lv[base + (k < nl ? k : nl - 1)];
     L.base = base;
+    L.late_wait = late_wait;
 #define PSNW_LAUNCH(NL_, TH_)                                                                               \
     return threads <= 256 ? launch_fused_t<NL_, TH_, 256>(map0, L, planes, stream) : launch_fused_t<NL_, TH_, 512>(map0, L, planes, stream)
     if (nl == 4) {

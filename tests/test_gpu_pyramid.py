@@ -35,7 +35,7 @@ def _check_apron(ctx, img, cam, slot, level, apron=26):
     assert np.array_equal(got, want), "apron of level %d differs" % level
 
 
-@pytest.mark.parametrize("mode", ["level", "fused", "hybrid"])
+@pytest.mark.parametrize("mode", ["level", "fused", "hybrid", "walk"])
 @pytest.mark.parametrize("w,h,levels", [(768, 576, 4), (767, 575, 4), (129, 33, 3), (16, 16, 2), (130, 70, 3),
                                         (1920, 1080, 4), (257, 131, 5), (640, 480, 6), (193, 65, 4), (385, 129, 3),
                                         (3840, 2160, 5)])
@@ -50,7 +50,7 @@ def test_bit_exact_vs_oracle(oracle, monkeypatch, w, h, levels, mode):
         _check_levels(ctx, oracle, img)
 
 
-@pytest.mark.parametrize("mode", ["level", "fused", "hybrid"])
+@pytest.mark.parametrize("mode", ["level", "fused", "hybrid", "walk"])
 @pytest.mark.parametrize("apron,w,h,levels", [(64, 768, 576, 4), (40, 333, 97, 4), (160, 640, 480, 5), (5, 130, 70, 3)])
 def test_apron_width_is_a_context_parameter(oracle, monkeypatch, apron, w, h, levels, mode):
     """psnw_params.apron: wider aprons for contexts that track large windows (clamped to [26, 160])."""
@@ -81,7 +81,7 @@ def test_golden_fixture(golden):
             assert np.array_equal(dxy[..., 1], golden["dy_odd_%d" % l])
 
 
-@pytest.mark.parametrize("mode", ["level", "fused", "hybrid"])
+@pytest.mark.parametrize("mode", ["level", "fused", "hybrid", "walk"])
 def test_batched_cameras_and_ring_rotation(oracle, monkeypatch, mode):
     monkeypatch.setenv("PSNW_PYR_MODE", mode)
     w, h, ncam = 384, 288, 3
@@ -154,3 +154,43 @@ def test_contiguous_block_takes_the_single_copy_path(oracle):
         ctx.push_frames([blk[c] for c in (4, 2, 0)], cams=[4, 2, 0])     # negative source stride, non-unit camera step
         for c in (4, 2, 0):
             _check_levels(ctx, oracle, blk[c], cam=c, slot=0)
+
+
+@pytest.mark.parametrize("ctas", ["0", "1"])
+def test_level_walker_many_frames(oracle, monkeypatch, ctas):
+    """The persistent level walker (one launch for every level of every frame, levels chained through per-frame completion
+    counters): a batch with far more tiles than resident CTAs, pushed repeatedly with changing content so that a tile read
+    before its producers finished would show as stale pixels; one CTA per SM forces long waits on the counters."""
+    monkeypatch.setenv("PSNW_PYR_MODE", "walk")
+    monkeypatch.setenv("PSNW_WALK_CTAS", ctas)
+    w, h, ncam = 333, 201, 40
+    rng = np.random.default_rng(11)
+    with klt.KLTContext(w, h, n_cameras=ncam, levels=4, ring_slots=2) as ctx:
+        for rep in range(3):
+            blk = rng.integers(0, 256, size=(ncam, h, w), dtype=np.uint8)
+            ctx.push_frames([blk[c] for c in range(ncam)])
+            for c in range(0, ncam, 3):
+                _check_levels(ctx, oracle, blk[c], cam=c, slot=0)
+
+
+def test_consecutive_builds_of_other_planes_overlap(oracle, monkeypatch):
+    """Back-to-back fused builds of disjoint ring slots start without waiting for each other (late_wait) and complete in
+    stream order; a build that revisits planes of the chain waits first.  Results are those of the serial order."""
+    monkeypatch.setenv("PSNW_PYR_MODE", "fused")
+    w, h, ncam, slots = 320, 240, 3, 4
+    rng = np.random.default_rng(5)
+    frames = [rng.integers(0, 256, size=(ncam, h, w), dtype=np.uint8) for _ in range(slots)]
+    with klt.KLTContext(w, h, n_cameras=ncam, levels=4, ring_slots=slots) as ctx:
+        for s in range(slots):
+            ctx.push_frames([frames[s][c] for c in range(ncam)])
+        cams = np.arange(ncam, dtype=np.int32)
+        for rep in range(3):
+            for s in range(slots):
+                ctx.rebuild_pyramids(cams, slot=s)
+            ctx.rebuild_pyramids(cams, slot=0)                    # planes already in the chain: waits first
+            ctx.rebuild_pyramids(cams[:1], slot=1)
+            ctx.rebuild_pyramids(cams[1:], slot=1)                # other cameras of the same slot: disjoint planes
+        ctx.sync()
+        for s in range(slots):
+            for c in range(ncam):
+                _check_levels(ctx, oracle, frames[slots - 1 - s][c], cam=c, slot=s)
