@@ -514,7 +514,7 @@ def pyramid_modes(rig, w, h, levels, frames, isolated_reps=10, stream_launches=4
     probe = klt.KLTContext(w, h, n_cameras=1, levels=levels, ring_slots=1, stream=rig.stream.cuda_stream, max_points=1024, max_targets=64)
     per_frame = probe.push_frame_bytes
     probe.close()
-    slots = int(min(max(np.ceil((256 << 20) / (per_frame * frames)), 2), 32))
+    slots = int(min(max(np.ceil((256 << 20) / (per_frame * frames)), 4), 32))
     ctx = klt.KLTContext(w, h, n_cameras=frames, levels=levels, ring_slots=slots, stream=rig.stream.cuda_stream, max_points=1024, max_targets=64)
     cams = np.arange(frames, dtype=np.int32)
     for _ in range(slots):

@@ -64,6 +64,7 @@ struct psnw_ctx {
     unsigned *walk_ctl = nullptr;
     size_t walk_ctl_stride = 0;
     unsigned walk_next = 0;
+    int walk_base = 0;                    // levels below this one take the per-level kernel ahead of the walker (PSNW_WALK_BASE, bring-up)
     int walk_ctas = 0;                    // CTAs per SM of the walker (0: what fits; PSNW_WALK_CTAS, bring-up)
     size_t walk_min_px = 2200000;         // auto mode: launches above this many level-0 pixels take the walker
     // Consecutive fused builds of disjoint planes on one stream overlap (launch_pyr_fused late_wait): the count of this
@@ -360,8 +361,16 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
         // 62; 32 x 1080p level 93 us / hybrid 99; 16 x 4K level 163 us / hybrid 173)
         if (mode == 0) mode = (ctx->fused_levels && px <= ctx->fused_max_px) ? 2 : (ctx->hyb_levels && (size_t)l0.w * l0.h <= ctx->hybrid_max_frame_px) ? 3 : 1;
         if (mode == 4) {
+            // the finest `walk_base` levels by the per-level kernel (no apron CTAs: the walker scatters the apron of every
+            // level it reads), the rest by the walker
+            const int wb = std::min(ctx->walk_base, ctx->pyr.levels - 1);
+            for (int l = 0; l < wb; ++l) {
+                const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, l > 0 ? 1 : 0, 0, st);
+                if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_scharr_kernel launch", cudaGetLastError());
+                ctx->launches += r;
+            }
             unsigned *ctl = ctx->walk_ctl + (ctx->walk_next++ % psnw_ctx::kWalkBlocks) * ctx->walk_ctl_stride;
-            const int r = launch_pyr_walk(ctx->pyr, ctx->maps, pl, ctl, ctx->walk_ctas, ctx->sm_count, st);
+            const int r = launch_pyr_walk(ctx->pyr, wb, ctx->maps, pl, ctl, ctx->walk_ctas, ctx->sm_count, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_walk_kernel launch", cudaGetLastError());
             ctx->launches += r;
             continue;
@@ -369,28 +378,31 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
         if (mode == 2 && !ctx->fused_levels) mode = 1;
         if (mode == 3 && !ctx->hyb_levels) mode = ctx->fused_levels ? 2 : 1;
         int first = 0, last = ctx->pyr.levels;                       // levels [first, last) take the per-level kernel
+        // A build reads only the frames (complete: a copy or an earlier call put them there) and writes only the levels of its
+        // own planes.  Straight after a build of OTHER planes on the same stream whose last launch was the fused kernel (which
+        // releases its dependents only after its own wait), the first launch of this build need not wait for it (late_wait):
+        // consecutive builds overlap.  pyr_chain_planes = planes built since the last build that waited first.
+        bool late = (mode == 2 || mode == 3) && ctx->pyr_overlap && ctx->launches == ctx->pyr_chain_launches && st == ctx->pyr_chain_stream;
+        if (ctx->pyr_chain_planes.size() != (size_t)ctx->planes) ctx->pyr_chain_planes.assign(ctx->planes, 0);
+        for (int i = 0; late && i < pl.n; ++i) late = !ctx->pyr_chain_planes[pl.plane[i]];
+        if (!late) std::fill(ctx->pyr_chain_planes.begin(), ctx->pyr_chain_planes.end(), 0);
+        for (int i = 0; i < pl.n; ++i) ctx->pyr_chain_planes[pl.plane[i]] = 1;
+        bool ends_fused = false;
         if (mode == 2) {
             int wide = 0;
             const int variant = fused_variant_for(ctx, 0, ctx->fused_levels, pl.n, &wide);
             // deeper pyramids: level 3 again (per-level kernel) only to feed level 4; it rewrites its apron with the same values
             first = ctx->fused_levels < ctx->pyr.levels ? ctx->fused_levels - 1 : ctx->pyr.levels;
-            // the build reads only the frames (complete: a copy or an earlier call put them there) and writes only the levels of
-            // its own planes: straight after a fused build of OTHER planes on the same stream it need not wait for it
-            const bool alone = first == ctx->pyr.levels;
-            bool late = alone && ctx->pyr_overlap && ctx->launches == ctx->pyr_chain_launches && st == ctx->pyr_chain_stream;
-            if (ctx->pyr_chain_planes.size() != (size_t)ctx->planes) ctx->pyr_chain_planes.assign(ctx->planes, 0);
-            for (int i = 0; late && i < pl.n; ++i) late = !ctx->pyr_chain_planes[pl.plane[i]];
-            if (!late) std::fill(ctx->pyr_chain_planes.begin(), ctx->pyr_chain_planes.end(), 0);
-            for (int i = 0; i < pl.n; ++i) ctx->pyr_chain_planes[pl.plane[i]] = 1;
             const int r = launch_pyr_fused(ctx->pyr, 0, ctx->fused_levels, variant, wide, &ctx->map_fused[variant], pl, late ? 1 : 0, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_fused_kernel launch", cudaGetLastError());
             ctx->launches += r;
-            if (alone) { ctx->pyr_chain_launches = ctx->launches; ctx->pyr_chain_stream = st; }
+            ends_fused = first == ctx->pyr.levels;
+            late = false;
         } else if (mode == 3) {
             last = ctx->hyb_base;
         }
         for (int l = first; l < last; ++l) {
-            const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, 1, st);
+            const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, 1, (late && l == 0) ? 1 : 0, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_scharr_kernel launch", cudaGetLastError());
             ctx->launches += r;
         }
@@ -400,7 +412,10 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
             const int r = launch_pyr_fused(ctx->pyr, ctx->hyb_base, ctx->hyb_levels, variant, wide, &ctx->map_hyb[variant], pl, 0, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_fused_kernel launch", cudaGetLastError());
             ctx->launches += r;
+            ends_fused = true;
         }
+        ctx->pyr_chain_launches = ends_fused ? ctx->launches : ~(uint64_t)0;
+        ctx->pyr_chain_stream = st;
     }
     return PSNW_OK;
 }
@@ -615,6 +630,7 @@ int psnw_create(psnw_ctx **out, const psnw_params *p)
     if (const char *m = getenv("PSNW_PYR_MODE")) ctx->pyr_mode = !strcmp(m, "level") ? 1 : !strcmp(m, "fused") ? 2 : !strcmp(m, "hybrid") ? 3 : !strcmp(m, "walk") ? 4 : 0;
     if (const char *m = getenv("PSNW_PYR_OVERLAP")) ctx->pyr_overlap = atoi(m) != 0;
     if (const char *m = getenv("PSNW_WALK_CTAS")) ctx->walk_ctas = atoi(m);
+    if (const char *m = getenv("PSNW_WALK_BASE")) ctx->walk_base = std::max(atoi(m), 0);
     if (const char *m = getenv("PSNW_WALK_MIN_PX")) ctx->walk_min_px = (size_t)atoll(m);
     if (const char *m = getenv("PSNW_FUSED_THREADS")) ctx->fused_wide = atoi(m);
     if (const char *m = getenv("PSNW_FUSED_VARIANT")) ctx->fused_variant = std::min(std::max(atoi(m), 0), kFusedVariants - 1);

@@ -93,7 +93,7 @@ int configure_detect_kernels();
 
 // --- launchers (each returns the number of kernels it enqueued, or -1 with cudaGetLastError set) ---
 // with_apron: the launch also writes the REFLECT_101 apron of its input level (levels >= 1) with extra CTAs
-int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron,
+int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron, int late_wait,
                      cudaStream_t stream);
 // fused multi-level variant (pyramid_fused.cu): levels 0..nl-1 AND their aprons in one launch.  Three region heights
 // (variant 0 / 1 / 2); fused_geometry = TMA box of the variant's level-0 map and the level-0 region one CTA owns
@@ -104,9 +104,9 @@ int configure_fused_kernels();
 // beside them and only completes after them
 int launch_pyr_fused(const PyrDesc &pyr, int base, int nl, int variant, int threads, const CUtensorMap *map0, const PlaneList &planes, int late_wait,
                      cudaStream_t stream);
-// level walker (pyramid.cu): every level and apron of the planes in one persistent launch; ctl = walk_ctl_words() zeroed words
+// level walker (pyramid.cu): the levels >= base and every apron of the planes in one persistent launch (levels < base complete); ctl = walk_ctl_words() zeroed words
 size_t walk_ctl_words(int levels, int n_planes);
-int launch_pyr_walk(const PyrDesc &pyr, const CUtensorMap *maps, const PlaneList &planes, unsigned *ctl, int ctas_per_sm, int sm_count,
+int launch_pyr_walk(const PyrDesc &pyr, int base, const CUtensorMap *maps, const PlaneList &planes, unsigned *ctl, int ctas_per_sm, int sm_count,
                     cudaStream_t stream);
 int launch_bgr2gray(const uint8_t *bgr, size_t bgr_pitch, uint8_t *gray, int gray_pitch, int w, int h,
                     int luma_bits, cudaStream_t stream);

@@ -15,6 +15,7 @@
 // lane = 512 contiguous bytes per warp row for the derivative image and 2 bytes per lane for the next
 // u8 level.  HBM traffic per level-l pixel: 1 B read, 4 B + 0.25 B written.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -109,9 +110,14 @@ __device__ __forceinline__ void apron_region(const LevelGeom &L, int plane, int 
 
 // Fix-up + arithmetic of one 128x32 tile of level `cur` held (with its halo) in `tile`: Scharr derivatives of the tile and,
 // with kHasNext, the 64x16 tile of the next level.  Shared by the per-level kernel and the level walker below.
-template <bool kHasNext>
+struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+// the 128 compute threads of a CTA that also holds a helper warp (level walker)
+struct ComputeSync { __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, 128;" ::: "memory"); } };
+
+template <bool kHasNext, typename Sync = CtaSync>
 __device__ __forceinline__ void tile_body(uint32_t *tile, const LevelGeom &cur, const LevelGeom &nxt, int plane, int x0, int y0, int tid)
 {
+    const Sync sync;
     // ---- REFLECT_101 fix-up of halo bytes that fell outside the image (TMA wrote zeros there) ----
     const int W = cur.w, H = cur.h;
     const bool edge_l = (x0 == 0), edge_r = (W - x0 + kHaloL + 1 < kBoxW);
@@ -128,7 +134,7 @@ __device__ __forceinline__ void tile_body(uint32_t *tile, const LevelGeom &cur, 
                     row[c + 1] = row[c - 3];                                        // x=W+1 <- W-3
                 }
             }
-            __syncthreads();
+            sync();
         }
         if (edge_t || edge_b) {
             for (int i = tid; i < kRowWords; i += 128) {
@@ -139,7 +145,7 @@ __device__ __forceinline__ void tile_body(uint32_t *tile, const LevelGeom &cur, 
                     if (r + 1 < kBoxH) tile[(r + 1) * kRowWords + i] = tile[(r - 3) * kRowWords + i];   // y=H+1 <- H-3
                 }
             }
-            __syncthreads();
+            sync();
         }
     }
 
@@ -208,10 +214,11 @@ __device__ __forceinline__ void tile_body(uint32_t *tile, const LevelGeom &cur, 
 template <bool kHasNext>
 __global__ void __launch_bounds__(128)
 pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, const LevelGeom nxt,
-                  const PlaneList planes, const int tiles_y)
+                  const PlaneList planes, const int tiles_y, const int late_wait)
 {
     if ((int)blockIdx.y >= tiles_y) {
         // extra CTAs of a level >= 1: the REFLECT_101 apron of this (input) level, complete since the previous launch
+        // (never launched with late_wait: level 0 has no apron)
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         asm volatile("griddepcontrol.wait;" ::: "memory");
         const int region = ((int)blockIdx.y - tiles_y) * (int)gridDim.x + (int)blockIdx.x;
@@ -229,10 +236,12 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
 #ifndef PSNW_DEBUG_NO_TMA
     // Programmatic dependent launch: let the next level's grid start its prologue now, and wait for the previous
     // level's grid (which wrote this level's u8 image) to complete before the first read.
+    // late_wait (level 0 of planes that no kernel before it in the stream touches; see launch_pyr_fused): the launch runs
+    // beside its predecessors and only completes after them
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) mbar_init(bar_a, 1);
     __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tid == 0) {
         mbar_expect_tx(bar_a, kBoxW * kBoxH);
         tma_load_3d(smem_u32(tile), &map, x0 - kHaloL, y0 - kHaloT, plane, bar_a);
@@ -251,17 +260,25 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
 #endif
 
     tile_body<kHasNext>(tile, cur, nxt, plane, x0, y0, tid);
+    if (late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---- level walker: every level of every frame of a batch in ONE persistent launch ------------------------------------------
 // The per-level kernel is bandwidth-efficient, but a batch pays one dependent launch (and one tail) per level, and the coarse
 // levels of small frames are mostly launch latency.  Here the tiles of all levels form one ordered work list (level-major,
-// then plane, then tile); a grid that just fills the machine draws items from a device counter.  A tile of level l >= 1 waits
-// until every tile of level l-1 of its frame has signalled completion (one counter per (level, frame); items are drawn in
-// order and an item only ever waits for items drawn before it, so the wait always ends).  Level l tiles of one frame run
-// while level l-1 tiles of the following frames are still being produced: no launch boundary, no per-level tail.  The
-// REFLECT_101 apron of a level >= 1 is scattered from the tile the CTA already holds in shared memory (pyr_common.cuh).
-// The inputs of the levels >= 1 were written with generic stores by other CTAs and are read by the TMA unit: the consumer
+// then plane, then tile) drawn from a device counter by a grid that just fills the machine.  A tile of level l >= 1 may start
+// once every tile of level l-1 of its frame has signalled completion (one counter per (level, frame); items are drawn in
+// order and an item only ever waits for items drawn before it, so every wait ends).  Level l of one frame runs while level
+// l-1 of the following frames is still being produced: no launch boundary, no per-level tail.
+//
+// A CTA is a small pipeline: four compute warps and one helper warp around kWalkStages tile buffers.
+//   helper (one thread)  draws items, polls their dependency, issues the TMA box of each into a free stage (mbarrier `full`),
+//                        and retires finished tiles: it watches the `done` barrier of every stage in flight and publishes
+//                        their completion with ONE fence + one reduction per tile.  The fence (which has to wait for the
+//                        tile's stores to reach L2) and the draw therefore never hold up the compute warps or the copies.
+//   compute (128 threads) wait for a stage, run the tile arithmetic of the per-level kernel, scatter the REFLECT_101 apron of
+//                        levels >= 1 from the tile they hold (pyr_common.cuh), arrive on `done`, move to the next stage.
+// The inputs of the levels >= 1 were written with generic stores by other CTAs and are read by the TMA unit: the helper
 // orders its acquire before the copy with fence.proxy.async.
 struct WalkParams {
     CUtensorMap map[PSNW_MAX_LEVELS];
@@ -269,6 +286,7 @@ struct WalkParams {
     int tiles_x[PSNW_MAX_LEVELS], tiles[PSNW_MAX_LEVELS];    // tiles per row / per plane of a level
     int begin[PSNW_MAX_LEVELS + 1];                             // first work item of a level
     int levels, n_planes;
+    int base;                                                   // first level of the walk (levels below it are complete in HBM)
     unsigned *ctl;                                              // [0] next item, [1] CTAs that left, [2 + l * n_planes + i] finished tiles
 };
 
@@ -279,75 +297,141 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
     return v;
 }
 
-constexpr int kWalkThreads = 128;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
-__global__ void __launch_bounds__(kWalkThreads, 8)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+
+constexpr int kWalkCompute = 128, kWalkThreads = kWalkCompute + 32, kWalkStages = 3, kWalkCtasPerSm = 7;
+constexpr int kWalkSigRing = 16, kWalkSigBatch = 8;            // finished tiles are published in batches: one fence per batch
+constexpr int kWalkStageWords = (kBoxH * kRowWords + 31) & ~31;      // 128-byte aligned tile buffers
+
+struct WalkItem {
+    int level;         // < 0: no more work
+    int plane, x0, y0;
+    int edge;          // the tile holds pixels whose mirror images lie in the level's apron
+};
+
+__global__ void __launch_bounds__(kWalkThreads, kWalkCtasPerSm)
 pyr_walk_kernel(const __grid_constant__ WalkParams P, const __grid_constant__ PlaneList planes)
 {
-    __shared__ __align__(128) uint32_t tile[kBoxH * kRowWords];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ ApronWork apron;
-    __shared__ int s_item[2];
+    __shared__ __align__(128) uint32_t tiles[kWalkStages * kWalkStageWords];
+    __shared__ __align__(8) uint64_t bar_full[kWalkStages], bar_done[kWalkStages];
+    __shared__ ApronWork apron[kWalkStages];
+    __shared__ WalkItem item[kWalkStages];
+    __shared__ int s_last;
     const int tid = threadIdx.x;
-    const uint32_t bar_a = smem_u32(&bar);
-    const int total = P.begin[P.levels];
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid == 0) mbar_init(bar_a, 1);
-    asm volatile("griddepcontrol.wait;" ::: "memory");           // the control block and the frames belong to the launch before
-    if (tid == 0) s_item[0] = (int)atomicAdd(&P.ctl[0], 1u);
-    __syncthreads();
-    uint32_t phase = 0;
-    int it = s_item[0];
-    for (int round = 0; it < total; ++round) {
-        int l = 0;
-#pragma unroll
-        for (int k = 1; k < PSNW_MAX_LEVELS; ++k) l += (k < P.levels && it >= P.begin[k]) ? 1 : 0;
-        const int q = it - P.begin[l], pi = q / P.tiles[l], t = q - pi * P.tiles[l];
-        const int ty = t / P.tiles_x[l], tx = t - ty * P.tiles_x[l];
-        const int x0 = tx * kTileW, y0 = ty * kTileH;
-        const int plane = planes.plane[pi];
-        const LevelGeom &cur = P.lv[l];
-        const bool has_next = l + 1 < P.levels;
-        const LevelGeom &nxt = P.lv[has_next ? l + 1 : l];
-        const int A = cur.apron;
-        const bool edge = A > 0 && (x0 <= A || x0 + kTileW >= cur.w - 1 - A || y0 <= A || y0 + kTileH >= cur.h - 1 - A);
-        if (tid == 0) {
-            if (l > 0) {
-                const unsigned *flag = &P.ctl[2 + (l - 1) * P.n_planes + pi];
-                const unsigned want = (unsigned)P.tiles[l - 1];
-                while (ld_acquire_u32(flag) < want) __nanosleep(64);
-            }
-            asm volatile("fence.proxy.async;" ::: "memory");     // generic writes (other CTAs' pixels, this buffer's fix-ups) before the copy
-            mbar_expect_tx(bar_a, kBoxW * kBoxH);
-            tma_load_3d(smem_u32(tile), &P.map[l], x0 - kHaloL, y0 - kHaloT, plane, bar_a);
-            s_item[(round + 1) & 1] = (int)atomicAdd(&P.ctl[0], 1u);          // the next item, drawn under this tile's copy
-        } else if (tid == 32) {
-            if (edge) apron_work_fill(apron, cur.w, cur.h, A, x0, y0, kTileW, kTileH);
-        }
-        mbar_wait(bar_a, phase);
-        phase ^= 1u;
-        __syncthreads();                                           // publishes the apron list and the next item
-        if (has_next) tile_body<true>(tile, cur, nxt, plane, x0, y0, tid);
-        else          tile_body<false>(tile, cur, nxt, plane, x0, y0, tid);
-        if (edge)
-            apron_scatter(apron, reinterpret_cast<const uint8_t *>(tile), kBoxW, x0 - kHaloL, y0 - kHaloT, x0, kTileW, 3, cur.w, cur.h, A,
-                          cur.img + (size_t)plane * cur.iplane_px, cur.ipitch, tid, kWalkThreads);
-        it = s_item[(round + 1) & 1];
-        __syncthreads();                                           // every store of the tile is issued; the buffers are free
-        if (tid == 0 && has_next) {
-            __threadfence();
-            atomicAdd(&P.ctl[2 + l * P.n_planes + pi], 1u);
-        }
-    }
-    // the last CTA to leave returns the control block to zero for the next launch
     if (tid == 0) {
-        __threadfence();
-        s_item[0] = atomicAdd(&P.ctl[1], 1u) == gridDim.x - 1 ? 1 : 0;
+        for (int s = 0; s < kWalkStages; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_done[s]), kWalkCompute / 32);
+        }
     }
     __syncthreads();
-    if (s_item[0]) {
-        for (int i = tid; i < 2 + P.levels * P.n_planes; i += kWalkThreads) P.ctl[i] = 0u;
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // the control block and the frames belong to the launches before
+
+    if (tid >= kWalkCompute) {
+        // ---------------------------------------------------------------- helper warp
+        if (tid == kWalkCompute) {
+            const int total = P.begin[P.levels];
+            int k_load = 0, k_free = 0, k_sig = 0;               // items loaded / finished by the compute warps / published
+            int sig[kWalkSigRing];                               // completion counter of item k (index into ctl), or -1
+            int it = (int)atomicAdd(&P.ctl[0], 1u);              // two draws ahead: the counter's latency stays off the path
+            int it_next = (int)atomicAdd(&P.ctl[0], 1u);
+            for (;;) {
+                if (k_free < k_load && mbar_test(smem_u32(&bar_done[k_free % kWalkStages]), (uint32_t)(k_free / kWalkStages) & 1u)) ++k_free;
+                const bool room = k_load - k_free < kWalkStages && k_load - k_sig < kWalkSigRing;
+                bool loaded = false;
+                if (it < total && room) {
+                    int l = P.base;
+#pragma unroll
+                    for (int k = 1; k < PSNW_MAX_LEVELS; ++k) l += (k > P.base && k < P.levels && it >= P.begin[k]) ? 1 : 0;
+                    const int q = it - P.begin[l], pi = q / P.tiles[l], t = q - pi * P.tiles[l];
+                    if (l == P.base || ld_acquire_u32(&P.ctl[2 + (l - 1) * P.n_planes + pi]) >= (unsigned)P.tiles[l - 1]) {
+                        const int ty = t / P.tiles_x[l], tx = t - ty * P.tiles_x[l];
+                        const int x0 = tx * kTileW, y0 = ty * kTileH, A = P.lv[l].apron, s = k_load % kWalkStages;
+                        WalkItem w;
+                        w.level = l; w.plane = planes.plane[pi]; w.x0 = x0; w.y0 = y0;
+                        w.edge = A > 0 && (x0 <= A || x0 + kTileW >= P.lv[l].w - 1 - A || y0 <= A || y0 + kTileH >= P.lv[l].h - 1 - A);
+                        item[s] = w;
+                        asm volatile("fence.proxy.async;" ::: "memory");     // generic writes (other CTAs' pixels, fix-ups of the stage) before the copy
+                        const uint32_t full = smem_u32(&bar_full[s]);
+                        mbar_expect_tx(full, kBoxW * kBoxH);
+                        tma_load_3d(smem_u32(tiles + s * kWalkStageWords), &P.map[l], x0 - kHaloL, y0 - kHaloT, w.plane, full);
+#pragma unroll
+                        for (int j = 0; j < kWalkSigRing; ++j)
+                            if (j == k_load % kWalkSigRing) sig[j] = l + 1 < P.levels ? 2 + l * P.n_planes + pi : -1;
+                        ++k_load;
+                        it = it_next;
+                        it_next = (int)atomicAdd(&P.ctl[0], 1u);
+                        loaded = true;
+                    }
+                }
+                // finished tiles are published in batches (one fence each), at once when there is nothing to load
+                if (k_sig < k_free && (!loaded || k_free - k_sig >= kWalkSigBatch)) {
+                    __threadfence();
+                    for (; k_sig < k_free; ++k_sig) {
+                        int f = -1;
+#pragma unroll
+                        for (int j = 0; j < kWalkSigRing; ++j)
+                            if (j == k_sig % kWalkSigRing) f = sig[j];
+                        if (f >= 0) atomicAdd(&P.ctl[f], 1u);
+                    }
+                    continue;
+                }
+                if (loaded) continue;
+                if (it >= total && k_sig == k_load) break;
+                __nanosleep(20);
+            }
+            // every stage is free: tell the compute warps to leave
+            item[k_load % kWalkStages].level = -1;
+            mbar_arrive(smem_u32(&bar_full[k_load % kWalkStages]));
+            __threadfence();
+            s_last = atomicAdd(&P.ctl[1], 1u) == gridDim.x - 1 ? 1 : 0;
+        }
+        __syncwarp();
+        // the last CTA to leave returns the control block to zero for the next launch
+        if (s_last)
+            for (int i = tid - kWalkCompute; i < 2 + P.levels * P.n_planes; i += 32) P.ctl[i] = 0u;
+        return;
+    }
+
+    // -------------------------------------------------------------------- compute warps
+    for (int k = 0;; ++k) {
+        const int s = k % kWalkStages;
+        mbar_wait(smem_u32(&bar_full[s]), (uint32_t)(k / kWalkStages) & 1u);
+        const WalkItem w = item[s];
+        if (w.level < 0) break;
+        const LevelGeom &cur = P.lv[w.level];
+        const bool has_next = w.level + 1 < P.levels;
+        const LevelGeom &nxt = P.lv[has_next ? w.level + 1 : w.level];
+        uint32_t *tile = tiles + s * kWalkStageWords;
+        if (w.edge) {
+            if (tid == 32) apron_work_fill(apron[s], cur.w, cur.h, cur.apron, w.x0, w.y0, kTileW, kTileH);
+            ComputeSync()();
+        }
+        if (has_next) tile_body<true, ComputeSync>(tile, cur, nxt, w.plane, w.x0, w.y0, tid);
+        else          tile_body<false, ComputeSync>(tile, cur, nxt, w.plane, w.x0, w.y0, tid);
+        if (w.edge)
+            apron_scatter(apron[s], reinterpret_cast<const uint8_t *>(tile), kBoxW, w.x0 - kHaloL, w.y0 - kHaloT, w.x0, kTileW, 3, cur.w, cur.h,
+                          cur.apron, cur.img + (size_t)w.plane * cur.iplane_px, cur.ipitch, tid, kWalkCompute);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(smem_u32(&bar_done[s]));      // the warp's reads of the stage and its stores are behind it
     }
 }
 
@@ -376,7 +460,7 @@ bgr2gray_kernel(const uint8_t *__restrict__ bgr, size_t bgr_pitch, uint8_t *__re
 
 }  // namespace
 
-int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron,
+int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron, int late_wait,
                      cudaStream_t stream)
 {
     const LevelGeom &cur = pyr.lv[level];
@@ -394,8 +478,8 @@ int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, c
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = has_next ? cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<true>, *map_in, cur, nxt, planes, tiles_y)
-                                   : cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<false>, *map_in, cur, nxt, planes, tiles_y);
+    const cudaError_t e = has_next ? cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<true>, *map_in, cur, nxt, planes, tiles_y, late_wait)
+                                   : cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<false>, *map_in, cur, nxt, planes, tiles_y, late_wait);
     return e == cudaSuccess ? 1 : -1;
 }
 
@@ -403,7 +487,7 @@ int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, c
 // planes.n) zeroed words, exclusively this launch's until it completes (the kernel leaves it zeroed).
 size_t walk_ctl_words(int levels, int n_planes) { return 2 + (size_t)levels * n_planes; }
 
-int launch_pyr_walk(const PyrDesc &pyr, const CUtensorMap *maps, const PlaneList &planes, unsigned *ctl, int ctas_per_sm, int sm_count,
+int launch_pyr_walk(const PyrDesc &pyr, int base, const CUtensorMap *maps, const PlaneList &planes, unsigned *ctl, int ctas_per_sm, int sm_count,
                     cudaStream_t stream)
 {
     static int occ = 0;
@@ -413,6 +497,7 @@ int launch_pyr_walk(const PyrDesc &pyr, const CUtensorMap *maps, const PlaneList
     P.levels = pyr.levels;
     P.n_planes = planes.n;
     P.ctl = ctl;
+    P.base = base;
     int begin = 0;
     for (int l = 0; l < pyr.levels; ++l) {
         P.map[l] = maps[l];
@@ -420,7 +505,7 @@ int launch_pyr_walk(const PyrDesc &pyr, const CUtensorMap *maps, const PlaneList
         P.tiles_x[l] = (pyr.lv[l].w + kTileW - 1) / kTileW;
         P.tiles[l] = P.tiles_x[l] * ((pyr.lv[l].h + kTileH - 1) / kTileH);
         P.begin[l] = begin;
-        begin += P.tiles[l] * planes.n;
+        if (l >= base) begin += P.tiles[l] * planes.n;
     }
     for (int l = pyr.levels; l <= PSNW_MAX_LEVELS; ++l) P.begin[l] = begin;
     const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : occ;

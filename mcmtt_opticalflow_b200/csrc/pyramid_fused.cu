@@ -294,8 +294,11 @@ __device__ __forceinline__ void apron_all(const uint8_t *smem, const ApronTable 
     }
 }
 
+#ifndef PSNW_FUSED_MINB
+#define PSNW_FUSED_MINB 4            // resident CTAs per SM of the 256-thread variant (half of it with 512 threads)
+#endif
 template <int NL, int TH, int NT>
-__global__ void __launch_bounds__(NT, NT <= 256 ? 4 : 2)
+__global__ void __launch_bounds__(NT, NT <= 256 ? PSNW_FUSED_MINB : PSNW_FUSED_MINB / 2)
 pyr_fused_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ FusedLevels L, const __grid_constant__ PlaneList planes)
 {
     using G = FG<NL, TH>;
@@ -340,7 +343,7 @@ pyr_fused_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant
     const int rot = (tid + NT - (n_sch % NT)) % NT;       // threads that did one Scharr item less go first
     for (int it = rot; it < n_cp; it += NT) copy_dispatch<NL, TH, 1>(smem, L, plane, it);
     PSNW_STAMP(4);
-    apron_all<NL, TH, 0, NT>(smem, aprons, L, plane, rot);
+    apron_all<NL, TH, 0, NT>(smem, aprons, L, plane, tid);
     PSNW_STAMP(5);
     if (L.late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
