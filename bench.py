@@ -382,12 +382,13 @@ class GpuRig:
         ms = sorted(a.elapsed_time(b) for a, b in ev)
         return float(np.mean(ms)) * 1e-3, float(ms[0]) * 1e-3
 
-    def time_track(self, reps=20):
+    def time_track(self, reps=20, prime=True):
         """LK kernel alone (forward+backward fused launch): the newest frame's seeds tracked into the previous frame."""
         t = self.torch
-        self.step(False)
-        if self.grid:
+        if prime:
             self.step(False)
+            if self.grid:
+                self.step(False)
         seeds = self.d_seeds[self.which]
         # pipelined: slot 0 already holds the next frame, the seeds belong to slot 1 -- exactly the next step's launch;
         # otherwise the newest frame's seeds are tracked back into the previous frame
@@ -574,20 +575,20 @@ def lk_report(rig, clocks, props):
     """The dominant kernel: live launch time, and its ARITHMETIC roofline from work counted in the run -- SURVEY 8d's model
     (template pass 441 px x 15 lane-ops, iteration 441 px x 7) x the template passes and iterations the counting build of the
     kernel reports for this very batch, over launch time x SMs x 128 lanes x clock."""
-    rig.ctx.lk_stats(True)
-    rig.time_track(reps=1)
-    st = rig.ctx.lk_stats(False)
     lk_sec, st_frac = rig.time_track()
+    rig.ctx.lk_stats(True)                       # counters zeroed; exactly ONE launch of the timed batch is counted
+    rig.time_track(reps=1, prime=False)
+    st = rig.ctx.lk_stats(False)
     solves = max(st["solves"], 1)
     mhz = ((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
-    per_solve = 441.0 * (15.0 * st["template_passes"] + 7.0 * st["iterations"]) / solves
-    lane_ops = per_solve * 2 * rig.npts          # one launch = forward + backward solve of every seed
+    lane_ops = 441.0 * (15.0 * st["template_passes"] + 7.0 * st["iterations"])      # of that one launch
     peak_ops = props.multi_processor_count * 128 * mhz * 1e6
     lk = {"kernel": "lk_w21_kernel (fwd+bwd fused, persistent warps, TMA-staged patches)", "ms": 1e3 * lk_sec,
           "lk_solves_per_s": 2 * rig.npts / lk_sec, "status_ok_frac": st_frac,
           "bound": "SM issue / ALU lanes (not HBM, not tensor) -- see DESIGN.md",
-          "counted": {"solves": st["solves"], "template_passes_per_solve": st["template_passes"] / solves,
-                      "iterations_per_solve": st["iterations"] / solves},
+          "counted": {"solves_run": st["solves"], "nominal_solves": 2 * rig.npts, "template_passes_per_solve": st["template_passes"] / solves,
+                      "iterations_per_solve": st["iterations"] / solves, "iterations_per_s": st["iterations"] / lk_sec,
+                      "note": "one launch; the backward solve of a seed the forward pass lost is not run"},
           "alg_roofline": {"bound": "alu lanes", "model": "441 x (15 x template passes + 7 x iterations) lane-ops (SURVEY 8d)",
                            "achieved": lane_ops / lk_sec / 1e12, "peak": peak_ops / 1e12, "unit": "T lane-ops/s",
                            "frac": lane_ops / lk_sec / peak_ops, "sm_mhz": mhz}}
@@ -610,6 +611,9 @@ def config_leg(wl, local, steps, peak):
         sec_e, _ = rig.timed(steps, 3, host=True)
         rig.prime(False)
         lk_sec, st_frac = rig.time_track(reps=10)
+        rig.ctx.lk_stats(True)                     # counting build of the LK kernel, ONE launch of the same batch
+        rig.time_track(reps=1, prime=False)
+        cnt = rig.ctx.lk_stats(False)
         pyr_mean, _ = rig.time_pyramid(reps=10)
         alg = rig.ctx.push_frame_bytes * ncam
         h2d, d2h = rig.e2e_bytes()
@@ -617,6 +621,12 @@ def config_leg(wl, local, steps, peak):
                 "ms_per_step": 1e3 * sec / steps, "value": rig.npts * steps / sec, "frames_per_s": ncam * steps / sec,
                 "e2e": {"value": rig.npts * steps / sec_e, "ms_per_step": 1e3 * sec_e / steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "lk_ms": 1e3 * lk_sec, "lk_solves_per_s": 2 * rig.npts / lk_sec, "status_ok_frac": st_frac,
+                "lk_counted": {"solves_run": cnt["solves"], "nominal_solves": 2 * rig.npts,
+                               "template_passes_per_nominal_solve": cnt["template_passes"] / (2.0 * rig.npts),
+                               "iterations_per_nominal_solve": cnt["iterations"] / (2.0 * rig.npts),
+                               "iterations_per_s": cnt["iterations"] / lk_sec,
+                               "note": "lk_solves_per_s counts two solves per seed; the backward solve of a seed the forward pass lost is "
+                                       "not run.  iterations_per_s compares configurations whose seeds need different numbers of iterations"},
                 "pyramid": {"isolated_ms": 1e3 * pyr_mean, "algorithmic_bytes": alg, "frac_isolated": alg / pyr_mean / 1e9 / peak},
                 "gpu_launches": int(launches)}
     finally:

@@ -21,9 +21,17 @@ namespace psnw {
 
 namespace {
 
-constexpr int kEigTW = 64, kEigTH = 16;
-constexpr int kSrcW = kEigTW + 4, kSrcH = kEigTH + 4;       // halo 2
-constexpr int kPrW = kEigTW + 2, kPrH = kEigTH + 2;         // halo 1
+// min_eig_kernel: a warp owns a strip of 120 columns and slides down kEigRows rows.  Every lane holds 4 adjacent columns as
+// one packed word per source row (lanes 0 and 31 are halo lanes: they compute products, no outputs); the words left and right
+// come from the neighbouring lanes by shuffle.  Sobel taps are dp4a dot products on the packed bytes (horizontal difference
+// (-1,0,1), horizontal smooth (1,2,1)) combined vertically in registers over a ring of three source rows; the three product
+// maps (fx*fx, fx*fy, fy*fy) of the last three rows stay in registers for the lane's 4 columns + 1 on each side (shuffled in),
+// and every output pixel adds its 3x3 products in the oracle's order (rows, then columns, starting from 0).
+// Borders: Sobel reads REFLECT_101 source pixels; the box filter reads REFLECT_101 PRODUCTS -- the product at the mirrored
+// pixel.  Computed from mirrored sources, a gradient just outside the frame equals the one at the mirrored pixel except for
+// the sign of its normal component, so the products are identical except for the sign of fx*fy: it is flipped back for
+// product rows / columns outside the frame (bit-identical, zeros included).
+constexpr int kEigWarps = 4, kEigRows = 8, kEigStripW = 120;
 
 __device__ __forceinline__ int refl_clamp(int p, int n)
 {
@@ -32,57 +40,103 @@ __device__ __forceinline__ int refl_clamp(int p, int n)
     return min(max(p, 0), n - 1);
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ int dp4a_us_d(uint32_t a, int b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// pixels c .. c+3 of a row as one word, REFLECT_101 outside [0, w)
+__device__ __forceinline__ uint32_t eig_row_word(const uint8_t *__restrict__ row, int c, int w)
+{
+    if (c >= 0 && c + 4 <= w) return __ldg(reinterpret_cast<const uint32_t *>(row + c));
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v |= (uint32_t)__ldg(row + refl_clamp(c + k, w)) << (8 * k);
+    return v;
+}
+
+__global__ void __launch_bounds__(kEigWarps * 32)
 min_eig_kernel(const uint8_t *__restrict__ img_base, int w, int h, int pitch, int plane_px, const EigList list)
 {
     const uint8_t *__restrict__ img = img_base + (size_t)list.plane[blockIdx.z] * plane_px;
     float *__restrict__ eig = list.eig[blockIdx.z];
-    __shared__ uint8_t src[kSrcH][kSrcW];
-    __shared__ float pxx[kPrH][kPrW], pxy[kPrH][kPrW], pyy[kPrH][kPrW];
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * kEigTW, y0 = blockIdx.y * kEigTH;
-
-    for (int i = tid; i < kSrcW * kSrcH; i += 256) {
-        const int sy = i / kSrcW, sx = i - sy * kSrcW;
-        src[sy][sx] = img[(size_t)refl_clamp(y0 - 2 + sy, h) * pitch + refl_clamp(x0 - 2 + sx, w)];
-    }
-    __syncthreads();
-
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x = blockIdx.x * kEigStripW + 4 * (lane - 1);            // first of the lane's 4 columns
+    const int y0 = (blockIdx.y * kEigWarps + warp) * kEigRows;            // first output row of the warp
+    if (y0 >= h) return;
+    constexpr int kDiffLo = 0x000100FF, kDiffHi = 0x0100FF00;             // (-1,0,1,0), (0,-1,0,1)
+    constexpr int kSmLo = 0x00010201, kSmHi = 0x01020100;                 // ( 1,2,1,0), (0, 1,2,1)
     const float scale = (float)(1.0 / (255.0 * 4.0 * 3.0));
-    for (int i = tid; i < kPrW * kPrH; i += 256) {
-        const int py = i / kPrW, px = i - py * kPrW;
-        // the covariance maps are image-sized and box-filtered with REFLECT_101: a product outside the frame
-        // is the product AT the mirrored pixel
-        const int X = refl_clamp(x0 - 1 + px, w), Y = refl_clamp(y0 - 1 + py, h);
-        const int sx = min(max(X - (x0 - 2), 1), kSrcW - 2), sy = min(max(Y - (y0 - 2), 1), kSrcH - 2);
-        const int gx = (src[sy - 1][sx + 1] + 2 * src[sy][sx + 1] + src[sy + 1][sx + 1]) -
-                       (src[sy - 1][sx - 1] + 2 * src[sy][sx - 1] + src[sy + 1][sx - 1]);
-        const int gy = (src[sy + 1][sx - 1] + 2 * src[sy + 1][sx] + src[sy + 1][sx + 1]) -
-                       (src[sy - 1][sx - 1] + 2 * src[sy - 1][sx] + src[sy - 1][sx + 1]);
-        const float fx = __fmul_rn((float)gx, scale), fy = __fmul_rn((float)gy, scale);
-        pxx[py][px] = __fmul_rn(fx, fx);
-        pxy[py][px] = __fmul_rn(fx, fy);
-        pyy[py][px] = __fmul_rn(fy, fy);
-    }
-    __syncthreads();
+    const bool out_lane = lane >= 1 && lane <= 30 && x < w;
+    // columns x-1 .. x+4 of the product window: those outside the frame carry a flipped fx*fy
+    bool col_out[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) col_out[i] = x - 1 + i < 0 || x - 1 + i >= w;
 
-    for (int i = tid; i < kEigTW * kEigTH; i += 256) {
-        const int oy = i / kEigTW, ox = i - oy * kEigTW;
-        const int X = x0 + ox, Y = y0 + oy;
-        if (X >= w || Y >= h) continue;
-        float a = 0.f, b = 0.f, c = 0.f;
+    int hd[3][4], hs[3][4];               // horizontal taps of the last three source rows
+    float pxx[3][6], pxy[3][6], pyy[3][6];   // products of the last three product rows, columns x-1 .. x+4
+    // source rows y0-2 .. y0+kEigRows+1 -> product rows y0-1 .. y0+kEigRows -> output rows y0 .. y0+kEigRows-1
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+    for (int rr = 0; rr < kEigRows + 4; ++rr) {
+        const int sy = y0 - 2 + rr;
+        const uint32_t wc = eig_row_word(img + (size_t)refl_clamp(sy, h) * pitch, x, w);
+        const uint32_t wp = __shfl_up_sync(0xffffffffu, wc, 1), wn = __shfl_down_sync(0xffffffffu, wc, 1);
+        const uint32_t sa = __funnelshift_r(wp, wc, 24), sb = __funnelshift_r(wc, wn, 8);     // bytes x-1 .. x+2, x+1 .. x+4
+        int *d = hd[rr % 3], *sm = hs[rr % 3];
+        d[0] = dp4a_us_d(sa, kDiffLo, 0);  d[1] = dp4a_us_d(sa, kDiffHi, 0);
+        d[2] = dp4a_us_d(sb, kDiffLo, 0);  d[3] = dp4a_us_d(sb, kDiffHi, 0);
+        sm[0] = dp4a_us_d(sa, kSmLo, 0);   sm[1] = dp4a_us_d(sa, kSmHi, 0);
+        sm[2] = dp4a_us_d(sb, kSmLo, 0);   sm[3] = dp4a_us_d(sb, kSmHi, 0);
+        if (rr < 2) continue;
+        // product row py = sy - 1 from the source rows rr-2, rr-1, rr
+        const int py = sy - 1;
+        const bool row_out = py < 0 || py >= h;
+        float *qxx = pxx[rr % 3], *qxy = pxy[rr % 3], *qyy = pyy[rr % 3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                a = __fadd_rn(a, pxx[oy + j][ox + k]);
-                b = __fadd_rn(b, pxy[oy + j][ox + k]);
-                c = __fadd_rn(c, pyy[oy + j][ox + k]);
-            }
-        a = __fmul_rn(a, 0.5f);
-        c = __fmul_rn(c, 0.5f);
-        const float d = __fsub_rn(a, c);
-        eig[(size_t)Y * pitch + X] = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(d, d), __fmul_rn(b, b))));
+        for (int i = 0; i < 4; ++i) {
+            const int gx = hd[(rr - 2) % 3][i] + 2 * hd[(rr - 1) % 3][i] + hd[rr % 3][i];
+            const int gy = hs[rr % 3][i] - hs[(rr - 2) % 3][i];
+            const float fx = __fmul_rn((float)gx, scale), fy = __fmul_rn((float)gy, scale);
+            const float xy = __fmul_rn(fx, fy);
+            qxx[i + 1] = __fmul_rn(fx, fx);
+            qxy[i + 1] = (row_out != col_out[i + 1]) ? -xy : xy;
+            qyy[i + 1] = __fmul_rn(fy, fy);
+        }
+        // columns x-1 and x+4 from the neighbouring lanes (their products carry their own column flags; the row flag is shared)
+        qxx[0] = __shfl_up_sync(0xffffffffu, qxx[4], 1);   qxx[5] = __shfl_down_sync(0xffffffffu, qxx[1], 1);
+        qxy[0] = __shfl_up_sync(0xffffffffu, qxy[4], 1);   qxy[5] = __shfl_down_sync(0xffffffffu, qxy[1], 1);
+        qyy[0] = __shfl_up_sync(0xffffffffu, qyy[4], 1);   qyy[5] = __shfl_down_sync(0xffffffffu, qyy[1], 1);
+        if (rr < 4) continue;
+        // output row oy = py - 1: product rows rr-2, rr-1, rr
+        const int oy = py - 1;
+        if (!out_lane || oy >= h) continue;
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    a = __fadd_rn(a, pxx[(rr - 2 + j) % 3][i + k]);
+                    b = __fadd_rn(b, pxy[(rr - 2 + j) % 3][i + k]);
+                    c = __fadd_rn(c, pyy[(rr - 2 + j) % 3][i + k]);
+                }
+            a = __fmul_rn(a, 0.5f);
+            c = __fmul_rn(c, 0.5f);
+            const float dd = __fsub_rn(a, c);
+            o[i] = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(dd, dd), __fmul_rn(b, b))));
+        }
+        float *dst = eig + (size_t)oy * pitch + x;
+        if (x + 4 <= w) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x + i < w) dst[i] = o[i];
+        }
     }
 }
 
@@ -508,8 +562,8 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
 int launch_min_eig(const LevelGeom &l0, const EigList &list, cudaStream_t stream)
 {
     if (list.n <= 0) return 0;
-    dim3 grid((l0.w + kEigTW - 1) / kEigTW, (l0.h + kEigTH - 1) / kEigTH, list.n);
-    min_eig_kernel<<<grid, 256, 0, stream>>>(l0.img, l0.w, l0.h, l0.pitch, l0.plane_px, list);
+    dim3 grid((l0.w + kEigStripW - 1) / kEigStripW, (l0.h + kEigWarps * kEigRows - 1) / (kEigWarps * kEigRows), list.n);
+    min_eig_kernel<<<grid, kEigWarps * 32, 0, stream>>>(l0.img, l0.w, l0.h, l0.pitch, l0.plane_px, list);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
