@@ -205,7 +205,62 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
         long long s11 = 0, s12 = 0, s22 = 0;
         {
             int x = lx0, y = ly0, q = q0;
-            if (acc32 && ipx >= 0 && ipy >= 0 && ipx + ww < L.w && ipy + wh < L.h) {
+            const int apt = L.apron;
+            if (acc32_4 && ipx >= -apt && ipy >= -apt && ipx + ww < L.w + apt && ipy + wh < L.h + apt &&
+                ipx + wp + 4 <= ipitch - L.apron_l) {
+                // Window inside the (padded) frame: four adjacent pixels per step like the iteration path below -- two aligned
+                // image words per row, funnel shifts to the window's byte phase, dp2a on the packed bytes; five derivative words
+                // per row serve the four bilinear taps; the template goes out as vectors.  The image taps of a window that leaves
+                // the frame read the REFLECT_101 apron kept in HBM; its derivative taps outside the frame are zero (OpenCV's
+                // constant border of the derivative image) and take the guarded loads.
+                const int sh8 = (ipx & 3) * 8;
+                const int wt = (w00 & 0xffff) | (w01 << 16), wb = (w10 & 0xffff) | (w11 << 16);
+                const uint8_t *base = IA + (ptrdiff_t)ipy * ipitch + (ipx - (ipx & 3));
+                int a11 = 0, a12 = 0, a22 = 0, gx = gx0, gy = gy0;
+                for (int it = tid; it < G * wh; it += kGenThreads) {
+                    const uint32_t *r0 = reinterpret_cast<const uint32_t *>(base + (ptrdiff_t)gy * ipitch + 4 * gx);
+                    const uint32_t *r1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(r0) + ipitch);
+                    const uint32_t i0 = __ldg(r0), i1 = __ldg(r0 + 1), z0 = __ldg(r1), z1 = __ldg(r1 + 1);
+                    const uint32_t t0 = __funnelshift_r(i0, i1, sh8), t4 = i1 >> sh8;          // bytes 0..3, byte 4
+                    const uint32_t u0 = __funnelshift_r(z0, z1, sh8), u4 = z1 >> sh8;
+                    const uint32_t ts = __funnelshift_r(t0, t4, 8), us = __funnelshift_r(u0, u4, 8);   // bytes 1..4
+                    int iv[4];
+                    iv[0] = dp2a_lo_su(wb, u0, dp2a_lo_su(wt, t0, 256)) >> 9; iv[1] = dp2a_lo_su(wb, us, dp2a_lo_su(wt, ts, 256)) >> 9;
+                    iv[2] = dp2a_hi_su(wb, u0, dp2a_hi_su(wt, t0, 256)) >> 9; iv[3] = dp2a_hi_su(wb, us, dp2a_hi_su(wt, ts, 256)) >> 9;
+                    const int X = ipx + 4 * gx, Y = ipy + gy;
+                    const uint32_t *d0 = reinterpret_cast<const uint32_t *>(DA) + (ptrdiff_t)Y * L.pitch + X, *d1 = d0 + L.pitch;
+                    uint32_t e0[5], e1[5];
+                    if (X >= 0 && X + 4 < L.w && Y >= 0 && Y + 1 < L.h) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) { e0[k] = __ldg(d0 + k); e1[k] = __ldg(d1 + k); }
+                    } else {
+                        const bool y0in = (unsigned)Y < (unsigned)L.h, y1in = (unsigned)(Y + 1) < (unsigned)L.h;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            const bool xin = (unsigned)(X + k) < (unsigned)L.w;
+                            e0[k] = (xin && y0in) ? __ldg(d0 + k) : 0u;
+                            e1[k] = (xin && y1in) ? __ldg(d1 + k) : 0u;
+                        }
+                    }
+                    const int valid = ww - 4 * gx;           // >= 4 except in the last group of a row
+                    int ixv[4], iyv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        int ix = (sext16(e0[k]) * w00 + sext16(e0[k + 1]) * w01 + sext16(e1[k]) * w10 + sext16(e1[k + 1]) * w11 + (1 << 13)) >> 14;
+                        int iy = (((int)e0[k] >> 16) * w00 + ((int)e0[k + 1] >> 16) * w01 + ((int)e1[k] >> 16) * w10 + ((int)e1[k + 1] >> 16) * w11 + (1 << 13)) >> 14;
+                        if (k >= valid) { ix = 0; iy = 0; }  // padding columns of the template row: never part of a sum
+                        ixv[k] = ix; iyv[k] = iy;
+                        a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                    }
+                    const int q4 = gy * wp + 4 * gx;
+                    *reinterpret_cast<uint2 *>(Iw + q4) = make_uint2((uint32_t)(iv[0] & 0xffff) | ((uint32_t)iv[1] << 16), (uint32_t)(iv[2] & 0xffff) | ((uint32_t)iv[3] << 16));
+                    *reinterpret_cast<uint4 *>(dIw + q4) = make_uint4((uint32_t)(ixv[0] & 0xffff) | ((uint32_t)iyv[0] << 16), (uint32_t)(ixv[1] & 0xffff) | ((uint32_t)iyv[1] << 16),
+                                                                     (uint32_t)(ixv[2] & 0xffff) | ((uint32_t)iyv[2] << 16), (uint32_t)(ixv[3] & 0xffff) | ((uint32_t)iyv[3] << 16));
+                    gx += sgx; gy += sgy;
+                    if (gx >= G) { gx -= G; gy++; }
+                }
+                s11 = a11; s12 = a12; s22 = a22;
+            } else if (acc32 && ipx >= 0 && ipy >= 0 && ipx + ww < L.w && ipy + wh < L.h) {
                 // window (plus its bilinear ring) inside the frame: no border arithmetic, 32-bit partial sums
                 int a11 = 0, a12 = 0, a22 = 0;
                 // running offsets instead of a 2-D address per pixel: one stride of kGenThreads pixels, minus a row wrap
@@ -284,27 +339,48 @@ __device__ void solve_generic(const LkParams &P, int plane_a, int plane_b, int w
                 const int sh8 = (inx & 3) * 8;
                 const int wt = (w00 & 0xffff) | (w01 << 16), wb = (w10 & 0xffff) | (w11 << 16);
                 const uint8_t *base = JB + (ptrdiff_t)iny * ipitch + (inx - (inx & 3));
-                int a1 = 0, a2 = 0, gx = gx0, gy = gy0;
-                for (int it = tid; it < G * wh; it += kGenThreads) {
-                    const uint32_t *r0 = reinterpret_cast<const uint32_t *>(base + (ptrdiff_t)gy * ipitch + 4 * gx);
-                    const uint32_t *r1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(r0) + ipitch);
-                    const uint32_t w0 = __ldg(r0), w1 = __ldg(r0 + 1), z0 = __ldg(r1), z1 = __ldg(r1 + 1);
-                    const uint32_t t0 = __funnelshift_r(w0, w1, sh8), t4 = w1 >> sh8;          // bytes 0..3, byte 4
+                // Running offsets instead of a 2-D address per group (the template offset of group `it` is 4 * it: rows are padded
+                // to whole groups), and TWO groups per trip with all eight image words requested before the first is used: the
+                // loads come from L1 / L2 every iteration and their latency was the kernel's largest stall.
+                int a1 = 0, a2 = 0, gx = gx0;
+                int oj = gy0 * ipitch + 4 * gx0;
+                const int sj = sgy * ipitch + 4 * sgx, wrapj = ipitch - 4 * G, n_groups = G * wh;
+                auto group = [&](uint32_t i0, uint32_t i1, uint32_t z0, uint32_t z1, int it, int gxx) {
+                    const uint32_t t0 = __funnelshift_r(i0, i1, sh8), t4 = i1 >> sh8;          // bytes 0..3, byte 4
                     const uint32_t u0 = __funnelshift_r(z0, z1, sh8), u4 = z1 >> sh8;
                     const uint32_t ts = __funnelshift_r(t0, t4, 8), us = __funnelshift_r(u0, u4, 8);   // bytes 1..4
                     const int v0 = dp2a_lo_su(wb, u0, dp2a_lo_su(wt, t0, 256)), v1 = dp2a_lo_su(wb, us, dp2a_lo_su(wt, ts, 256));
                     const int v2 = dp2a_hi_su(wb, u0, dp2a_hi_su(wt, t0, 256)), v3 = dp2a_hi_su(wb, us, dp2a_hi_su(wt, ts, 256));
-                    const int q4 = gy * wp + 4 * gx;
-                    const uint2 iw = *reinterpret_cast<const uint2 *>(Iw + q4);
-                    const uint4 dw = *reinterpret_cast<const uint4 *>(dIw + q4);
+                    const uint2 iw = *reinterpret_cast<const uint2 *>(Iw + 4 * it);
+                    const uint4 dw = *reinterpret_cast<const uint4 *>(dIw + 4 * it);
                     int d0 = (v0 >> 9) - sext16(iw.x), d1 = (v1 >> 9) - ((int)iw.x >> 16);
                     int d2 = (v2 >> 9) - sext16(iw.y), d3 = (v3 >> 9) - ((int)iw.y >> 16);
-                    const int valid = ww - 4 * gx;           // >= 4 except in the last group of a row
+                    const int valid = ww - 4 * gxx;          // >= 4 except in the last group of a row
                     if (valid < 4) { d3 = 0; if (valid < 3) d2 = 0; if (valid < 2) d1 = 0; }
                     a1 += d0 * sext16(dw.x) + d1 * sext16(dw.y) + d2 * sext16(dw.z) + d3 * sext16(dw.w);
                     a2 += d0 * ((int)dw.x >> 16) + d1 * ((int)dw.y >> 16) + d2 * ((int)dw.z >> 16) + d3 * ((int)dw.w >> 16);
-                    gx += sgx; gy += sgy;
-                    if (gx >= G) { gx -= G; gy++; }
+                };
+                int it = tid;
+                for (; it + kGenThreads < n_groups; it += 2 * kGenThreads) {
+                    const uint32_t *r0 = reinterpret_cast<const uint32_t *>(base + oj);
+                    const uint32_t *r1 = reinterpret_cast<const uint32_t *>(base + oj + ipitch);
+                    const int gxa = gx;
+                    gx += sgx; oj += sj;
+                    if (gx >= G) { gx -= G; oj += wrapj; }
+                    const uint32_t *s0 = reinterpret_cast<const uint32_t *>(base + oj);
+                    const uint32_t *s1 = reinterpret_cast<const uint32_t *>(base + oj + ipitch);
+                    const int gxb = gx;
+                    gx += sgx; oj += sj;
+                    if (gx >= G) { gx -= G; oj += wrapj; }
+                    const uint32_t a0 = __ldg(r0), a1w = __ldg(r0 + 1), b0 = __ldg(r1), b1w = __ldg(r1 + 1);
+                    const uint32_t c0 = __ldg(s0), c1w = __ldg(s0 + 1), e0 = __ldg(s1), e1w = __ldg(s1 + 1);
+                    group(a0, a1w, b0, b1w, it, gxa);
+                    group(c0, c1w, e0, e1w, it + kGenThreads, gxb);
+                }
+                if (it < n_groups) {
+                    const uint32_t *r0 = reinterpret_cast<const uint32_t *>(base + oj);
+                    const uint32_t *r1 = reinterpret_cast<const uint32_t *>(base + oj + ipitch);
+                    group(__ldg(r0), __ldg(r0 + 1), __ldg(r1), __ldg(r1 + 1), it, gx);
                 }
                 sb1 = a1; sb2 = a2;
             } else if (acc32 && inx >= -ap && iny >= -ap && inx + ww < L.w + ap && iny + wh < L.h + ap) {
@@ -723,6 +799,8 @@ __device__ __forceinline__ void solve_w21(const LkParams &P, int plane_a, int pl
                 }
             }
             if (!R.two) { b1[1] = 0; b2[1] = 0; }
+            // (a vote-guarded single REDUX per sum -- all partials below 2^26 -- was measured: 0.2555 against 0.2513 ms per c2
+            // launch, the vote and the branch cost more than the second REDUX and conversion)
             const float sb1 = sum_to_float(warp_sum_split(b1[0] + b1[1])), sb2 = sum_to_float(warp_sum_split(b2[0] + b2[1]));
             if (lk_step(P, sb1, sb2, A11, A12, A22, Dinv, half, half, j, nx, ny, pdx, pdy, next_x, next_y)) break;
         }

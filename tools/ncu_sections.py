@@ -29,11 +29,14 @@ for r in rows:
         line = int(r[0])
         key = next((nm for (f, lo, hi, nm) in ranges if f == fname and lo <= line <= hi), fname)
         acc[key] += n
-        per_line.append((n, fname, line, r[1].strip()[:100]))
+        per_line.append((n, fname, line, r[1].strip()[:100], key == fname))
 tot = sum(acc.values())
 print("total warp-instructions", tot)
 for k, v in acc.most_common():
     print("%-28s %12d %5.1f%%" % (k, v, 100.0 * v / tot))
 print("-- top lines")
-for n, f, l, s in sorted(per_line, reverse=True)[:25]:
+for n, f, l, s, un in sorted(per_line, reverse=True)[:25]:
+    print("%9d %5.1f%% %s:%d  %s" % (n, 100.0 * n / tot, f, l, s))
+print("-- top lines outside every named range")
+for n, f, l, s, un in [x for x in sorted(per_line, reverse=True) if x[4]][:25]:
     print("%9d %5.1f%% %s:%d  %s" % (n, 100.0 * n / tot, f, l, s))
