@@ -72,7 +72,16 @@ enum { PSNW_MEM_HOST = 0, PSNW_MEM_PINNED = 1, PSNW_MEM_DEVICE = 2 };
 
 /* psnw_box_update estimators */
 enum {
-    PSNW_BOX_REFERENCE = 0 /* LocalSearchKLT semantics, Tracker2D.cpp:452-554 (parity-graded) */
+    PSNW_BOX_REFERENCE = 0, /* LocalSearchKLT semantics, Tracker2D.cpp:452-554 (parity-graded) */
+    /* Median flow (Kalal et al.; the "median-displacement/scale reduction" of north_star).  NOT what
+     * the reference runs, so it has no reference parity; its oracle is oracle/klt_oracle.c::psnwo_box_medianflow (bit-exact).
+     *   V = the target's points with status != 0 (all when status is NULL), in index order, n = |V|;  n == 0: box unchanged.
+     *   d_i = (double)cur_i - (double)pre_i.   median of m values = middle one (m odd) or mean of the two middle ones.
+     *   (mdx, mdy) = per-axis medians of d_i;  res_i = |d_i - (mdx, mdy)|;  inlier <=> res_i <= median(res).
+     *   scale s = median of |cur_a - cur_b| / |pre_a - pre_b| over the pairs a < b with |pre_a - pre_b| > 0 among S = V (n <= 128)
+     *   or S = { V[floor(k n / 128)], k = 0..127 } (n > 128);  s = 1 without such a pair.
+     *   box' = { x + mdx - (s-1) w / 2,  y + mdy - (s-1) h / 2,  w s,  h s }. */
+    PSNW_BOX_MEDIANFLOW = 1
 };
 
 #define PSNW_MAX_LEVELS 8

@@ -1100,14 +1100,14 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
     if (!ctx) return PSNW_EARG;
     if (int rc_enter = enter(ctx)) return rc_enter;
     if (n_targets == 0) return PSNW_OK;
-    if (n_targets < 0 || !boxes_in || !target_offsets || !boxes_out || !inlier_mask || !inlier_counts || mode != PSNW_BOX_REFERENCE)
+    if (n_targets < 0 || !boxes_in || !target_offsets || !boxes_out || !inlier_mask || !inlier_counts || (mode != PSNW_BOX_REFERENCE && mode != PSNW_BOX_MEDIANFLOW))
         return fail(ctx, PSNW_EARG, "psnw_box_update arguments");
     if (n_targets > ctx->p.max_targets) return fail(ctx, PSNW_ENOMEM, "psnw_box_update: max_targets exceeded");
     mem_flags &= 0xff;
     int r;
     if (mem_flags == PSNW_MEM_DEVICE) {
         r = launch_box_update(boxes_in, n_targets, reinterpret_cast<const float2 *>(pre_xy), reinterpret_cast<const float2 *>(cur_xy),
-                              status, target_offsets, boxes_out, inlier_mask, inlier_counts, PSNW_MAX_PTS_PER_TARGET, ctx->stream);
+                              status, target_offsets, boxes_out, inlier_mask, inlier_counts, PSNW_MAX_PTS_PER_TARGET, ctx->stream, mode);
         if (r < 0) return fail(ctx, PSNW_ECUDA, "box_update_kernel launch", cudaGetLastError());
         ctx->launches += r;
         return PSNW_OK;
@@ -1139,7 +1139,7 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
             if (d_st) memcpy(mirror(ctx, s, d_st), status, n_pts);
         }
         CK(cudaMemcpyAsync(ctx->arena.p, s->h, ctx->arena_off, cudaMemcpyHostToDevice, ctx->stream));
-        r = launch_box_update(d_in, n_targets, d_pre, d_cur, d_st, d_off, d_out, d_mask, d_cnt, max_per, ctx->stream);
+        r = launch_box_update(d_in, n_targets, d_pre, d_cur, d_st, d_off, d_out, d_mask, d_cnt, max_per, ctx->stream, mode);
         if (r < 0) return fail(ctx, PSNW_ECUDA, "box_update_kernel launch", cudaGetLastError());
         ctx->launches += r;
         CK(cudaMemcpyAsync(s->h, ctx->arena.p, ctx->arena_off, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1156,7 +1156,7 @@ int psnw_box_update(psnw_ctx *ctx, const double *boxes_in, int n_targets, const 
         CK(cudaMemcpyAsync(d_cur, cur_xy, sizeof(float2) * n_pts, cudaMemcpyHostToDevice, ctx->stream));
         if (d_st) CK(cudaMemcpyAsync(d_st, status, n_pts, cudaMemcpyHostToDevice, ctx->stream));
     }
-    r = launch_box_update(d_in, n_targets, d_pre, d_cur, d_st, d_off, d_out, d_mask, d_cnt, max_per, ctx->stream);
+    r = launch_box_update(d_in, n_targets, d_pre, d_cur, d_st, d_off, d_out, d_mask, d_cnt, max_per, ctx->stream, mode);
     if (r < 0) return fail(ctx, PSNW_ECUDA, "box_update_kernel launch", cudaGetLastError());
     ctx->launches += r;
     CK(cudaMemcpyAsync(boxes_out, d_out, sizeof(double) * 4 * n_targets, cudaMemcpyDeviceToHost, ctx->stream));

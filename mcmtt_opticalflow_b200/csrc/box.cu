@@ -344,17 +344,198 @@ int launch_flow_majority(const float2 *pts, const int *offsets, int n_trk, const
 }
 
 // opt-in shared-memory sizes are a per-device attribute: psnw_create calls this for the context's device
+// ------------------------------------------------------------------------------------------------------------------
+// PSNW_BOX_MEDIANFLOW: median displacement + median pairwise-distance ratio (Kalal, Mikolajczyk, Matas: "Forward-Backward
+// Error", the estimator north_star names).  Not what the reference runs (LocalSearchKLT above is),
+// so it has no reference parity: its oracle is oracle/klt_oracle.c::psnwo_box_medianflow, bit for bit.  Definition in
+// include/psnw_klt.h.  One CTA per target; every median is an exact order statistic found by an 8-pass radix select over
+// order-preserving 64-bit keys of the doubles in shared memory (no sort).
+constexpr int kMfThreads = 256;
+constexpr int kMfPairPts = 128;                                // the scale uses at most this many (evenly strided) points
+constexpr int kMfMaxKeys = kMfPairPts * (kMfPairPts - 1) / 2;  // 8128 pairs  (> kMaxPts)
+
+__device__ __forceinline__ unsigned long long mf_key(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double mf_val(unsigned long long k)
+{
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
+// k-th smallest (0-based) of keys[0..n): block-wide radix select, 8 bits per pass from the top.  All threads return it.
+__device__ unsigned long long mf_select(const unsigned long long *keys, int n, int k, int *hist, int *ctl, int tid)
+{
+    unsigned long long prefix = 0;
+#pragma unroll 1
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += kMfThreads) {
+            const unsigned long long key = keys[i];
+            if (shift == 56 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(int)((key >> shift) & 255u)], 1);
+        }
+        __syncthreads();
+        // exclusive prefix of the 256 bins (one per thread): warp scan + the warps' totals
+        const int c = hist[tid];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((tid & 31) >= o) incl += v;
+        }
+        if ((tid & 31) == 31) ctl[2 + (tid >> 5)] = incl;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < (tid >> 5); ++w) before += ctl[2 + w];
+        const int excl = before + incl - c;
+        if (k >= excl && k < excl + c) { ctl[0] = tid; ctl[1] = k - excl; }
+        __syncthreads();
+        prefix |= (unsigned long long)ctl[0] << shift;
+        k = ctl[1];
+        __syncthreads();
+    }
+    return prefix;
+}
+
+// median of n keys: the middle one, or the mean of the two middle ones
+__device__ double mf_median(const unsigned long long *keys, int n, int *hist, int *ctl, int tid)
+{
+    const double hi = mf_val(mf_select(keys, n, n >> 1, hist, ctl, tid));
+    if (n & 1) return hi;
+    const double lo = mf_val(mf_select(keys, n, (n >> 1) - 1, hist, ctl, tid));
+    return __dmul_rn(__dadd_rn(lo, hi), 0.5);
+}
+
+__global__ void __launch_bounds__(kMfThreads)
+box_medianflow_kernel(const double *__restrict__ boxes_in, const float2 *__restrict__ pre, const float2 *__restrict__ cur,
+                      const uint8_t *__restrict__ status, const int *__restrict__ offsets,
+                      double *__restrict__ boxes_out, uint8_t *__restrict__ mask, int *__restrict__ counts, int cap)
+{
+    extern __shared__ __align__(16) unsigned char box_smem[];
+    __shared__ int hist[256], ctl[2 + kMfThreads / 32], s_n, s_pairs, s_inl;
+    __shared__ double s_pts[kMfPairPts][4];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(box_smem);              // kMfMaxKeys
+    unsigned short *vidx = reinterpret_cast<unsigned short *>(keys + kMfMaxKeys);              // cap
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int beg = offsets[t], end = offsets[t + 1];
+    const int n_all = min(max(end - beg, 0), cap);
+    const double bx = boxes_in[4 * t], by = boxes_in[4 * t + 1], bw = boxes_in[4 * t + 2], bh = boxes_in[4 * t + 3];
+    if (tid == 0) { s_n = 0; s_pairs = 0; s_inl = 0; }
+    for (int i = tid; i < end - beg; i += kMfThreads) mask[beg + i] = 0;
+    __syncthreads();
+
+    // valid points in index order: chunks of 256 in turn, ballot-ordered inside a chunk
+    for (int i0 = 0; i0 < n_all; i0 += kMfThreads) {
+        const int i = i0 + tid;
+        const bool valid = i < n_all && (status ? status[beg + i] != 0 : true);
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0) ctl[2 + (tid >> 5)] = __popc(vm);
+        __syncthreads();
+        int before = s_n;
+        for (int w = 0; w < (tid >> 5); ++w) before += ctl[2 + w];
+        if (valid) vidx[before + __popc(vm & ((1u << lane) - 1u))] = (unsigned short)i;
+        __syncthreads();
+        if (tid == 0) { int tot = 0; for (int w = 0; w < kMfThreads / 32; ++w) tot += ctl[2 + w]; s_n += tot; }
+        __syncthreads();
+    }
+    const int n = s_n;
+    if (n == 0) {
+        if (tid == 0) {
+            boxes_out[4 * t] = bx; boxes_out[4 * t + 1] = by; boxes_out[4 * t + 2] = bw; boxes_out[4 * t + 3] = bh;
+            counts[t] = 0;
+        }
+        return;
+    }
+    // median displacement per axis
+    for (int j = tid; j < n; j += kMfThreads) {
+        const int i = beg + vidx[j];
+        keys[j] = mf_key(__dsub_rn((double)cur[i].x, (double)pre[i].x));
+    }
+    __syncthreads();
+    const double mdx = mf_median(keys, n, hist, ctl, tid);
+    for (int j = tid; j < n; j += kMfThreads) {
+        const int i = beg + vidx[j];
+        keys[j] = mf_key(__dsub_rn((double)cur[i].y, (double)pre[i].y));
+    }
+    __syncthreads();
+    const double mdy = mf_median(keys, n, hist, ctl, tid);
+    // residuals to the median displacement, their median, the inlier mask
+    for (int j = tid; j < n; j += kMfThreads) {
+        const int i = beg + vidx[j];
+        const double rx = __dsub_rn(__dsub_rn((double)cur[i].x, (double)pre[i].x), mdx);
+        const double ry = __dsub_rn(__dsub_rn((double)cur[i].y, (double)pre[i].y), mdy);
+        keys[j] = mf_key(sqrt(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry))));
+    }
+    __syncthreads();
+    const double mres = mf_median(keys, n, hist, ctl, tid);
+    int inl = 0;
+    for (int j = tid; j < n; j += kMfThreads) {
+        if (mf_val(keys[j]) <= mres) { mask[beg + vidx[j]] = 1; ++inl; }
+    }
+    if (inl) atomicAdd(&s_inl, inl);
+    __syncthreads();
+    // scale: median ratio of pairwise distances over at most kMfPairPts evenly strided valid points
+    const int ns = min(n, kMfPairPts);
+    if (tid < ns) {
+        const int j = n <= kMfPairPts ? tid : (int)(((long long)tid * n) / kMfPairPts);
+        const int i = beg + vidx[j];
+        s_pts[tid][0] = (double)pre[i].x; s_pts[tid][1] = (double)pre[i].y;
+        s_pts[tid][2] = (double)cur[i].x; s_pts[tid][3] = (double)cur[i].y;
+    }
+    __syncthreads();
+    const int n_pairs = ns * (ns - 1) / 2;
+    int good = 0;
+    for (int p = tid; p < n_pairs; p += kMfThreads) {
+        // pair p -> (a, b), a < b, row-major over the strict upper triangle
+        int a = (int)((2.0 * ns - 1.0 - sqrt((2.0 * ns - 1.0) * (2.0 * ns - 1.0) - 8.0 * p)) * 0.5);
+        while (a * (2 * ns - a - 1) / 2 > p) --a;
+        while ((a + 1) * (2 * ns - a - 2) / 2 <= p) ++a;
+        const int b = a + 1 + (p - a * (2 * ns - a - 1) / 2);
+        const double px = __dsub_rn(s_pts[a][0], s_pts[b][0]), py = __dsub_rn(s_pts[a][1], s_pts[b][1]);
+        const double cx = __dsub_rn(s_pts[a][2], s_pts[b][2]), cy = __dsub_rn(s_pts[a][3], s_pts[b][3]);
+        const double dp = sqrt(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)));
+        const double dc = sqrt(__dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy)));
+        if (dp > 0.0) { keys[p] = mf_key(__ddiv_rn(dc, dp)); ++good; }
+        else          keys[p] = ~0ull;                        // coincident source points: sorts last, never counted
+    }
+    if (good) atomicAdd(&s_pairs, good);
+    __syncthreads();
+    const int np = s_pairs;
+    double scale = 1.0;
+    if (np > 0) {
+        // the np valid keys are the np smallest of the array: their median = order statistics np/2 (and np/2 - 1) of the whole
+        const double hi = mf_val(mf_select(keys, n_pairs, np >> 1, hist, ctl, tid));
+        scale = (np & 1) ? hi : __dmul_rn(__dadd_rn(mf_val(mf_select(keys, n_pairs, (np >> 1) - 1, hist, ctl, tid)), hi), 0.5);
+    }
+    if (tid == 0) {
+        const double g = __dmul_rn(0.5, __dsub_rn(scale, 1.0));
+        boxes_out[4 * t] = __dsub_rn(__dadd_rn(bx, mdx), __dmul_rn(g, bw));
+        boxes_out[4 * t + 1] = __dsub_rn(__dadd_rn(by, mdy), __dmul_rn(g, bh));
+        boxes_out[4 * t + 2] = __dmul_rn(bw, scale);
+        boxes_out[4 * t + 3] = __dmul_rn(bh, scale);
+        counts[t] = s_inl;
+    }
+}
+
 int configure_box_kernels()
 {
+    if (cudaFuncSetAttribute(box_medianflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMfMaxKeys * 8 + kMaxPts * 2) != cudaSuccess) return -1;
     return cudaFuncSetAttribute(box_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPts * 20 + 16) == cudaSuccess ? 0 : -1;
 }
 
 int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
                       const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,
-                      int *counts, int max_pts_per_target, cudaStream_t stream)
+                      int *counts, int max_pts_per_target, cudaStream_t stream, int mode)
 {
     if (n_targets <= 0) return 0;
     const int cap = std::min(std::max(max_pts_per_target, 1), kMaxPts);
+    if (mode == PSNW_BOX_MEDIANFLOW) {
+        box_medianflow_kernel<<<n_targets, kMfThreads, (size_t)kMfMaxKeys * 8 + (size_t)cap * 2, stream>>>(boxes_in, pre, cur, status, offsets,
+                                                                                                         boxes_out, mask, counts, cap);
+        return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    }
     const size_t smem = (size_t)cap * 20 + 16;
     box_update_kernel<<<n_targets, kBoxThreads, smem, stream>>>(boxes_in, pre, cur, status, offsets, boxes_out, mask, counts, cap);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

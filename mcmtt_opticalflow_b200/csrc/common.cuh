@@ -114,7 +114,7 @@ int lk_w21_resident_ctas(int max_per_sm);   // CTAs of the persistent 21x21 kern
 int launch_lk(const LkParams &P, int all_21x21, int max_win_px, int resident_ctas, cudaStream_t stream);
 int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, const float2 *cur,
                       const uint8_t *status, const int *offsets, double *boxes_out, uint8_t *mask,
-                      int *counts, int max_pts_per_target, cudaStream_t stream);
+                      int *counts, int max_pts_per_target, cudaStream_t stream, int mode = PSNW_BOX_REFERENCE);
 int launch_chain_init(float2 *pts, const int *counts, int n_targets, int cap, uint8_t *live, int *tgt, int *offsets, int *alive,
                       int *steps_done, cudaStream_t stream);
 int launch_chain_compact(const float2 *tracked, const uint8_t *mask, const int *n_inl, const double *box_step, int n_targets, int cap,

@@ -23,6 +23,7 @@ MEM_HOST, MEM_PINNED, MEM_DEVICE = 0, 1, 2
 MEM_OVERLAP = 0x100
 PUSH_EIG = 0x200
 BOX_REFERENCE = 0
+BOX_MEDIANFLOW = 1
 _ERR = {EARG: "PSNW_EARG", ECUDA: "PSNW_ECUDA", ENOMEM: "PSNW_ENOMEM", ESTATE: "PSNW_ESTATE"}
 
 
@@ -337,8 +338,8 @@ class KLTContext:
             a.out_xy, a.status, a.err, a.fb_err = _ptr(j["out"]), _ptr(j["status"]), _ptr(j["err"]), _ptr(j.get("fb_err"))
         self._ck(self.lib.psnw_klt_track_batch(self._h, arr, len(jobs), mem))
 
-    def box_update(self, boxes, pre, cur, offsets, status=None):
-        """-> (boxes_out f64 [n,4], inlier_mask u8 [n_pts], inlier_counts i32 [n])."""
+    def box_update(self, boxes, pre, cur, offsets, status=None, mode=None):
+        """-> (boxes_out f64 [n,4], inlier_mask u8 [n_pts], inlier_counts i32 [n]).  mode: BOX_REFERENCE (default) / BOX_MEDIANFLOW"""
         boxes = np.ascontiguousarray(boxes, np.float64).reshape(-1, 4)
         pre = np.ascontiguousarray(pre, np.float32).reshape(-1, 2)
         cur = np.ascontiguousarray(cur, np.float32).reshape(-1, 2)
@@ -349,7 +350,7 @@ class KLTContext:
         mask = np.zeros(max(pre.shape[0], 1), np.uint8)
         counts = np.zeros(max(n, 1), np.int32)
         self._ck(self.lib.psnw_box_update(self._h, _ptr(boxes), n, _ptr(pre), _ptr(cur), _ptr(st), _ptr(offsets),
-                                          BOX_REFERENCE, _ptr(out), _ptr(mask), _ptr(counts), MEM_HOST))
+                                          BOX_REFERENCE if mode is None else mode, _ptr(out), _ptr(mask), _ptr(counts), MEM_HOST))
         return out, mask[:pre.shape[0]], counts[:n]
 
     def points_in_boxes(self, pts, tracker_offsets, det_boxes):

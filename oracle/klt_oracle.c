@@ -364,6 +364,83 @@ PSNWO_API void psnwo_flow_majority(const float *pts, const int *offsets, int n_t
 /*     writes ascending original indices to inlier_idx.  `valid` (may be NULL) restates the forward   */
 /*     caller's status filter (:883-888); the backward caller passes every point (:787).              */
 /* ------------------------------------------------------------------------------------------------ */
+/* ---- PSNW_BOX_MEDIANFLOW (include/psnw_klt.h): median displacement + median pairwise-distance ratio.  Not reference code
+ * (the reference runs LocalSearchKLT, below): this restatement IS the definition the CUDA kernel is checked against.  Medians
+ * are order statistics of the doubles under the total order of their IEEE bit patterns (-0 < +0), so that the result does
+ * not depend on a sort's handling of equal values. ---- */
+static unsigned long long mf_key(double v)
+{
+    unsigned long long b;
+    memcpy(&b, &v, 8);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+static double mf_val(unsigned long long k)
+{
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+}
+static int cmp_u64(const void *a, const void *b)
+{
+    const unsigned long long x = *(const unsigned long long *)a, y = *(const unsigned long long *)b;
+    return (x > y) - (x < y);
+}
+static double mf_median(unsigned long long *keys, int n)        /* sorts keys */
+{
+    qsort(keys, (size_t)n, sizeof(unsigned long long), cmp_u64);
+    if (n & 1) return mf_val(keys[n >> 1]);
+    return (mf_val(keys[(n >> 1) - 1]) + mf_val(keys[n >> 1])) * 0.5;
+}
+
+PSNWO_API int psnwo_box_medianflow(const double *box_in, const float *pre, const float *cur, const uint8_t *valid, int n_all,
+                                   double *box_out, uint8_t *inlier_mask)
+{
+    enum { PAIR_PTS = 128 };
+    int n = 0, inl = 0;
+    int *vidx = (int *)malloc(sizeof(int) * (size_t)(n_all + 1));
+    unsigned long long *keys = (unsigned long long *)malloc(sizeof(unsigned long long) * (size_t)(n_all + PAIR_PTS * PAIR_PTS));
+    double *res = (double *)malloc(sizeof(double) * (size_t)(n_all + 1));
+    for (int i = 0; i < n_all; ++i) {
+        inlier_mask[i] = 0;
+        if (!valid || valid[i]) vidx[n++] = i;
+    }
+    memcpy(box_out, box_in, sizeof(double) * 4);
+    if (n == 0) { free(vidx); free(keys); free(res); return 0; }
+    for (int j = 0; j < n; ++j) keys[j] = mf_key((double)cur[2 * vidx[j]] - (double)pre[2 * vidx[j]]);
+    const double mdx = mf_median(keys, n);
+    for (int j = 0; j < n; ++j) keys[j] = mf_key((double)cur[2 * vidx[j] + 1] - (double)pre[2 * vidx[j] + 1]);
+    const double mdy = mf_median(keys, n);
+    for (int j = 0; j < n; ++j) {
+        const int i = vidx[j];
+        const double rx = ((double)cur[2 * i] - (double)pre[2 * i]) - mdx, ry = ((double)cur[2 * i + 1] - (double)pre[2 * i + 1]) - mdy;
+        res[j] = sqrt(rx * rx + ry * ry);
+        keys[j] = mf_key(res[j]);
+    }
+    const double mres = mf_median(keys, n);
+    for (int j = 0; j < n; ++j)
+        if (res[j] <= mres) { inlier_mask[vidx[j]] = 1; ++inl; }
+    /* scale */
+    const int ns = n < PAIR_PTS ? n : PAIR_PTS;
+    int np = 0;
+    for (int a = 0; a < ns; ++a)
+        for (int b = a + 1; b < ns; ++b) {
+            const int ia = vidx[n <= PAIR_PTS ? a : (int)(((long long)a * n) / PAIR_PTS)], ib = vidx[n <= PAIR_PTS ? b : (int)(((long long)b * n) / PAIR_PTS)];
+            const double px = (double)pre[2 * ia] - (double)pre[2 * ib], py = (double)pre[2 * ia + 1] - (double)pre[2 * ib + 1];
+            const double cx = (double)cur[2 * ia] - (double)cur[2 * ib], cy = (double)cur[2 * ia + 1] - (double)cur[2 * ib + 1];
+            const double dp = sqrt(px * px + py * py), dc = sqrt(cx * cx + cy * cy);
+            if (dp > 0.0) keys[np++] = mf_key(dc / dp);
+        }
+    const double s = np > 0 ? mf_median(keys, np) : 1.0;
+    const double g = 0.5 * (s - 1.0);
+    box_out[0] = (box_in[0] + mdx) - g * box_in[2];
+    box_out[1] = (box_in[1] + mdy) - g * box_in[3];
+    box_out[2] = box_in[2] * s;
+    box_out[3] = box_in[3] * s;
+    free(vidx); free(keys); free(res);
+    return inl;
+}
+
 static int cmp_double(const void *a, const void *b)
 {
     double x = *(const double *)a, y = *(const double *)b;

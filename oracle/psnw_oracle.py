@@ -137,6 +137,21 @@ def local_search_klt(box, pre, cur, valid=None):
     return out, idx[:k].copy()
 
 
+def box_medianflow(box, pre, cur, valid=None):
+    """PSNW_BOX_MEDIANFLOW (include/psnw_klt.h) -> (new box float64[4], inlier mask uint8[n])."""
+    box = np.ascontiguousarray(box, np.float64).reshape(4)
+    pre = np.ascontiguousarray(pre, np.float32).reshape(-1, 2)
+    cur = np.ascontiguousarray(cur, np.float32).reshape(-1, 2)
+    n = pre.shape[0]
+    out = np.zeros(4, np.float64)
+    mask = np.zeros(max(n, 1), np.uint8)
+    v = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+    f = lib().psnwo_box_medianflow
+    f.restype = C.c_int
+    f(_p(box), _p(pre), _p(cur), _p(v) if v is not None else None, C.c_int(n), _p(out), _p(mask))
+    return out, mask[:n].copy()
+
+
 def flow_majority(pts, tracker_offsets, tracker_boxes, tracker_ok, det_boxes, ratio=0.5):
     """Optical-flow majority check (Tracker2D.cpp:931-944, :981-1022) -> (counts int32 [n_det, n_trk], wipe uint8 [n_det])."""
     pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)

@@ -93,3 +93,25 @@ def test_local_search_klt_properties(oracle):
     # empty input
     nb6, inl6 = oracle.local_search_klt(box, np.zeros((0, 2), np.float32), np.zeros((0, 2), np.float32))
     assert np.array_equal(nb6, box) and len(inl6) == 0
+
+
+def test_medianflow_definition_on_a_clean_motion():
+    """The median-flow restatement (oracle/klt_oracle.c::psnwo_box_medianflow) recovers a pure translation + scale, equals
+    numpy's medians on distinct values and keeps at least half of the points."""
+    from oracle import psnw_oracle as po
+    po.build()
+    rng = np.random.default_rng(3)
+    pre = rng.uniform(50, 300, size=(101, 2)).astype(np.float64)
+    c, s, t = pre.mean(axis=0), 1.0625, np.array([3.5, -2.25])
+    cur = (pre - c) * s + c + t
+    pre32, cur32 = pre.astype(np.float32), cur.astype(np.float32)
+    box = np.array([100.0, 80.0, 40.0, 90.0])
+    out, mask = po.box_medianflow(box, pre32, cur32)
+    d = cur32.astype(np.float64) - pre32.astype(np.float64)
+    assert out[2] == box[2] * (out[2] / box[2]) and abs(out[2] / box[2] - s) < 1e-4 and abs(out[3] / box[3] - s) < 1e-4
+    mdx, mdy = np.median(d[:, 0]), np.median(d[:, 1])
+    sc = out[2] / box[2]
+    assert abs(out[0] - (box[0] + mdx - 0.5 * (sc - 1) * box[2])) < 1e-9 and abs(out[1] - (box[1] + mdy - 0.5 * (sc - 1) * box[3])) < 1e-9
+    assert mask.sum() >= 51
+    out0, mask0 = po.box_medianflow(box, pre32, cur32, np.zeros(101, np.uint8))
+    assert np.array_equal(out0, box) and mask0.sum() == 0

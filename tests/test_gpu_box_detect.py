@@ -208,3 +208,43 @@ def test_points_in_boxes(ctx):
         for t in range(nt):
             want[d, t] = inside[off[t]:off[t + 1]].sum()
     assert np.array_equal(got, want)
+
+
+def _medianflow_case(rng, n, n_valid_frac=1.0, dup=False, quant=False):
+    pre = rng.uniform(20, 400, size=(n, 2)).astype(np.float32)
+    s, t = rng.uniform(0.9, 1.1), rng.uniform(-6, 6, size=2)
+    c = pre.mean(axis=0) if n else np.zeros(2)
+    cur = ((pre - c) * s + c + t + rng.normal(0, 0.3, size=(n, 2))).astype(np.float32)
+    if n:
+        out = rng.random(n) < 0.15                                   # gross outliers
+        cur[out] += rng.uniform(-40, 40, size=(int(out.sum()), 2)).astype(np.float32)
+    if dup and n > 3:
+        pre[1] = pre[0]; pre[3] = pre[2]                             # coincident source points: pairs without a ratio
+    if quant:
+        pre, cur = np.round(pre), np.round(cur)                      # many equal displacements and ratios: ties
+    st = (rng.random(n) < n_valid_frac).astype(np.uint8)
+    return pre.astype(np.float32), cur.astype(np.float32), st
+
+
+def test_medianflow_estimator_equals_oracle(oracle):
+    """PSNW_BOX_MEDIANFLOW (north_star's median-displacement / scale reduction; not the reference's estimator): the CUDA
+    kernel against its C definition, bit for bit -- odd and even counts, empty and single-point targets, more than 128
+    points (strided pair subset), the 4096-point capacity, a status filter, coincident points, ties."""
+    rng = np.random.default_rng(21)
+    sizes = [0, 1, 2, 3, 4, 7, 50, 100, 128, 129, 257, 1000, 4096]
+    cases = []
+    for k, n in enumerate(sizes):
+        cases.append(_medianflow_case(rng, n, n_valid_frac=1.0 if k % 3 else 0.7, dup=(k % 4 == 1), quant=(k % 5 == 2)))
+    cases.append(_medianflow_case(rng, 60, n_valid_frac=0.0))         # no valid point at all
+    boxes = np.stack([np.array([rng.uniform(0, 300), rng.uniform(0, 300), rng.uniform(20, 80), rng.uniform(40, 160)]) for _ in cases])
+    pre = np.concatenate([c[0] for c in cases]); cur = np.concatenate([c[1] for c in cases]); st = np.concatenate([c[2] for c in cases])
+    off = np.concatenate([[0], np.cumsum([len(c[0]) for c in cases])]).astype(np.int32)
+    with klt.KLTContext(64, 64, levels=2, max_points=1 << 14, max_targets=64) as ctx:
+        for status in (st, None):
+            got_b, got_m, got_c = ctx.box_update(boxes, pre, cur, off, status=status, mode=klt.BOX_MEDIANFLOW)
+            for t, c in enumerate(cases):
+                a, b = off[t], off[t + 1]
+                want_b, want_m = oracle.box_medianflow(boxes[t], c[0], c[1], None if status is None else c[2])
+                assert np.array_equal(got_b[t], want_b), (t, len(c[0]), got_b[t], want_b)
+                assert np.array_equal(got_m[a:b], want_m), (t, len(c[0]))
+                assert got_c[t] == int(want_m.sum())
