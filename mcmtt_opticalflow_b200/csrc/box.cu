@@ -54,6 +54,7 @@ box_update_kernel(const double *__restrict__ boxes_in, const float2 *__restrict_
     __shared__ Best s_bx[kBoxThreads / 32], s_by[kBoxThreads / 32];
 
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // (launched with programmatic stream serialisation)
     const int beg = offsets[t], end = offsets[t + 1];
     const int n_all = min(max(end - beg, 0), cap);
     double *mvx = reinterpret_cast<double *>(box_smem);
@@ -537,8 +538,18 @@ int launch_box_update(const double *boxes_in, int n_targets, const float2 *pre, 
         return cudaGetLastError() == cudaSuccess ? 1 : -1;
     }
     const size_t smem = (size_t)cap * 20 + 16;
-    box_update_kernel<<<n_targets, kBoxThreads, smem, stream>>>(boxes_in, pre, cur, status, offsets, boxes_out, mask, counts, cap);
-    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+    // programmatic dependent launch: set up under the tail of the LK launch whose points it reads (the kernel waits first)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_targets);
+    cfg.blockDim = dim3(kBoxThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, box_update_kernel, boxes_in, pre, cur, status, offsets, boxes_out, mask, counts, cap) == cudaSuccess ? 1 : -1;
 }
 
 }  // namespace psnw

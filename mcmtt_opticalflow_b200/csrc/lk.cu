@@ -870,6 +870,7 @@ lk_w21_kernel(const __grid_constant__ LkParams P)
     S.pend_src = S.pend_tgt = false;
     if (lane == 0) { mbar_init(S.bar_src, 1); mbar_init(S.bar_tgt, 1); }
     __syncwarp();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // (launched with programmatic stream serialisation, launch_lk)
 
     // Work items: point i < split_from is one item (forward + backward pass); the points of the tail are two items each --
     // forward passes first, [split_from, n_pts), then their backward passes, [n_pts, n_pts + n_tail) -- so that the last
@@ -979,8 +980,19 @@ int launch_lk(const LkParams &P, int all_21x21, int max_win_px, int resident_cta
     if (all_21x21) {
         int grid = (P.n_pts + kWarpsPerCta - 1) / kWarpsPerCta;
         if (P.work) grid = min(grid, max(resident_ctas, 1));
-        if (P.stats) lk_w21_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(P);
-        else         lk_w21_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(P);
+        // programmatic dependent launch: the grid is set up (and its prologue runs) under the tail of the kernel before it in
+        // the stream; the kernel waits for that kernel's completion before its first global access
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kWarpsPerCta * 32);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = P.stats ? cudaLaunchKernelEx(&cfg, lk_w21_kernel<true>, P) : cudaLaunchKernelEx(&cfg, lk_w21_kernel<false>, P);
+        return e == cudaSuccess ? 1 : -1;
     } else {
         const int stride = (max_win_px + 7) & ~7;
         const size_t smem = (size_t)stride * 6;
