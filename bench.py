@@ -538,6 +538,11 @@ def pyramid_modes(rig, w, h, levels, frames, isolated_reps=10, stream_launches=4
         for i in range(slots):
             ctx.rebuild_pyramids(cams, slot=i % slots)
         (a, b), = _events(torch, 1)
+        # the launches are enqueued while the stream is still busy with a few L2-flush memsets (~60 us each), so that they
+        # run back to back at the device's pace whatever the host's enqueue rate is (16 host threads may still be spinning
+        # after the CPU arm); the start event is recorded behind the memsets
+        for _ in range(16):
+            rig.flush.zero_()
         a.record(rig.stream)
         for i in range(n):
             ctx.rebuild_pyramids(cams, slot=i % slots)
@@ -897,7 +902,9 @@ def main():
                 "traffic": prof["traffic_bytes_per_group"] if prof else None, "traffic_source": prof.get("source") if prof else
                 "no committed ncu capture of the current pyramid sources", "algorithmic_bytes": alg, "ms": 1e3 * strm_s, "peak_source": peak_src,
                 "timing": "average launch-group duration inside a stream of %d back-to-back launches walking a ring of %d slots (%.0f MB touched "
-                          "between two visits of a slot: inputs larger than L2, no flush), one pair of CUDA events around the stream"
+                          "between two visits of a slot: inputs larger than L2, no flush), one pair of CUDA events around the stream, the launches "
+                          "enqueued behind 16 L2-flush memsets so that the host's enqueue rate does not enter; consecutive builds of other ring "
+                          "slots overlap (late_wait, DESIGN.md K1)"
                           % (max(48, 2 * main_modes["ring_slots"]), main_modes["ring_slots"], main_modes["working_set_bytes"] / 1e6),
                 "isolated": {"ms": 1e3 * iso_s, "achieved": alg / iso_s / 1e9, "frac": alg / iso_s / 1e9 / peak,
                              "event_floor_ms": 1e3 * floor,
