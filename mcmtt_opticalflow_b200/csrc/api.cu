@@ -326,7 +326,7 @@ cudaMemcpyKind h2d(int mem_flags) { return mem_flags == PSNW_MEM_DEVICE ? cudaMe
 // SM its two CTAs for a few rounds -- the halo rows every CTA recomputes weigh less the taller its region -- but never one
 // that leaves SMs without work.  *threads: 512 per CTA (two CTAs per SM) from level 0, 256 (four per SM) for the smaller
 // regions of the coarse-level launch of the hybrid builder.
-int fused_variant_for(const psnw_ctx *ctx, int base, int nl, int n, int *threads)
+int fused_variant_for(const psnw_ctx *ctx, int base, int nl, int n, int *threads, bool chained = false)
 {
     const LevelGeom &g = ctx->pyr.lv[base];
     int variant = 0;
@@ -335,9 +335,13 @@ int fused_variant_for(const psnw_ctx *ctx, int base, int nl, int n, int *threads
         fused_geometry(nl, v, &bw, &bh, &ow, &oh);
         const size_t ctas = (size_t)((g.w + ow - 1) / ow) * ((g.h + oh - 1) / oh) * n;
         if (ctas >= (size_t)ctx->sm_count * 6) variant = v;
+        // a build that runs beside its predecessor (late_wait) is one of a stream of builds: throughput counts, not the latency
+        // of this launch -- half as many CTAs of twice the height recompute fewer halo rows (4 x 768x576 in-stream: 4.8 us
+        // against 5.5; alone 16.8 us against 14.7)
+        if (chained && v == 1 && ctas >= (size_t)ctx->sm_count / 2) variant = v;
     }
     if (ctx->fused_variant >= 0) variant = ctx->fused_variant;
-    *threads = base > 0 ? 256 : 512;
+    *threads = (base > 0 || (chained && variant >= 1)) ? 256 : 512;
     if (ctx->fused_wide >= 0) *threads = ctx->fused_wide;
     return variant;
 }
@@ -390,7 +394,7 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
         bool ends_fused = false;
         if (mode == 2) {
             int wide = 0;
-            const int variant = fused_variant_for(ctx, 0, ctx->fused_levels, pl.n, &wide);
+            const int variant = fused_variant_for(ctx, 0, ctx->fused_levels, pl.n, &wide, late);
             // deeper pyramids: level 3 again (per-level kernel) only to feed level 4; it rewrites its apron with the same values
             first = ctx->fused_levels < ctx->pyr.levels ? ctx->fused_levels - 1 : ctx->pyr.levels;
             const int r = launch_pyr_fused(ctx->pyr, 0, ctx->fused_levels, variant, wide, &ctx->map_fused[variant], pl, late ? 1 : 0, st);

@@ -177,7 +177,7 @@ def test_consecutive_builds_of_other_planes_overlap(oracle, monkeypatch):
     """Back-to-back fused builds of disjoint ring slots start without waiting for each other (late_wait) and complete in
     stream order; a build that revisits planes of the chain waits first.  Results are those of the serial order."""
     monkeypatch.setenv("PSNW_PYR_MODE", "fused")
-    w, h, ncam, slots = 320, 240, 3, 4
+    w, h, ncam, slots = 768, 576, 4, 4        # (large enough for the taller 256-thread regions chained builds switch to)
     rng = np.random.default_rng(5)
     frames = [rng.integers(0, 256, size=(ncam, h, w), dtype=np.uint8) for _ in range(slots)]
     with klt.KLTContext(w, h, n_cameras=ncam, levels=4, ring_slots=slots) as ctx:
