@@ -364,6 +364,14 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
         // (measured, tools/pyr_sweep.py: 4 x 768x576 fused 14.0 us / level 15.9; 64 x 768x576 hybrid 56 us / level 64 / fused
         // 62; 32 x 1080p level 93 us / hybrid 99; 16 x 4K level 163 us / hybrid 173)
         if (mode == 0) mode = (ctx->fused_levels && px <= ctx->fused_max_px) ? 2 : (ctx->hyb_levels && (size_t)l0.w * l0.h <= ctx->hybrid_max_frame_px) ? 3 : 1;
+        // one of a stream of builds (it may run beside its predecessor, below): the single fused launch overlaps better than the
+        // hybrid's dependent pair (16 x 768x576 in-stream 17.7 us against 19.2, 64 x 57.9 against 58.7; alone it is the slower one)
+        if (ctx->pyr_mode == 0 && mode == 3 && ctx->fused_levels == ctx->pyr.levels && ctx->pyr_overlap && ctx->launches == ctx->pyr_chain_launches &&
+            st == ctx->pyr_chain_stream && ctx->pyr_chain_planes.size() == (size_t)ctx->planes) {
+            bool disjoint = true;
+            for (int i = 0; disjoint && i < pl.n; ++i) disjoint = !ctx->pyr_chain_planes[pl.plane[i]];
+            if (disjoint) mode = 2;
+        }
         if (mode == 4) {
             // the finest `walk_base` levels by the per-level kernel (no apron CTAs: the walker scatters the apron of every
             // level it reads), the rest by the walker
