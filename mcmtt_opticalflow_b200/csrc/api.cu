@@ -394,7 +394,7 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
         // own planes.  Straight after a build of OTHER planes on the same stream whose last launch was the fused kernel (which
         // releases its dependents only after its own wait), the first launch of this build need not wait for it (late_wait):
         // consecutive builds overlap.  pyr_chain_planes = planes built since the last build that waited first.
-        bool late = (mode == 2 || mode == 3) && ctx->pyr_overlap && ctx->launches == ctx->pyr_chain_launches && st == ctx->pyr_chain_stream;
+        bool late = (mode >= 1 && mode <= 3) && ctx->pyr_overlap && ctx->launches == ctx->pyr_chain_launches && st == ctx->pyr_chain_stream;
         if (ctx->pyr_chain_planes.size() != (size_t)ctx->planes) ctx->pyr_chain_planes.assign(ctx->planes, 0);
         for (int i = 0; late && i < pl.n; ++i) late = !ctx->pyr_chain_planes[pl.plane[i]];
         if (!late) std::fill(ctx->pyr_chain_planes.begin(), ctx->pyr_chain_planes.end(), 0);
@@ -414,9 +414,12 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
             last = ctx->hyb_base;
         }
         for (int l = first; l < last; ++l) {
-            const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, 1, (late && l == 0) ? 1 : 0, st);
+            // (the last launch of a per-level build waits before it releases its dependents, like the fused kernel)
+            const bool closes = mode == 1 && l + 1 == last && l > 0;
+            const int r = launch_pyr_level(ctx->pyr, l, &ctx->maps[l], pl, 1, (late && l == 0) ? 1 : closes ? 2 : 0, st);
             if (r < 0) return fail(ctx, PSNW_ECUDA, "pyr_scharr_kernel launch", cudaGetLastError());
             ctx->launches += r;
+            if (closes) ends_fused = true;
         }
         if (mode == 3) {
             int wide = 0;

@@ -93,7 +93,7 @@ int configure_detect_kernels();
 
 // --- launchers (each returns the number of kernels it enqueued, or -1 with cudaGetLastError set) ---
 // with_apron: the launch also writes the REFLECT_101 apron of its input level (levels >= 1) with extra CTAs
-int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron, int late_wait,
+int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron, int pdl_mode,
                      cudaStream_t stream);
 // fused multi-level variant (pyramid_fused.cu): levels 0..nl-1 AND their aprons in one launch.  Three region heights
 // (variant 0 / 1 / 2); fused_geometry = TMA box of the variant's level-0 map and the level-0 region one CTA owns

@@ -214,13 +214,20 @@ __device__ __forceinline__ void tile_body(uint32_t *tile, const LevelGeom &cur, 
 template <bool kHasNext>
 __global__ void __launch_bounds__(128)
 pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, const LevelGeom nxt,
-                  const PlaneList planes, const int tiles_y, const int late_wait)
+                  const PlaneList planes, const int tiles_y, const int pdl_mode)
 {
+    // pdl_mode 0: release the dependents at once, wait before the first read (the next level's launch is set up meanwhile)
+    //          1: late_wait -- level 0 of planes that no kernel before it in the stream touches (see launch_pyr_fused): the
+    //             launch runs beside its predecessors and only completes after them
+    //          2: wait first, THEN release the dependents -- the last launch of a build, so that a late_wait launch of the
+    //             next build never runs beside anything older than this launch's wait
+    const bool late_wait = pdl_mode == 1;
     if ((int)blockIdx.y >= tiles_y) {
         // extra CTAs of a level >= 1: the REFLECT_101 apron of this (input) level, complete since the previous launch
         // (never launched with late_wait: level 0 has no apron)
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (pdl_mode != 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         const int region = ((int)blockIdx.y - tiles_y) * (int)gridDim.x + (int)blockIdx.x;
         if (region < apron_regions(cur.h, cur.apron, 128)) apron_region(cur, planes.plane[blockIdx.z], region, threadIdx.x, 128);
         return;
@@ -236,12 +243,11 @@ pyr_scharr_kernel(const __grid_constant__ CUtensorMap map, const LevelGeom cur, 
 #ifndef PSNW_DEBUG_NO_TMA
     // Programmatic dependent launch: let the next level's grid start its prologue now, and wait for the previous
     // level's grid (which wrote this level's u8 image) to complete before the first read.
-    // late_wait (level 0 of planes that no kernel before it in the stream touches; see launch_pyr_fused): the launch runs
-    // beside its predecessors and only completes after them
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (pdl_mode != 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) mbar_init(bar_a, 1);
     __syncthreads();
     if (!late_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (pdl_mode == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         mbar_expect_tx(bar_a, kBoxW * kBoxH);
         tma_load_3d(smem_u32(tile), &map, x0 - kHaloL, y0 - kHaloT, plane, bar_a);
@@ -460,7 +466,7 @@ bgr2gray_kernel(const uint8_t *__restrict__ bgr, size_t bgr_pitch, uint8_t *__re
 
 }  // namespace
 
-int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron, int late_wait,
+int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, const PlaneList &planes, int with_apron, int pdl_mode,
                      cudaStream_t stream)
 {
     const LevelGeom &cur = pyr.lv[level];
@@ -478,8 +484,8 @@ int launch_pyr_level(const PyrDesc &pyr, int level, const CUtensorMap *map_in, c
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = has_next ? cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<true>, *map_in, cur, nxt, planes, tiles_y, late_wait)
-                                   : cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<false>, *map_in, cur, nxt, planes, tiles_y, late_wait);
+    const cudaError_t e = has_next ? cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<true>, *map_in, cur, nxt, planes, tiles_y, pdl_mode)
+                                   : cudaLaunchKernelEx(&cfg, pyr_scharr_kernel<false>, *map_in, cur, nxt, planes, tiles_y, pdl_mode);
     return e == cudaSuccess ? 1 : -1;
 }
 
