@@ -58,7 +58,7 @@ struct psnw_ctx {
     CUtensorMap *lk_maps = nullptr;       // device copy of the LK kernel's patch maps: 3 per level (LkParams::tmaps)
     int fused_levels = 0;                 // 3 or 4 when the fused kernel is usable, else 0
     size_t fused_max_px = 2200000;   // auto mode: fused kernel up to this many level-0 pixels per launch
-    size_t hybrid_max_frame_px = 600000;   // auto mode: larger launches of frames up to this size take the hybrid builder
+    size_t fused_chained_max_px = 10000000;   // auto mode: a build that runs beside its predecessor takes the fused kernel up to this size
     int pyr_mode = 0;                     // 0 auto, 1 per-level kernels only, 2 fused from level 0, 3 hybrid, 4 level walker (PSNW_PYR_MODE, bring-up)
     static constexpr int kWalkBlocks = 8; // control blocks of the level walker, used in turn (each launch leaves its block zeroed)
     unsigned *walk_ctl = nullptr;
@@ -356,18 +356,21 @@ int build_pyramids(psnw_ctx *ctx, const std::vector<int> &planes, cudaStream_t s
         //   fused   levels 0..3 AND their aprons in ONE launch of independent CTAs: a rig frame of a few small cameras, where
         //           one launch per level would be pure latency;
         //   hybrid  the per-level kernel for the finest level(s) (no halo recomputed where the pixels are), then ONE fused
-        //           launch for the remaining 3-4 levels and every apron: large batches and large frames;
-        //   level   one launch per level (each writes the apron of its input level with extra CTAs).
+        //           launch for the remaining 3-4 levels and every apron (PSNW_PYR_MODE=hybrid only);
+        //   level   one launch per level (each writes the apron of its input level with extra CTAs): everything larger.
         const LevelGeom &l0 = ctx->pyr.lv[0];
         const size_t px = (size_t)l0.w * l0.h * pl.n;
         int mode = ctx->pyr_mode;                                    // 1 level, 2 fused, 3 hybrid
-        // (measured, tools/pyr_sweep.py: 4 x 768x576 fused 14.0 us / level 15.9; 64 x 768x576 hybrid 56 us / level 64 / fused
-        // 62; 32 x 1080p level 93 us / hybrid 99; 16 x 4K level 163 us / hybrid 173)
-        if (mode == 0) mode = (ctx->fused_levels && px <= ctx->fused_max_px) ? 2 : (ctx->hyb_levels && (size_t)l0.w * l0.h <= ctx->hybrid_max_frame_px) ? 3 : 1;
+        // (measured, tools/pyr_sweep.py: 4 x 768x576 fused 14.0 us / level 15.9; 32 x 1080p level 93 us / hybrid 99; 16 x 4K
+        // level 163 us / hybrid 173)
+        // round 2, final kernels (tools/pyr_sweep.py, isolated): 16 / 32 / 64 / 128 x 768x576 level 24.1 / 34.7 / 57.2 / 98.2 us against
+        // hybrid 25.5 / 37.5 / 60.3 / 107.4; 8 x 1080p 34.7 against 39.7 -- the hybrid builder is no longer chosen by itself
+        if (mode == 0) mode = (ctx->fused_levels && px <= ctx->fused_max_px) ? 2 : 1;
         // one of a stream of builds (it may run beside its predecessor, below): the single fused launch overlaps better than the
         // hybrid's dependent pair (16 x 768x576 in-stream 17.7 us against 19.2, 64 x 57.9 against 58.7; alone it is the slower one)
-        if (ctx->pyr_mode == 0 && mode == 3 && ctx->fused_levels == ctx->pyr.levels && ctx->pyr_overlap && ctx->launches == ctx->pyr_chain_launches &&
-            st == ctx->pyr_chain_stream && ctx->pyr_chain_planes.size() == (size_t)ctx->planes) {
+        // (in-stream 16 x 768x576: fused 17.3 us, level 19.8; 64 x: level 54.2, fused 56.0)
+        if (ctx->pyr_mode == 0 && mode == 1 && px <= ctx->fused_chained_max_px && ctx->fused_levels == ctx->pyr.levels && ctx->pyr_overlap &&
+            ctx->launches == ctx->pyr_chain_launches && st == ctx->pyr_chain_stream && ctx->pyr_chain_planes.size() == (size_t)ctx->planes) {
             bool disjoint = true;
             for (int i = 0; disjoint && i < pl.n; ++i) disjoint = !ctx->pyr_chain_planes[pl.plane[i]];
             if (disjoint) mode = 2;
