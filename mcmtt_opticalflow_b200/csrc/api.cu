@@ -778,14 +778,24 @@ int psnw_push_frames(psnw_ctx *ctx, int n, const int *cams, const uint8_t *const
     if (one_copy) {
         sstride = grays[1] - grays[0];
         dstride = ((ptrdiff_t)planes[1] - planes[0]) * l0.plane_px;
-        one_copy = sstride >= (ptrdiff_t)l0.plane_px && dstride >= (ptrdiff_t)l0.plane_px;
+        // (a 2-D copy takes pitches up to cudaDevAttrMaxPitch = 2^31 - 1: frames that merely happen to lie at equal distances in
+        // separate, far-apart allocations -- any two frames do -- keep one copy each)
+        constexpr ptrdiff_t kMaxCopyPitch = 0x7fffffff;
+        one_copy = sstride >= (ptrdiff_t)l0.plane_px && dstride >= (ptrdiff_t)l0.plane_px && sstride <= kMaxCopyPitch && dstride <= kMaxCopyPitch;
         for (int i = 2; one_copy && i < n; ++i)
             one_copy = (grays[i] - grays[i - 1]) == sstride && ((ptrdiff_t)planes[i] - planes[i - 1]) * l0.plane_px == dstride;
     }
     if (one_copy) {
-        CK(cudaMemcpy2DAsync(l0.img + (size_t)planes[0] * l0.plane_px, (size_t)dstride, grays[0], (size_t)sstride,
-                             (size_t)l0.plane_px, n, h2d(mem_flags), st));
-    } else {
+        // Frames at equal distances are usually slices of one block -- but any two frames are "at equal distances", and a copy
+        // whose source rows lie in DIFFERENT host allocations is refused by the runtime (invalid argument, nothing enqueued):
+        // those take one copy each like everything else.
+        if (cudaMemcpy2DAsync(l0.img + (size_t)planes[0] * l0.plane_px, (size_t)dstride, grays[0], (size_t)sstride, (size_t)l0.plane_px, n,
+                              h2d(mem_flags), st) != cudaSuccess) {
+            (void)cudaGetLastError();
+            one_copy = false;
+        }
+    }
+    if (!one_copy) {
         for (int i = 0; i < n; ++i)
             CK(cudaMemcpy2DAsync(l0.img + (size_t)planes[i] * l0.plane_px, l0.pitch, grays[i], pitch, l0.w, l0.h,
                                  h2d(mem_flags), st));

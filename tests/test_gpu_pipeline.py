@@ -135,3 +135,82 @@ def test_pipelined_bench_steps_are_periodic():
         assert sums[k] == sums[k - period], k
     assert len(set(sums[2 * period:])) == period
     rig.ctx.close()
+
+
+def _fuzz_run(monkeypatch, seed, relaxed, mode, n_cmds=60):
+    """A random sequence of pushes (subsets of cameras, overlapped or not, with or without the eager Shi-Tomasi map),
+    pyramid rebuilds of random slots and LK launches on one context.  relaxed: everything the library may overlap is allowed to
+    (upload stream, consecutive builds beside each other, programmatic launches); strict: no overlap flag, every build waits,
+    a sync after every call.  -> (list of track outputs, every level of every plane at the end)."""
+    import torch
+    monkeypatch.setenv("PSNW_PYR_MODE", mode)
+    monkeypatch.setenv("PSNW_PYR_OVERLAP", "1" if relaxed else "0")
+    dev = torch.device("cuda", 0)
+    w, h, ncam, slots, levels, n = 256, 192, 3, 3, 3, 300
+    rng = np.random.default_rng(seed)
+    pool = [torch.from_numpy(rng.integers(0, 256, size=(h, w), dtype=np.uint8)).pin_memory() for _ in range(8)]
+    # smooth content so that LK has something to track: blur by averaging shifted copies
+    for k, p in enumerate(pool):
+        a = p.numpy().astype(np.float32)
+        for _ in range(3):
+            a = (a + np.roll(a, 1, 0) + np.roll(a, 1, 1) + np.roll(a, -1, 0) + np.roll(a, -1, 1)) / 5.0
+        p.numpy()[:] = np.clip(np.roll(a, k, 1), 0, 255).astype(np.uint8)
+    pts = np.stack([rng.uniform(20, w - 20, n), rng.uniform(20, h - 20, n)], axis=1).astype(np.float32)
+    d_pts = torch.from_numpy(pts).to(dev)
+    held = [0] * ncam
+    outs, res = [], []
+    with klt.KLTContext(w, h, n_cameras=ncam, levels=levels, ring_slots=slots, fb_thresh=1.0, max_points=1024) as ctx:
+        for c in range(ncam):                                   # every camera starts with two frames
+            for k in range(2):
+                ctx.push_frames([pool[(c + k) % 8].data_ptr()], [c], k, klt.MEM_PINNED, pitch=w)
+            held[c] = 2
+        ctx.sync()
+        for step in range(n_cmds):
+            op = int(rng.integers(0, 3))
+            if op == 0:                                         # push a subset of cameras
+                cams = sorted(rng.choice(ncam, size=int(rng.integers(1, ncam + 1)), replace=False).tolist())
+                flags = klt.MEM_PINNED
+                ov = rng.random() < 0.7                          # (drawn in both runs: the sequences must stay identical)
+                if relaxed and ov:
+                    flags |= klt.MEM_OVERLAP
+                if rng.random() < 0.3:
+                    flags |= klt.PUSH_EIG
+                ctx.push_frames([pool[int(rng.integers(0, 8))].data_ptr() for _ in cams], cams, step, flags, pitch=w)
+                for c in cams:
+                    held[c] = min(held[c] + 1, slots)
+            elif op == 1:                                       # rebuild some slot of some cameras
+                cams = sorted(rng.choice(ncam, size=int(rng.integers(1, ncam + 1)), replace=False).tolist())
+                slot = int(rng.integers(0, min(held[c] for c in cams)))
+                ctx.rebuild_pyramids(np.array(cams, np.int32), slot=slot)
+            else:                                               # LK between two slots of one camera
+                c = int(rng.integers(0, ncam))
+                a, b = rng.choice(held[c], size=2, replace=False).tolist()
+                o = dict(out=torch.zeros((n, 2), dtype=torch.float32, device=dev), status=torch.zeros(n, dtype=torch.uint8, device=dev),
+                         err=torch.zeros(n, dtype=torch.float32, device=dev), fb=torch.zeros(n, dtype=torch.float32, device=dev))
+                outs.append(o)
+                ctx.track_batch([dict(cam=c, slot_from=int(a), slot_to=int(b), n_pts=n, pts=d_pts.data_ptr(), out=o["out"].data_ptr(),
+                                      status=o["status"].data_ptr(), err=o["err"].data_ptr(), fb_err=o["fb"].data_ptr())], mem=klt.MEM_DEVICE)
+            if not relaxed:
+                ctx.sync()
+        ctx.sync()
+        for o in outs:
+            res.append(tuple(o[key].cpu().numpy() for key in ("out", "status", "err", "fb")))
+        planes = [[ctx.read_level(c, s, l) for l in range(levels)] for c in range(ncam) for s in range(held[c])]
+    return res, planes
+
+
+@pytest.mark.parametrize("mode", ["auto", "level", "hybrid"])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_command_sequences_equal_the_serialised_run(monkeypatch, seed, mode):
+    """Stream-ordering fuzz: overlapped pushes, consecutive builds running beside each other (late_wait), programmatically
+    launched LK kernels and rebuilds in random order give bit-identical tracks and pyramids to the same sequence run without
+    any overlap and with a host sync after every call."""
+    strict_tracks, strict_planes = _fuzz_run(monkeypatch, seed, False, mode)
+    relaxed_tracks, relaxed_planes = _fuzz_run(monkeypatch, seed, True, mode)
+    assert len(strict_tracks) == len(relaxed_tracks) > 5
+    for k, (a, b) in enumerate(zip(strict_tracks, relaxed_tracks)):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), ("track", k)
+    for k, (pa, pb) in enumerate(zip(strict_planes, relaxed_planes)):
+        for l, ((ia, da), (ib, db)) in enumerate(zip(pa, pb)):
+            assert np.array_equal(ia, ib) and np.array_equal(da, db), ("plane", k, "level", l)

@@ -194,3 +194,18 @@ def test_consecutive_builds_of_other_planes_overlap(oracle, monkeypatch):
         for s in range(slots):
             for c in range(ncam):
                 _check_levels(ctx, oracle, frames[slots - 1 - s][c], cam=c, slot=s)
+
+
+def test_frames_in_separate_pinned_allocations(oracle):
+    """Two frames are always 'at equal distances' in memory; when they live in different page-locked allocations the single
+    strided copy is refused by the runtime and every frame takes its own copy (found by the stream-ordering fuzz test)."""
+    import torch
+    w, h = 256, 192                                            # w == pitch: the single-copy path is considered
+    rng = np.random.default_rng(17)
+    bufs = [torch.from_numpy(rng.integers(0, 256, size=(h, w), dtype=np.uint8)).pin_memory() for _ in range(6)]
+    with klt.KLTContext(w, h, n_cameras=3, levels=3) as ctx:
+        for order in ([0, 3, 5], [5, 1, 2], [4, 4, 0]):        # ascending, mixed, the same source frame for two cameras
+            ctx.push_frames([bufs[i].data_ptr() for i in order], [0, 1, 2], 0, klt.MEM_PINNED, pitch=w)
+            ctx.sync()
+            for c, i in enumerate(order):
+                _check_levels(ctx, oracle, bufs[i].numpy(), cam=c, slot=0)
