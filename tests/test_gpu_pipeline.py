@@ -139,7 +139,7 @@ def test_pipelined_bench_steps_are_periodic():
 
 def _fuzz_run(monkeypatch, seed, relaxed, mode, n_cmds=60):
     """A random sequence of pushes (subsets of cameras, overlapped or not, with or without the eager Shi-Tomasi map),
-    pyramid rebuilds of random slots and LK launches on one context.  relaxed: everything the library may overlap is allowed to
+    pyramid rebuilds of random slots, Shi-Tomasi detections (on the auxiliary stream or not) and LK launches on one context.  relaxed: everything the library may overlap is allowed to
     (upload stream, consecutive builds beside each other, programmatic launches); strict: no overlap flag, every build waits,
     a sync after every call.  -> (list of track outputs, every level of every plane at the end)."""
     import torch
@@ -158,7 +158,7 @@ def _fuzz_run(monkeypatch, seed, relaxed, mode, n_cmds=60):
     pts = np.stack([rng.uniform(20, w - 20, n), rng.uniform(20, h - 20, n)], axis=1).astype(np.float32)
     d_pts = torch.from_numpy(pts).to(dev)
     held = [0] * ncam
-    outs, res = [], []
+    outs, res, dets = [], [], []
     with klt.KLTContext(w, h, n_cameras=ncam, levels=levels, ring_slots=slots, fb_thresh=1.0, max_points=1024) as ctx:
         for c in range(ncam):                                   # every camera starts with two frames
             for k in range(2):
@@ -166,8 +166,19 @@ def _fuzz_run(monkeypatch, seed, relaxed, mode, n_cmds=60):
             held[c] = 2
         ctx.sync()
         for step in range(n_cmds):
-            op = int(rng.integers(0, 3))
-            if op == 0:                                         # push a subset of cameras
+            op = int(rng.integers(0, 4))
+            if op == 3:                                         # Shi-Tomasi detection in a few boxes of one camera's slot
+                c = int(rng.integers(0, ncam))
+                slot = int(rng.integers(0, held[c]))
+                nb, per = 4, 40
+                bx = np.stack([rng.uniform(0, w - 80, nb), rng.uniform(0, h - 80, nb), rng.uniform(30, 80, nb), rng.uniform(30, 80, nb)], axis=1)
+                ov = rng.random() < 0.6
+                d = dict(pts=torch.zeros((nb, per, 2), dtype=torch.float32, device=dev), cnt=torch.zeros(nb, dtype=torch.int32, device=dev),
+                         boxes=np.ascontiguousarray(bx, np.float64))
+                dets.append(d)
+                ctx._ck(ctx.lib.psnw_klt_detect(ctx._h, c, slot, d["boxes"].ctypes.data, nb, per, 0.01, 3.0, d["pts"].data_ptr(), d["cnt"].data_ptr(),
+                                                klt.MEM_DEVICE | (klt.MEM_OVERLAP if (relaxed and ov) else 0)))
+            elif op == 0:                                       # push a subset of cameras
                 cams = sorted(rng.choice(ncam, size=int(rng.integers(1, ncam + 1)), replace=False).tolist())
                 flags = klt.MEM_PINNED
                 ov = rng.random() < 0.7                          # (drawn in both runs: the sequences must stay identical)
@@ -196,6 +207,8 @@ def _fuzz_run(monkeypatch, seed, relaxed, mode, n_cmds=60):
         for o in outs:
             res.append(tuple(o[key].cpu().numpy() for key in ("out", "status", "err", "fb")))
         planes = [[ctx.read_level(c, s, l) for l in range(levels)] for c in range(ncam) for s in range(held[c])]
+        for d in dets:
+            res.append((d["pts"].cpu().numpy(), d["cnt"].cpu().numpy()))
     return res, planes
 
 
