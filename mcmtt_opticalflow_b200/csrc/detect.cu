@@ -201,6 +201,7 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
     __shared__ __align__(16) unsigned s_acc[kMaxAccepted + 4];   // accepted corners (x | y << 16), padded with far-away sentinels
     __shared__ int s_nc, s_nout;
     __shared__ __align__(16) unsigned s_near[32];                // chunk-local "too close to an earlier lane" masks of the walk
+    __shared__ unsigned s_alive[kSelThreads / 32];               // per-warp survivor masks of the chunk
     __shared__ __align__(16) unsigned long long s_top[kSelThreads];   // the strongest <= 512 candidates of a long list (radix select)
     __shared__ int s_hist[kHistBins];
     __shared__ int s_sel[4];                                      // {lowest kept bin, kept count above the bin, compaction cursor, -}
@@ -453,62 +454,77 @@ detect_select_kernel(int w, int h, int pitch, const DetectTarget *__restrict__ t
                 }
             }
         __syncthreads();
-        if (warp == 0) {
-            // One warp walks the sorted list 32 candidates at a time.  (a) drop candidates closer than min_dist to a
-            // corner accepted in an earlier chunk (4 accepted corners per shared-memory load); (b) every lane builds
-            // the bit mask of EARLIER lanes of the chunk that are too close; (c) the in-order greedy rule becomes a
-            // 32-step bit recurrence that all lanes evaluate identically: lane j is accepted iff it survived (a) and
-            // none of its close predecessors was accepted.
+        {
+            // The CTA walks the sorted list 32 candidates at a time.  (a) drop candidates closer than min_dist to a corner
+            // accepted in an earlier chunk: every warp tests the chunk against ITS slice of the accepted list (4 corners per
+            // shared-memory load) and the survivor masks are AND-ed -- the list grows to max_per_target corners and one warp
+            // walking all of it kept the other 15 (half an SM's registers) at a barrier for 40 % of the kernel at a quota of
+            // 256; (b) meanwhile warp 1 builds, per lane, the bit mask of EARLIER lanes of the chunk that are too close;
+            // (c) warp 0 resolves the chunk: the in-order greedy rule is a 32-step bit recurrence that all lanes evaluate
+            // identically -- lane j is accepted iff it survived (a) and none of its close predecessors was accepted.
             // Coordinates are integers: distances are exact in int32 and d2 < min_dist^2 <=> d2 < ceil(min_dist^2).
             const int md2i = (int)fminf(ceilf(md2), 2.0e9f);
-            for (int base = 0; base < m && n_out < max_per_target; base += 32) {
+            if (tid == 0) s_nout = 0;
+            __syncthreads();
+            int n_acc = 0;
+            for (int base = 0; base < m && n_acc < max_per_target; base += 32) {
                 const unsigned long long key = (base + lane < m) ? LST[base + lane] : 0ull;
                 const unsigned idx = (unsigned)key;
                 const int xi = (int)(idx % (unsigned)w), yi = (int)(idx / (unsigned)w);
                 const unsigned xy = (unsigned)xi | ((unsigned)yi << 16);
                 bool alive = key != 0ull;
-                unsigned near = 0u;
                 if (suppress) {
-                    for (int a = 0; a < n_out; a += 4) {
+                    for (int a = 4 * warp; a < n_acc; a += 4 * nwarps) {
                         const uint4 q = *reinterpret_cast<const uint4 *>(&s_acc[a]);
                         const unsigned qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const int dx = xi - (int)(qq[u] & 0xffffu), dy = yi - (int)(qq[u] >> 16);   // |d| < 32768: no overflow
-                            if (a + u < n_out && dx * dx + dy * dy < md2i) alive = false;
+                            if (a + u < n_acc && dx * dx + dy * dy < md2i) alive = false;
                         }
                     }
+                }
+                if (warp == 1) {
+                    unsigned near = 0u;
+                    if (suppress) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const unsigned q = __shfl_sync(0xffffffffu, xy, i);
-                        const int dx = xi - (int)(q & 0xffffu), dy = yi - (int)(q >> 16);
-                        if (i < lane && dx * dx + dy * dy < md2i) near |= 1u << i;
+                        for (int i = 0; i < 32; ++i) {
+                            const unsigned q = __shfl_sync(0xffffffffu, xy, i);
+                            const int dx = xi - (int)(q & 0xffffu), dy = yi - (int)(q >> 16);
+                            if (i < lane && dx * dx + dy * dy < md2i) near |= 1u << i;
+                        }
                     }
+                    s_near[lane] = near;
                 }
-                const unsigned pre = __ballot_sync(0xffffffffu, alive);
-                s_near[lane] = near;
-                __syncwarp();
-                unsigned acc = 0u;
-                int room = max_per_target - n_out;
+                const unsigned mine = __ballot_sync(0xffffffffu, alive);
+                if (lane == 0) s_alive[warp] = mine;
+                __syncthreads();
+                if (warp == 0) {
+                    unsigned pre = 0xffffffffu;
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const uint4 nq = *reinterpret_cast<const uint4 *>(&s_near[4 * j4]);     // broadcast reads
-                    const unsigned nj4[4] = {nq.x, nq.y, nq.z, nq.w};
+                    for (int i = 0; i < nwarps; ++i) pre &= s_alive[i];
+                    unsigned acc = 0u;
+                    int room = max_per_target - n_acc;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int j = 4 * j4 + u;
-                        if (room > 0 && ((pre >> j) & 1u) && (nj4[u] & acc) == 0u) { acc |= 1u << j; --room; }
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const uint4 nq = *reinterpret_cast<const uint4 *>(&s_near[4 * j4]);     // broadcast reads
+                        const unsigned nj4[4] = {nq.x, nq.y, nq.z, nq.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = 4 * j4 + u;
+                            if (room > 0 && ((pre >> j) & 1u) && (nj4[u] & acc) == 0u) { acc |= 1u << j; --room; }
+                        }
                     }
+                    if ((acc >> lane) & 1u) {
+                        const int slot = n_acc + __popc(acc & ((1u << lane) - 1u));
+                        s_acc[slot] = xy;
+                        my_out[slot] = make_float2((float)xi, (float)yi);
+                    }
+                    if (lane == 0) s_nout = n_acc + __popc(acc);
                 }
-                if ((acc >> lane) & 1u) {
-                    const int slot = n_out + __popc(acc & ((1u << lane) - 1u));
-                    s_acc[slot] = xy;
-                    my_out[slot] = make_float2((float)xi, (float)yi);
-                }
-                n_out += __popc(acc);
-                __syncwarp();
+                __syncthreads();
+                n_acc = s_nout;
             }
-            if (lane == 0) s_nout = n_out;
         }
         __syncthreads();
         n_out = s_nout;
