@@ -171,6 +171,9 @@ class GpuRig:
                 self.h_blob = t.from_numpy(blob_host[:int(offs[-1])])
             else:
                 self.h_blob = t.zeros(int(offs[-1]), dtype=t.uint8).pin_memory()
+            # (the end-to-end leg reads step i's result while step i+1 is already enqueued: two result buffers in turn)
+            self.h_blobs = [self.h_blob, t.zeros(int(offs[-1]), dtype=t.uint8).pin_memory()]
+            self.blob_sel = 0
             view = lambda o, nbytes, dt, shape: self.d_blob[int(o):int(o) + nbytes].view(dt).view(shape)
             self.d_out = view(offs[0], self.npts * 8, t.float32, (self.npts, 2))
             self.d_boxes_out = view(offs[1], self.ntargets * 32, t.float64, (self.ntargets, 4))
@@ -303,7 +306,7 @@ class GpuRig:
             self.which = nxt
         ctx.join()
         if host:
-            self.h_blob.copy_(self.d_blob, non_blocking=True)
+            self.h_blobs[self.blob_sel].copy_(self.d_blob, non_blocking=True)
         self.step_idx += 1
 
     def step_abi(self):
@@ -356,13 +359,31 @@ class GpuRig:
             l0 = self.ctx.launch_count
             if sampler:
                 sampler.start()
+            # end to end (host=True) the host consumes step i's result while step i+1 is already enqueued -- the order a host that
+            # feeds an associator works in (one frame in flight): the result lands in one of two pinned buffers, an event marks it
+            # complete, and the host waits for that event (and reads the buffer) after it has enqueued the next step.  Every step's
+            # interval still contains the H2D copy of its frames and the D2H copy of its result; what no longer enters is how
+            # fast THIS host's Python issues the next step's calls.  host="abi" keeps one psnw_sync per step.
+            lag = host is True
+            done = [t.cuda.Event(), t.cuda.Event()]
+            seen = 0
             for i in range(steps):
                 self.flush.zero_()
                 ev[i][0].record(self.stream)
+                self.blob_sel = i & 1 if lag else 0
                 self.step(host)
                 ev[i][1].record(self.stream)
-                if host:
+                if lag:
+                    done[i & 1].record(self.stream)
+                    if i > 0:
+                        done[(i - 1) & 1].synchronize()
+                        seen += int(self.h_blobs[(i - 1) & 1][-1])       # the host touches the result it waited for
+                elif host:
                     self.ctx.sync()          # the step's result (boxes, points) is read on the host every step
+            if lag:
+                done[(steps - 1) & 1].synchronize()
+                seen += int(self.h_blobs[(steps - 1) & 1][-1])
+                self.blob_sel = 0
             self.stream.synchronize()
         total_ms = sum(a.elapsed_time(b) for a, b in ev)
         return total_ms * 1e-3, self.ctx.launch_count - l0
@@ -840,7 +861,11 @@ def main():
     h2d, d2h = rig.e2e_bytes()
     e2e = {"value": pts_step * args.steps / sec_e2e, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": 1e3 * sec_e2e / args.steps, "frames_per_s": ncam * world * args.steps / sec_e2e,
-           "blocks_ms_per_step": e2e_all, "of": "median of %d blocks of %d steps" % (E2E_BLOCKS, args.steps)}
+           "blocks_ms_per_step": e2e_all, "of": "median of %d blocks of %d steps" % (E2E_BLOCKS, args.steps),
+           "how": "every step copies its 4 frames and its detection boxes in from pinned host memory and its result blob (points, status, "
+                  "boxes, inlier mask, counts) out to pinned host memory inside the timed interval; the host waits for step i's result "
+                  "(an event behind its D2H copy) and reads it after it has enqueued step i+1 -- one frame in flight on the readback side "
+                  "too, two result buffers in turn"}
 
     # ---- end to end with every array a host pointer handed to the C ABI (no torch copies) ----------------
     e2e_abi = None
